@@ -1,0 +1,41 @@
+"""ctypes binding of librlitg.so (C ABI: include/rlitg.h).  Fails loudly when the library is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librlitg.so")
+
+F32, F64 = 0, 1
+Q_SOA, OUT_SOA = 1, 2
+
+
+class RlitgError(RuntimeError):
+    pass
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "librlitg.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` or "
+        "`make -C rl-itg_b200/csrc`. There is no CPU fallback." % LIB_PATH)
+
+lib = C.CDLL(LIB_PATH)
+lib.rlitg_last_error.restype = C.c_char_p
+lib.rlitg_launch_count.restype = C.c_int64
+
+_vp, _i64, _i = C.c_void_p, C.c_int64, C.c_int
+lib.rlitg_fk_jac.argtypes = [_vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]
+lib.rlitg_fk.argtypes = [_vp, _i64, _i, _i, _i, _vp, _vp, _vp]
+lib.rlitg_allfk.argtypes = [_vp, _i64, _i, _i, _i, _vp, _vp]
+lib.rlitg_jacobian.argtypes = [_vp, _i64, _i, _i, _i, _vp, _vp]
+lib.rlitg_fk_jac_host.argtypes = [_vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp]
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise RlitgError("rlitg error %d: %s" % (rc, (lib.rlitg_last_error() or b"").decode()))
+
+
+def launch_count() -> int:
+    return int(lib.rlitg_launch_count())

@@ -1,0 +1,159 @@
+// extern "C" entry points of librlitg.so (include/rlitg.h): argument validation, dtype dispatch, error state.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "rlitg_internal.h"
+
+namespace rlitg {
+
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+int set_error(int code, const char* msg) {
+    g_err = msg ? msg : "";
+    return code;
+}
+int set_cuda_error(const char* where) {
+    cudaError_t e = cudaGetLastError();
+    g_err = std::string(where) + ": " + cudaGetErrorString(e);
+    return RLITG_ERR_CUDA;
+}
+int check_launch(const char* kernel_name) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        g_err = std::string(kernel_name) + " launch failed: " + cudaGetErrorString(e);
+        return RLITG_ERR_CUDA;
+    }
+    return RLITG_OK;
+}
+const char* last_error_cstr() { return g_err.c_str(); }
+
+static int check_common(const void* q, int64_t B, int D, int dtype) {
+    if (B < 0) return set_error(RLITG_ERR_SHAPE, "B must be >= 0");
+    if (D != 7 && D != 8) return set_error(RLITG_ERR_SHAPE, "D must be 7 (arm) or 8 (torso + arm)");
+    if (dtype != RLITG_F32 && dtype != RLITG_F64) return set_error(RLITG_ERR_DTYPE, "dtype must be RLITG_F32 or RLITG_F64");
+    if (B > 0 && q == nullptr) return set_error(RLITG_ERR_NULL, "q is NULL");
+    const size_t es = dtype == RLITG_F32 ? 4 : 8;
+    if (reinterpret_cast<uintptr_t>(q) % es) return set_error(RLITG_ERR_ALIGN, "q is not aligned to its element size");
+    return RLITG_OK;
+}
+
+// ---- pinned / device workspace for the _host entry points ------------------------------------------------
+struct HostPipe {
+    static constexpr int kStreams = 3;
+    std::mutex mu;
+    cudaStream_t st[kStreams] = {};
+    void* dbuf[kStreams] = {};
+    size_t dcap[kStreams] = {};
+    bool init = false;
+    int ensure(size_t bytes_per_slot) {
+        if (!init) {
+            for (int i = 0; i < kStreams; i++)
+                if (cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking) != cudaSuccess)
+                    return set_cuda_error("cudaStreamCreate");
+            init = true;
+        }
+        for (int i = 0; i < kStreams; i++) {
+            if (dcap[i] < bytes_per_slot) {
+                if (dbuf[i]) cudaFree(dbuf[i]);
+                if (cudaMalloc(&dbuf[i], bytes_per_slot) != cudaSuccess) { dcap[i] = 0; return set_cuda_error("cudaMalloc(workspace)"); }
+                dcap[i] = bytes_per_slot;
+            }
+        }
+        return RLITG_OK;
+    }
+};
+static HostPipe g_pipe;
+
+template <typename T>
+static int fk_jac_host_t(const T* q, int64_t B, int D, int flags, T* pos, T* rot, T* quat, T* J) {
+    if (flags & (RLITG_Q_SOA | RLITG_OUT_SOA))
+        return set_error(RLITG_ERR_ARG, "rlitg_fk_jac_host takes array-of-structs buffers ([B,D] in, [B,*] out)");
+    std::lock_guard<std::mutex> lk(g_pipe.mu);
+    // chunk so that copies of one chunk overlap the kernel / copies of its neighbours
+    const int64_t chunk = 1 << 17;
+    const size_t per_cfg = sizeof(T) * (size_t)(D + 3 + 9 + 4 + 6 * D);
+    int rc = g_pipe.ensure(per_cfg * chunk);
+    if (rc) return rc;
+    int slot = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += chunk, slot = (slot + 1) % HostPipe::kStreams) {
+        const int64_t n = (B - b0 < chunk) ? B - b0 : chunk;
+        cudaStream_t st = g_pipe.st[slot];
+        T* dq = static_cast<T*>(g_pipe.dbuf[slot]);
+        T* dpos = dq + chunk * D;
+        T* drot = dpos + chunk * 3;
+        T* dquat = drot + chunk * 9;
+        T* dJ = dquat + chunk * 4;
+        if (cudaMemcpyAsync(dq, q + b0 * D, sizeof(T) * n * D, cudaMemcpyHostToDevice, st) != cudaSuccess)
+            return set_cuda_error("H2D q");
+        rc = launch_fk_jac<T>(dq, n, D, 0, pos ? dpos : nullptr, rot ? drot : nullptr, quat ? dquat : nullptr,
+                              J ? dJ : nullptr, st);
+        if (rc) return rc;
+        cudaError_t e = cudaSuccess;
+        if (pos) e = cudaMemcpyAsync(pos + b0 * 3, dpos, sizeof(T) * n * 3, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && rot) e = cudaMemcpyAsync(rot + b0 * 9, drot, sizeof(T) * n * 9, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && quat) e = cudaMemcpyAsync(quat + b0 * 4, dquat, sizeof(T) * n * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && J) e = cudaMemcpyAsync(J + b0 * 6 * D, dJ, sizeof(T) * n * 6 * D, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return set_cuda_error("D2H outputs");
+    }
+    for (int i = 0; i < HostPipe::kStreams; i++)
+        if (cudaStreamSynchronize(g_pipe.st[i]) != cudaSuccess) return set_cuda_error("cudaStreamSynchronize");
+    return RLITG_OK;
+}
+
+}  // namespace rlitg
+
+using namespace rlitg;
+
+extern "C" {
+
+RLITG_API int rlitg_version(void) { return RLITG_VERSION; }
+RLITG_API const char* rlitg_last_error(void) { return last_error_cstr(); }
+RLITG_API int64_t rlitg_launch_count(void) { return g_launches.load(); }
+
+RLITG_API int rlitg_fk_jac(const void* q, int64_t B, int D, int dtype, int flags, void* pos, void* rot, void* quat, void* J,
+                 void* stream) {
+    int rc = check_common(q, B, D, dtype);
+    if (rc) return rc;
+    if (!pos && !rot && !quat && !J) return set_error(RLITG_ERR_NULL, "all outputs are NULL");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == RLITG_F32)
+        return launch_fk_jac<float>((const float*)q, B, D, flags, (float*)pos, (float*)rot, (float*)quat, (float*)J, st);
+    return launch_fk_jac<double>((const double*)q, B, D, flags, (double*)pos, (double*)rot, (double*)quat, (double*)J, st);
+}
+
+RLITG_API int rlitg_fk(const void* q, int64_t B, int D, int dtype, int flags, void* pos, void* quat, void* stream) {
+    if (!pos || !quat) return set_error(RLITG_ERR_NULL, "pos / quat is NULL");
+    return rlitg_fk_jac(q, B, D, dtype, flags, pos, nullptr, quat, nullptr, stream);
+}
+
+RLITG_API int rlitg_jacobian(const void* q, int64_t B, int D, int dtype, int flags, void* J, void* stream) {
+    if (!J) return set_error(RLITG_ERR_NULL, "J is NULL");
+    return rlitg_fk_jac(q, B, D, dtype, flags, nullptr, nullptr, nullptr, J, stream);
+}
+
+RLITG_API int rlitg_allfk(const void* q, int64_t B, int D, int dtype, int flags, void* out, void* stream) {
+    int rc = check_common(q, B, D, dtype);
+    if (rc) return rc;
+    if (!out) return set_error(RLITG_ERR_NULL, "out is NULL");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == RLITG_F32) return launch_allfk<float>((const float*)q, B, D, flags, (float*)out, st);
+    return launch_allfk<double>((const double*)q, B, D, flags, (double*)out, st);
+}
+
+RLITG_API int rlitg_fk_jac_host(const void* q, int64_t B, int D, int dtype, int flags, void* pos, void* rot, void* quat,
+                      void* J) {
+    int rc = check_common(q, B, D, dtype);
+    if (rc) return rc;
+    if (!pos && !rot && !quat && !J) return set_error(RLITG_ERR_NULL, "all outputs are NULL");
+    if (dtype == RLITG_F32)
+        return fk_jac_host_t<float>((const float*)q, B, D, flags, (float*)pos, (float*)rot, (float*)quat, (float*)J);
+    return fk_jac_host_t<double>((const double*)q, B, D, flags, (double*)pos, (double*)rot, (double*)quat, (double*)J);
+}
+
+}  // extern "C"

@@ -1,0 +1,254 @@
+// Kernel 1: batched Fetch forward kinematics + geometric Jacobian.
+//
+// Replaces, for a whole batch at once, the reference's per-configuration KDL calls
+//   TormIKSolver::fkSolver / allfkSolver / getJacobian   torm/src/torm_ik_solver.cpp:156-175
+//   KinematicsSolverSrv::fkSolver_srv / allLinkfkSolver_srv   pirl/src/kinematic_solver.cpp:206-261
+//
+// One thread per configuration walks the chain in registers (fetch_chain.cuh).  HBM-bound: 4*(D + 12 + 6D)
+// bytes per configuration in FP32 (244 B at D = 7).  Array-of-structs outputs ([B,3], [B,9], [B,6,D], the
+// layout a drop-in caller holds) are staged per 128-configuration tile in shared memory -- 64-bit stores at a
+// 42-word thread stride are bank-conflict free -- and drained with TMA bulk stores (cp.async.bulk
+// shared::cta -> global), one per output array, so the write-back is fully coalesced and asynchronous to the
+// threads.  Struct-of-arrays outputs ([3,B], [9,B], [6D,B]) are stored directly (already coalesced).
+#include "fetch_chain.cuh"
+#include "rlitg_internal.h"
+
+namespace rlitg {
+
+constexpr int kTile = 128;  // configurations per CTA
+
+template <typename T>
+RLITG_DEV T ld_stream(const T* p) { return __ldg(p); }
+
+// vectorised shared-memory tile write: N values per thread at thread stride N (see header comment)
+template <typename T, int N>
+RLITG_DEV void stage_row(T* tile, int tid, const T (&v)[N]) {
+    T* dst = tile + tid * N;
+    if constexpr (sizeof(T) == 4 && (N % 4) == 0) {
+#pragma unroll
+        for (int i = 0; i < N; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    } else if constexpr (sizeof(T) == 4 && (N % 2) == 0) {
+#pragma unroll
+        for (int i = 0; i < N; i += 2) *reinterpret_cast<float2*>(dst + i) = make_float2(v[i], v[i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; i++) dst[i] = v[i];
+    }
+}
+
+// drain a staged [n, N] tile to global memory
+template <typename T>
+RLITG_DEV void drain_tile(T* gdst, const T* tile, int n_elems, bool bulk, int tid, int nthreads) {
+    if (bulk) {
+        if (tid == 0) bulk_store(gdst, tile, (uint32_t)(n_elems * sizeof(T)));
+    } else {
+        for (int i = tid; i < n_elems; i += nthreads) gdst[i] = tile[i];
+    }
+}
+
+template <typename T, int D, bool QSOA, bool OSOA>
+__global__ void __launch_bounds__(kTile) fk_jac_kernel(const T* __restrict__ q, int64_t B, T* __restrict__ pos,
+                                                       T* __restrict__ rot, T* __restrict__ quat,
+                                                       T* __restrict__ J, int allow_bulk) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* sJ = reinterpret_cast<T*>(smem_raw);   // [kTile, 6D]
+    T* sRot = sJ + kTile * 6 * D;             // [kTile, 9]
+    T* sQuat = sRot + kTile * 9;              // [kTile, 4]
+    T* sPos = sQuat + kTile * 4;              // [kTile, 3]
+    T* sQ = sPos + kTile * 3;                 // [kTile, D]  (AoS input staging)
+
+    const int tid = threadIdx.x;
+    const int64_t base = (int64_t)blockIdx.x * kTile;
+    const int n = (int)min((int64_t)kTile, B - base);
+    const int64_t b = base + tid;
+    const bool live = tid < n;
+
+    T qv[D];
+    if constexpr (QSOA) {
+#pragma unroll
+        for (int j = 0; j < D; j++) qv[j] = live ? ld_stream(q + (int64_t)j * B + b) : T(0);
+    } else {
+        // coalesced tile load, then a conflict-free strided read (D is odd or 8 -> at worst 8-way on D = 8)
+        const T* src = q + base * D;
+        for (int i = tid; i < n * D; i += kTile) sQ[i] = ld_stream(src + i);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < D; j++) qv[j] = live ? sQ[tid * D + j] : T(0);
+    }
+
+    FkJac<T, D> fj;
+    walk_chain<T, D>(qv, fj);
+
+    if constexpr (OSOA) {
+        if (!live) return;
+        if (pos) { pos[b] = fj.ee.p.x; pos[B + b] = fj.ee.p.y; pos[2 * B + b] = fj.ee.p.z; }
+        if (rot) {
+            rot[0 * B + b] = fj.ee.c0.x; rot[1 * B + b] = fj.ee.c1.x; rot[2 * B + b] = fj.ee.c2.x;
+            rot[3 * B + b] = fj.ee.c0.y; rot[4 * B + b] = fj.ee.c1.y; rot[5 * B + b] = fj.ee.c2.y;
+            rot[6 * B + b] = fj.ee.c0.z; rot[7 * B + b] = fj.ee.c1.z; rot[8 * B + b] = fj.ee.c2.z;
+        }
+        if (quat) {
+            T x, y, z, w;
+            rot_to_quat_kdl(fj.ee.c0, fj.ee.c1, fj.ee.c2, x, y, z, w);
+            quat[b] = x; quat[B + b] = y; quat[2 * B + b] = z; quat[3 * B + b] = w;
+        }
+        if (J) {
+            T jv[6 * D];
+            fill_jac(fj, jv);
+#pragma unroll
+            for (int i = 0; i < 6 * D; i++) J[(int64_t)i * B + b] = jv[i];
+        }
+    } else {
+        if (J) {
+            T jv[6 * D];
+            fill_jac(fj, jv);
+            stage_row<T, 6 * D>(sJ, tid, jv);
+        }
+        if (rot) {
+            const T rv[9] = {fj.ee.c0.x, fj.ee.c1.x, fj.ee.c2.x, fj.ee.c0.y, fj.ee.c1.y,
+                             fj.ee.c2.y, fj.ee.c0.z, fj.ee.c1.z, fj.ee.c2.z};
+            stage_row<T, 9>(sRot, tid, rv);
+        }
+        if (quat) {
+            T qq[4];
+            rot_to_quat_kdl(fj.ee.c0, fj.ee.c1, fj.ee.c2, qq[0], qq[1], qq[2], qq[3]);
+            stage_row<T, 4>(sQuat, tid, qq);
+        }
+        if (pos) {
+            const T pv[3] = {fj.ee.p.x, fj.ee.p.y, fj.ee.p.z};
+            stage_row<T, 3>(sPos, tid, pv);
+        }
+        // bulk (TMA) drain needs 16-byte sizes: a full tile always qualifies, a partial tile falls back
+        const bool bulk = allow_bulk && n == kTile;
+        if (bulk) fence_proxy_async_smem();
+        __syncthreads();
+        if (J) drain_tile(J + base * 6 * D, sJ, n * 6 * D, bulk, tid, kTile);
+        if (rot) drain_tile(rot + base * 9, sRot, n * 9, bulk, tid, kTile);
+        if (quat) drain_tile(quat + base * 4, sQuat, n * 4, bulk, tid, kTile);
+        if (pos) drain_tile(pos + base * 3, sPos, n * 3, bulk, tid, kTile);
+        if (bulk && tid == 0) {
+            bulk_commit();
+            bulk_wait_read_all();
+        }
+    }
+}
+
+template <typename T, int D, int K = 0>
+RLITG_DEV void fill_jac_cols(const FkJac<T, D>& fj, T* jv) {
+    V3<T> lin, ang;
+    fj.template column<K>(lin, ang);
+    jv[0 * D + K] = lin.x; jv[1 * D + K] = lin.y; jv[2 * D + K] = lin.z;
+    jv[3 * D + K] = ang.x; jv[4 * D + K] = ang.y; jv[5 * D + K] = ang.z;
+    if constexpr (K + 1 < D) fill_jac_cols<T, D, K + 1>(fj, jv);
+}
+template <typename T, int D>
+RLITG_DEV void fill_jac(const FkJac<T, D>& fj, T (&jv)[6 * D]) { fill_jac_cols<T, D, 0>(fj, jv); }
+
+// ---- all-link FK: [B, D+1, 7] = (pos, quat xyzw) per segment tip (allLinkfkSolver_srv) --------------------
+template <typename T, int D>
+struct AllFkVisit {
+    T* row;  // this thread's padded shared-memory row
+    template <int K>
+    RLITG_DEV void operator()(jidx<K>, const FrameC<T>& f) {
+        T x, y, z, w;
+        rot_to_quat_kdl(f.c0, f.c1, f.c2, x, y, z, w);
+        T* o = row + K * 7;
+        o[0] = f.p.x; o[1] = f.p.y; o[2] = f.p.z; o[3] = x; o[4] = y; o[5] = z; o[6] = w;
+    }
+};
+
+template <typename T, int D, bool QSOA>
+__global__ void __launch_bounds__(kTile) allfk_kernel(const T* __restrict__ q, int64_t B, T* __restrict__ out) {
+    constexpr int N = (D + 1) * 7, NP = N + 1;  // padded row stride: odd -> conflict-free scalar stores
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* sOut = reinterpret_cast<T*>(smem_raw);  // [kTile, NP]
+    T* sQ = sOut + kTile * NP;
+    const int tid = threadIdx.x;
+    const int64_t base = (int64_t)blockIdx.x * kTile;
+    const int n = (int)min((int64_t)kTile, B - base);
+    const bool live = tid < n;
+    T qv[D];
+    if constexpr (QSOA) {
+#pragma unroll
+        for (int j = 0; j < D; j++) qv[j] = live ? ld_stream(q + (int64_t)j * B + base + tid) : T(0);
+    } else {
+        const T* src = q + base * D;
+        for (int i = tid; i < n * D; i += kTile) sQ[i] = ld_stream(src + i);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < D; j++) qv[j] = live ? sQ[tid * D + j] : T(0);
+    }
+    AllFkVisit<T, D> v{sOut + tid * NP};
+    walk_chain<T, D>(qv, v);
+    __syncthreads();
+    T* dst = out + base * N;
+    for (int i = tid; i < n * N; i += kTile) {
+        const int r = i / N, c = i - r * N;
+        dst[i] = sOut[r * NP + c];
+    }
+}
+
+// ---- launchers -------------------------------------------------------------------------------------------
+template <typename T, int D, bool QSOA, bool OSOA>
+static int launch_fk_jac_t(const T* q, int64_t B, T* pos, T* rot, T* quat, T* J, cudaStream_t st) {
+    const size_t smem = sizeof(T) * kTile * (6 * D + 9 + 4 + 3 + D);
+    auto kern = fk_jac_kernel<T, D, QSOA, OSOA>;
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return set_cuda_error("cudaFuncSetAttribute(fk_jac_kernel)");
+        attr_set = true;
+    }
+    // TMA bulk stores need 16-byte aligned global addresses; tile offsets keep the alignment of the base
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const int allow_bulk = al16(pos) && al16(rot) && al16(quat) && al16(J);
+    const int64_t grid = (B + kTile - 1) / kTile;
+    kern<<<(unsigned)grid, kTile, smem, st>>>(q, B, pos, rot, quat, J, allow_bulk);
+    return check_launch("fk_jac_kernel");
+}
+
+template <typename T>
+int launch_fk_jac(const T* q, int64_t B, int D, int flags, T* pos, T* rot, T* quat, T* J, cudaStream_t st) {
+    if (B == 0) return RLITG_OK;
+    const bool qs = flags & RLITG_Q_SOA, os = flags & RLITG_OUT_SOA;
+#define RLITG_DISPATCH(DD)                                                                     \
+    if (qs && os) return launch_fk_jac_t<T, DD, true, true>(q, B, pos, rot, quat, J, st);      \
+    if (qs && !os) return launch_fk_jac_t<T, DD, true, false>(q, B, pos, rot, quat, J, st);    \
+    if (!qs && os) return launch_fk_jac_t<T, DD, false, true>(q, B, pos, rot, quat, J, st);    \
+    return launch_fk_jac_t<T, DD, false, false>(q, B, pos, rot, quat, J, st);
+    if (D == 7) { RLITG_DISPATCH(7) }
+    if (D == 8) { RLITG_DISPATCH(8) }
+#undef RLITG_DISPATCH
+    return set_error(RLITG_ERR_SHAPE, "D must be 7 (arm) or 8 (torso + arm)");
+}
+
+template <typename T, int D, bool QSOA>
+static int launch_allfk_t(const T* q, int64_t B, T* out, cudaStream_t st) {
+    const size_t smem = sizeof(T) * kTile * ((D + 1) * 7 + 1 + D);
+    auto kern = allfk_kernel<T, D, QSOA>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return set_cuda_error("cudaFuncSetAttribute(allfk_kernel)");
+        attr_set = true;
+    }
+    const int64_t grid = (B + kTile - 1) / kTile;
+    kern<<<(unsigned)grid, kTile, smem, st>>>(q, B, out);
+    return check_launch("allfk_kernel");
+}
+
+template <typename T>
+int launch_allfk(const T* q, int64_t B, int D, int flags, T* out, cudaStream_t st) {
+    if (B == 0) return RLITG_OK;
+    const bool qs = flags & RLITG_Q_SOA;
+    if (D == 7) return qs ? launch_allfk_t<T, 7, true>(q, B, out, st) : launch_allfk_t<T, 7, false>(q, B, out, st);
+    if (D == 8) return qs ? launch_allfk_t<T, 8, true>(q, B, out, st) : launch_allfk_t<T, 8, false>(q, B, out, st);
+    return set_error(RLITG_ERR_SHAPE, "D must be 7 (arm) or 8 (torso + arm)");
+}
+
+template int launch_fk_jac<float>(const float*, int64_t, int, int, float*, float*, float*, float*, cudaStream_t);
+template int launch_fk_jac<double>(const double*, int64_t, int, int, double*, double*, double*, double*, cudaStream_t);
+template int launch_allfk<float>(const float*, int64_t, int, int, float*, cudaStream_t);
+template int launch_allfk<double>(const double*, int64_t, int, int, double*, cudaStream_t);
+
+}  // namespace rlitg
