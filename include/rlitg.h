@@ -87,6 +87,43 @@ RLITG_API int rlitg_jacobian(const void* q, int64_t B, int D, int dtype, int fla
 RLITG_API int rlitg_fk_jac_host(const void* q, int64_t B, int D, int dtype, int flags, void* pos, void* rot, void* quat,
                       void* J);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Scene: link-sphere table + occupancy grid / distance volume (device resident, owned by the handle)
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct RlitgScene RlitgScene;
+
+/* Creates an empty scene on the current CUDA device / frees it and its device memory. */
+RLITG_API int rlitg_scene_create(RlitgScene** out);
+RLITG_API int rlitg_scene_destroy(RlitgScene* scene);
+
+/* Collision spheres (HOST pointers): link[S] = segment-tip index 0..7 (7 = gripper_link; the fingers ride on it),
+ * sorted ascending; center [S,3] in the link frame; radius [S].  S <= 64.  Stands in for MoveIt's
+ * CollisionRobotDistanceField sphere decomposition (torm/src/torm_optimizer.cpp:131-135,195-206), which is
+ * third-party and unpinned: the table is an input. */
+RLITG_API int rlitg_scene_set_spheres(RlitgScene* scene, int S, const int32_t* link, const double* center,
+                                      const double* radius);
+
+/* Occupancy volume (HOST uint8 [nz][ny][nx], non-zero = occupied; the pirl_gazebo occ_N.npy format,
+ * pirl_gazebo/script/save_pointcloud.py:22-32) -> on device: bit-packed occupancy + exact signed Euclidean
+ * distance records (d, dd/dx, dd/dy, dd/dz) per cell with MoveIt PropagationDistanceField semantics
+ * (torm/src/torm_optimizer.cpp:110-120).  origin = centre of cell (0,0,0) in the planning frame (base_link). */
+RLITG_API int rlitg_scene_set_occupancy(RlitgScene* scene, const uint8_t* occ, int nx, int ny, int nz,
+                                        const double* origin, double res, double max_prop);
+
+/* Distance volume given directly (HOST float [nz][ny][nx][4] records; d >= 1e30 marks an inactive cell). */
+RLITG_API int rlitg_scene_set_field(RlitgScene* scene, const float* field, int nx, int ny, int nz,
+                                    const double* origin, double res);
+/* Read-back for parity tests: field_out float [nz][ny][nx][4]; bits_out uint32 [nz][ny][ceil(nx/32)]. */
+RLITG_API int rlitg_scene_get_field(const RlitgScene* scene, float* field_out);
+RLITG_API int rlitg_scene_get_bits(const RlitgScene* scene, uint32_t* bits_out);
+
+/* cc_srv: `/collision_check` service (pirl_msgs/srv/collision.srv, pirl/src/collision_checker.cpp:39-61) and
+ * TormIKSolver::collisionChecking (torm/src/torm_ik_solver.cpp:59-66).  out[b] = 1 when any sphere of
+ * configuration q[b] (D = 7, [B,7]) has signed distance - radius < 0.  An approximation of the reference's FCL
+ * mesh test, not a parity target.  base_off = chain base -> planning frame (HOST double[3]). */
+RLITG_API int rlitg_sphere_grid_collide(const void* q, int64_t B, int dtype, const RlitgScene* scene,
+                                        const double* base_off, uint8_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -120,6 +120,7 @@ RLITG_API int rlitg_fk_jac(const void* q, int64_t B, int D, int dtype, int flags
                  void* stream) {
     int rc = check_common(q, B, D, dtype);
     if (rc) return rc;
+    if (B == 0) return RLITG_OK;
     if (!pos && !rot && !quat && !J) return set_error(RLITG_ERR_NULL, "all outputs are NULL");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == RLITG_F32)
@@ -128,18 +129,19 @@ RLITG_API int rlitg_fk_jac(const void* q, int64_t B, int D, int dtype, int flags
 }
 
 RLITG_API int rlitg_fk(const void* q, int64_t B, int D, int dtype, int flags, void* pos, void* quat, void* stream) {
-    if (!pos || !quat) return set_error(RLITG_ERR_NULL, "pos / quat is NULL");
+    if (B > 0 && (!pos || !quat)) return set_error(RLITG_ERR_NULL, "pos / quat is NULL");
     return rlitg_fk_jac(q, B, D, dtype, flags, pos, nullptr, quat, nullptr, stream);
 }
 
 RLITG_API int rlitg_jacobian(const void* q, int64_t B, int D, int dtype, int flags, void* J, void* stream) {
-    if (!J) return set_error(RLITG_ERR_NULL, "J is NULL");
+    if (B > 0 && !J) return set_error(RLITG_ERR_NULL, "J is NULL");
     return rlitg_fk_jac(q, B, D, dtype, flags, nullptr, nullptr, nullptr, J, stream);
 }
 
 RLITG_API int rlitg_allfk(const void* q, int64_t B, int D, int dtype, int flags, void* out, void* stream) {
     int rc = check_common(q, B, D, dtype);
     if (rc) return rc;
+    if (B == 0) return RLITG_OK;
     if (!out) return set_error(RLITG_ERR_NULL, "out is NULL");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == RLITG_F32) return launch_allfk<float>((const float*)q, B, D, flags, (float*)out, st);
@@ -150,6 +152,7 @@ RLITG_API int rlitg_fk_jac_host(const void* q, int64_t B, int D, int dtype, int 
                       void* J) {
     int rc = check_common(q, B, D, dtype);
     if (rc) return rc;
+    if (B == 0) return RLITG_OK;
     if (!pos && !rot && !quat && !J) return set_error(RLITG_ERR_NULL, "all outputs are NULL");
     if (dtype == RLITG_F32)
         return fk_jac_host_t<float>((const float*)q, B, D, flags, (float*)pos, (float*)rot, (float*)quat, (float*)J);

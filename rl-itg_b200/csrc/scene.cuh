@@ -1,0 +1,58 @@
+// Device-side view of a collision scene: link-sphere table + distance-record volume (+ bit-packed occupancy).
+//
+// The reference queries MoveIt's PropagationDistanceField per sphere (CollisionWorldHybrid::getCollisionGradients,
+// torm/src/torm_optimizer.cpp:1281,1323): nearest cell value + central-difference gradient over six neighbours.
+// Both depend only on the cell, so the volume stores one 16-byte record (d, gx, gy, gz) per cell: one gather per
+// sphere instead of seven.  Cell k is centred at origin + k * res; border cells and cells
+// at or beyond the maximum propagation distance hold d = 1e30, g = 0 ("untouched" in MoveIt's terms).
+#pragma once
+#include "rlitg_common.cuh"
+
+namespace rlitg {
+
+constexpr int kMaxSpheres = 64;
+constexpr int kNumLinks = 8;  // segment tips of the 7-joint arm chain; 7 = gripper_link (fingers ride on it)
+
+struct SceneDev {
+    const float4* field;     // [nz][ny][nx]
+    const uint32_t* bits;    // occupancy, bit-packed along x: word (z*ny + y)*wx + (x >> 5)
+    const float4* spheres;   // [S] (cx, cy, cz, r) in the link frame, sorted by link
+    const int* link_start;   // [kNumLinks + 1] sphere index ranges per link
+    int S;
+    int nx, ny, nz, wx;
+    double origin[3];
+    double res;
+};
+
+template <typename T>
+struct GridMap {  // world -> cell
+    T ox, oy, oz, res, inv_res;
+    int nx, ny, nz;
+    RLITG_DEV explicit GridMap(const SceneDev& s)
+        : ox(T(s.origin[0])), oy(T(s.origin[1])), oz(T(s.origin[2])), res(T(s.res)), inv_res(T(1.0 / s.res)),
+          nx(s.nx), ny(s.ny), nz(s.nz) {}
+    RLITG_DEV int cell1(T x, T o) const {
+        if constexpr (sizeof(T) == 8) return (int)floor((x - o) / res + T(0.5));  // literal (oracle) form
+        else return (int)floorf(fmaf(x - o, inv_res, 0.5f));
+    }
+    // linear cell index or -1 when outside the grid
+    RLITG_DEV int64_t cell(V3<T> x) const {
+        const int cx = cell1(x.x, ox), cy = cell1(x.y, oy), cz = cell1(x.z, oz);
+        if (cx < 0 || cy < 0 || cz < 0 || cx >= nx || cy >= ny || cz >= nz) return -1;
+        return ((int64_t)cz * ny + cy) * nx + cx;
+    }
+};
+
+// distance record at a world point: returns false when out of grid / inactive (potential 0, gradient 0)
+template <typename T>
+RLITG_DEV bool field_lookup(const SceneDev& s, const GridMap<T>& gm, V3<T> x, T& d, V3<T>& g) {
+    const int64_t c = gm.cell(x);
+    if (c < 0) return false;
+    const float4 r = __ldg(s.field + c);
+    if (!(r.x < 1e29f)) return false;
+    d = T(r.x);
+    g = {T(r.y), T(r.z), T(r.w)};
+    return true;
+}
+
+}  // namespace rlitg

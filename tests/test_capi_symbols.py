@@ -33,4 +33,5 @@ def test_argument_validation_without_gpu():
     assert lib.rlitg_fk_jac(ctypes.c_void_p(16), 4, 7, 5, 0, None, None, None, None, None) == -3
     assert lib.rlitg_fk_jac(ctypes.c_void_p(18), 4, 7, 0, 0, None, None, None, None, None) == -4
     assert b"aligned" in lib.rlitg_last_error()
-    assert lib.rlitg_fk_jac(ctypes.c_void_p(16), 0, 7, 0, 0, None, None, None, None, None) == -1  # all outputs NULL
+    assert lib.rlitg_fk_jac(ctypes.c_void_p(16), 4, 7, 0, 0, None, None, None, None, None) == -1  # all outputs NULL
+    assert lib.rlitg_fk_jac(None, 0, 7, 0, 0, None, None, None, None, None) == 0  # empty batch is a no-op
