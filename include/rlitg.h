@@ -124,6 +124,69 @@ RLITG_API int rlitg_scene_get_bits(const RlitgScene* scene, uint32_t* bits_out);
 RLITG_API int rlitg_sphere_grid_collide(const void* q, int64_t B, int dtype, const RlitgScene* scene,
                                         const double* base_off, uint8_t* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Null-space imitation objective and pseudo-inverse velocity step
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* jaco_srv: `/jaco_reward` service (pirl_msgs/srv/jaco.srv, pirl/src/kinematic_solver.cpp:332-351):
+ * out[b] = || (I - J^T (J J^T)^-1 J) err[b] ||, J = Jacobian at q[b].  err, q [B,7]; out [B]. */
+RLITG_API int rlitg_nullspace_norm(const void* err, const void* q, int64_t B, int dtype, void* out, void* stream);
+
+/* TormIKSolver::vikSolver (torm/src/torm_ik_solver.cpp:169-171) = KDL::ChainIkSolverVel_pinv::CartToJnt:
+ * dq[b] = pinv(J(q[b])) twist[b], singular values below eps (KDL default 1e-5) zeroed.  q [B,D], twist [B,6]
+ * (linear, angular), dq [B,D]. */
+RLITG_API int rlitg_pinv_step(const void* q, const void* twist, int64_t B, int D, int dtype, double eps, void* dq,
+                              void* stream);
+
+/* KDL::diff(FK(q[b]), target[b]) as used at torm/src/torm_optimizer.cpp:1413,1440 and
+ * torm/src/utils/traj_evaluator.cpp:72,79: twist [B,6] = (p_t - p, R * rotvec(R^T R_t)).  target [B,7]. */
+RLITG_API int rlitg_pose_diff(const void* q, const void* target, int64_t B, int D, int dtype, void* twist,
+                              void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * PIRL path-wise IK environment step (PirlEnv_Fetch, pirl/script/envs/PirlEnv.py)
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct RlitgPirlCfg {
+    double ll[7], ul[7];    /* joint limits as the env sees them (pirl/launch/pirl.yaml:11-12) */
+    int32_t cjoint[7];      /* 1 = continuous joint (pirl.yaml:9) */
+    int32_t n_future;       /* t: future targets in the observation (PirlEnv.py:77,311-315) */
+    int32_t z_dim;          /* scene latent length appended to the observation (:89,318) */
+    int32_t obs_type;       /* 0 onlyConf, 1 Conf+LinkPoses, 2 Conf+EE, 3 onlyLinkPoses (:80-87) */
+    int32_t train_mode;     /* mode == 'train' (:193) */
+    int32_t refine_flag;    /* refineFlag (:221,233,238,253,258) */
+    int32_t task_reward_flag, imitate_reward_flag, null_reward_flag; /* (:130-161) */
+    double task_suc_r, dist_suc_r, rot_suc_r, imit_suc_r;
+    double thr_early_stop, thr_dist, thr_rot, thr_imitate, zero_task_dist; /* (:123-128) */
+    double dist_p[4], rot_p[4], imit_p[4], null_p[4];                      /* (:165-168) */
+    double w_col, w_jlimit, w_early_stop;                                  /* (:170-172) */
+} RlitgPirlCfg;
+
+/* Observation length for a configuration (PirlEnv.py:79-89). */
+RLITG_API int rlitg_pirl_obs_dim(const RlitgPirlCfg* cfg);
+
+/* One env.step(action) for B independent environments (PirlEnv.py:209-289), fused in one kernel:
+ * _set_action (:184-207: add, single +-2pi wrap of continuous joints, clip, np.allclose joint-limit test, collision
+ * test on the candidate) -> all-link FK (:216) -> _get_obs (:292-320) -> task / imitation / null-space rewards
+ * (:495-542) -> done and info flags (:226-282).
+ *   q [B,7] in/out; action [B,7] float32 (the policy's dtype, pirl/script/algos/sac/core.py:98-101);
+ *   timestep [B] int32 in/out (incremented); max_timestep [B] int32;
+ *   targets [B,Tmax,7], demos [B,Tmax,7] (may be NULL), latent [B,z_dim] (NULL when z_dim = 0);
+ *   scene may be NULL (no collision test); base_off HOST double[3];
+ *   obs [B,O]; reward [B]; done [B] uint8; flags [B,8] uint8 = (is_col, is_jlimit, is_early_stop, is_timeout,
+ *   is_dist_suc, is_rot_suc, is_imitate_suc, is_task_suc); counters [B,4] int32 in/out = (task, dist, rot, imitate)
+ *   success counts (may be NULL); errs [B,4] = (dist_err, rot_err, imitate_err, nullspace objective) (may be NULL).
+ * Floating tensors share dtype. */
+RLITG_API int rlitg_pirl_env_step(const RlitgPirlCfg* cfg, int64_t B, int dtype, void* q, const float* action,
+                                  int32_t* timestep, const int32_t* max_timestep, const void* targets,
+                                  const void* demos, int Tmax, const void* latent, const RlitgScene* scene,
+                                  const double* base_off, void* obs, void* reward, uint8_t* done, uint8_t* flags,
+                                  int32_t* counters, void* errs, void* stream);
+
+/* Observation only (env.reset, PirlEnv.py:378-392; PirlInterpolator::getObs, torm/src/pirl_interpolator.cpp:176-248). */
+RLITG_API int rlitg_pirl_obs(const RlitgPirlCfg* cfg, int64_t B, int dtype, const void* q, const int32_t* timestep,
+                             const int32_t* max_timestep, const void* targets, int Tmax, const void* latent,
+                             void* obs, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

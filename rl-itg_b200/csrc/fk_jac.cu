@@ -133,17 +133,6 @@ __global__ void __launch_bounds__(kTile) fk_jac_kernel(const T* __restrict__ q, 
     }
 }
 
-template <typename T, int D, int K = 0>
-RLITG_DEV void fill_jac_cols(const FkJac<T, D>& fj, T* jv) {
-    V3<T> lin, ang;
-    fj.template column<K>(lin, ang);
-    jv[0 * D + K] = lin.x; jv[1 * D + K] = lin.y; jv[2 * D + K] = lin.z;
-    jv[3 * D + K] = ang.x; jv[4 * D + K] = ang.y; jv[5 * D + K] = ang.z;
-    if constexpr (K + 1 < D) fill_jac_cols<T, D, K + 1>(fj, jv);
-}
-template <typename T, int D>
-RLITG_DEV void fill_jac(const FkJac<T, D>& fj, T (&jv)[6 * D]) { fill_jac_cols<T, D, 0>(fj, jv); }
-
 // ---- all-link FK: [B, D+1, 7] = (pos, quat xyzw) per segment tip (allLinkfkSolver_srv) --------------------
 template <typename T, int D>
 struct AllFkVisit {

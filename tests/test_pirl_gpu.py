@@ -1,0 +1,173 @@
+"""GPU parity: fused PIRL env step (kernel 2), null-space norm, pinv step, pose diff vs the CPU oracle.
+
+Stated tolerances.  FP64 build: 1e-10 on everything.  FP32: observation 1e-5 relative (floor 2e-6); dist_err
+2e-6; rot_err compared through cos(r/2) to 5e-7 (r = 2 acos|w| is ill-conditioned near 0: SURVEY section 7);
+reward 1e-4 + the propagated rot_err sensitivity; flags identical except where an error sits within tolerance of
+its threshold (counted)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def build_case(B, T, seed, with_scene, cuda_device):
+    from oracle import oracle as O
+    from rlitg_b200 import fetch, synth
+    rng = np.random.default_rng(seed)
+    demos = synth.random_joint_paths(B, T, seed=seed)
+    noisy = demos + rng.normal(0, 0.01, size=demos.shape)
+    targets = np.round(O.fk_quat(noisy.reshape(-1, 7)).reshape(B, T, 7), 6)  # 6-digit poses like the demo CSVs
+    mts = rng.integers(12, T, size=B).astype(np.int32)
+    ts = np.array([rng.integers(0, m) for m in mts], dtype=np.int32)
+    ts[: B // 16] = mts[: B // 16] - 1  # some envs time out on this step
+    q = demos[np.arange(B), ts] + rng.normal(0, 0.02, size=(B, 7))
+    q = np.clip(q, fetch.LL + 1e-3, fetch.UL - 1e-3)
+    act = rng.uniform(-0.26, 0.26, size=(B, 7)).astype(np.float32)
+    act[B // 2:: 7] *= 6.0  # some joint-limit violations / wraps
+    q[B // 3:: 11, 2] = 3.1  # continuous joints near the seam
+    osc = gsc = None
+    if with_scene:
+        from rlitg_b200 import scene as S
+        occ, _ = synth.random_box_scene((64, 96, 64), (-0.2, -0.96, 0.0), 0.02, seed=seed, n_clutter=3)
+        link, center, radius = fetch.default_spheres()
+        osc = O.Scene(O.build_field(occ, 0.02, 1.0), (-0.2, -0.96, 0.0), 0.02, link, center, radius)
+        gsc = S.Scene(cuda_device)
+        gsc.set_occupancy(occ, (-0.2, -0.96, 0.0), 0.02, 1.0)
+    return dict(demos=demos, targets=targets, mts=mts, ts=ts, q=q, act=act, osc=osc, gsc=gsc)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("reward_type,obs_type,t,z,with_scene,refine", [
+    ("Task+NullSpaceImitation", "Conf+LinkPoses", 1, 0, False, False),  # the trained setting (88-d obs)
+    ("Task+NullSpaceImitation", "Conf+LinkPoses", 1, 32, True, False),  # obs scenes: 120-d obs + collision
+    ("Task+Imitation", "Conf+EE", 3, 0, True, False),
+    ("Imitation", "onlyConf", 2, 4, False, False),
+    ("Task", "onlyLinkPoses", 1, 0, False, True),
+])
+def test_env_step_parity(cuda_device, dtype, reward_type, obs_type, t, z, with_scene, refine):
+    import torch
+    from oracle import oracle as O
+    from rlitg_b200 import pirl_env as P
+    B, T = 3001, 40
+    c = build_case(B, T, 5, with_scene, cuda_device)
+    rng = np.random.default_rng(9)
+    latent = rng.normal(size=(B, z)) if z else None
+    for mode in ("train", "test"):
+        ocfg = O.pirl_cfg(reward_type, obs_type, t, z, train_mode=(mode == "train"), refine_flag=refine)
+        want = O.pirl_env_step(ocfg, c["q"], c["act"], c["ts"], c["mts"], c["targets"], c["demos"], latent, c["osc"])
+        env = P.PirlVecEnv(B, reward_type, obs_type, t, z, refine, c["gsc"], cuda_device, getattr(torch, dtype),
+                           want_errs=True)
+        env.set_problems(c["targets"], c["demos"], c["mts"], latent)
+        env.reset(start_conf=c["q"], mode=mode)
+        env.timestep.copy_(torch.tensor(c["ts"], device=cuda_device))
+        obs, rew, done, info = env.step(torch.tensor(c["act"], device=cuda_device))
+        torch.cuda.synchronize()
+        f64 = dtype == "float64"
+        g = dict(obs=obs.double().cpu().numpy(), rew=rew.double().cpu().numpy(), done=done.cpu().numpy(),
+                 flags=env.flags.cpu().numpy(), errs=env.errs.double().cpu().numpy(),
+                 q=env.cur_conf.double().cpu().numpy(), ts=env.timestep.cpu().numpy(), cnt=env.counters.cpu().numpy())
+        assert np.array_equal(g["ts"], want["timestep"])
+        assert want["obs"].shape == g["obs"].shape == (B, env.obs_dim)
+        # flags can legitimately differ when an error is within tolerance of a threshold, or (FP32) when a sphere
+        # centre sits on a voxel boundary; such envs are counted and excluded
+        tol = 1e-10 if f64 else 3e-6
+        e = want["errs"]
+        near = (np.abs(e[:, 0] - 0.2) < tol) | (np.abs(e[:, 0] - 0.04) < tol) | (np.abs(e[:, 0] - 0.08) < tol) | \
+               (np.abs(e[:, 1] - 0.104) < 30 * tol) | (np.abs(e[:, 2] - 0.087) < tol)
+        flag_mism = (g["flags"] != want["flags"]).any(axis=1)
+        bad = flag_mism & ~near
+        assert bad.sum() <= (0 if f64 else 3), (int(bad.sum()), np.nonzero(bad)[0][:5])
+        ok = ~flag_mism
+        assert ok.mean() > 0.995
+        if mode == "train":
+            assert want["flags"][:, 1].sum() > 10  # joint-limit rejections exercised
+            if with_scene:
+                assert want["flags"][:, 0].sum() > 10  # collisions exercised
+        assert np.abs(g["q"][ok] - want["q"][ok]).max() < (1e-12 if f64 else 5e-7)
+        rel, floor = (1e-10, 1e-12) if f64 else (1e-5, 2e-6)
+        assert (np.abs(g["obs"][ok] - want["obs"][ok]) / (floor + rel * np.abs(want["obs"][ok]))).max() <= 1.0
+        assert np.abs(g["errs"][ok, 0] - e[ok, 0]).max() < (1e-12 if f64 else 2e-6)
+        assert np.abs(np.cos(g["errs"][ok, 1] / 2) - np.cos(e[ok, 1] / 2)).max() < (1e-12 if f64 else 5e-7)
+        assert np.abs(g["errs"][ok, 2] - e[ok, 2]).max() < (1e-12 if f64 else 1e-6)
+        if not refine:
+            assert np.abs(g["errs"][ok, 3] - e[ok, 3]).max() < (1e-9 if f64 else 2e-5)
+        # reward: recompute the rot-error dependent term's sensitivity
+        drot = np.abs(g["errs"][:, 1] - e[:, 1])
+        rtol = (1e-9 if f64 else 2e-4) + 10.0 * drot
+        assert (np.abs(g["rew"][ok] - want["reward"][ok]) <= rtol[ok]).all()
+        assert np.array_equal(g["done"][ok], want["done"][ok])
+        assert np.array_equal(g["cnt"][ok], want["counters"][ok])
+
+
+def test_reset_observation_and_scalar_wrapper(cuda_device):
+    from oracle import oracle as O
+    from rlitg_b200 import pirl_env as P
+    c = build_case(8, 30, 2, False, cuda_device)
+    env = P.PirlEnvFetch(device=cuda_device)
+    assert env.observation_space_shape == (88,) and env.action_space_shape == (7,)
+    T = int(c["mts"][0]) + 1
+    obs = env.reset(c["targets"][0, :T], c["demos"][0, :T])
+    ocfg = O.pirl_cfg()
+    want = O.pirl_obs(ocfg, c["demos"][:1, 0], [0], [T - 1], c["targets"][:1, :T])
+    assert np.abs(obs - want[0]).max() < 1e-12
+    assert env.max_timestep == T - 1 and env.timestep == 0
+    q = c["demos"][0, 0].copy()
+    ts = 0
+    for k in range(5):
+        a = env.random_action().astype(np.float32)
+        o, r, d, info = env.step(a)
+        w = O.pirl_env_step(ocfg, q[None], a[None], [ts], [T - 1], c["targets"][:1, :T], c["demos"][:1, :T])
+        q, ts = w["q"][0], int(w["timestep"][0])
+        assert np.abs(o - w["obs"][0]).max() < 1e-10 and abs(r - w["reward"][0]) < 1e-9 and d == bool(w["done"][0])
+        assert set(info) == {"task_suc_count", "dist_suc_count", "rot_suc_count", "imitate_suc_count", "is_col",
+                             "is_jlimit", "is_early_stop", "is_timeout"}
+        assert env.timestep == ts
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-9), ("float32", 2e-5)])
+def test_nullspace_pinv_posediff(cuda_device, dtype, tol):
+    import torch
+    from oracle import oracle as O
+    from rlitg_b200 import pirl_env as P, synth
+    B = 5000
+    q = synth.random_configs(B, seed=21)
+    rng = np.random.default_rng(3)
+    err = rng.normal(0, 0.3, size=(B, 7))
+    tw = rng.normal(0, 0.05, size=(B, 6))
+    tgt = np.round(O.fk_quat(q + rng.normal(0, 0.05, size=q.shape)), 6)
+    dt = getattr(torch, dtype)
+    tq = torch.tensor(q, dtype=dt, device=cuda_device)
+    man = O.manipulability(q)
+    good = man > 1e-2  # pinv conditioning: exclusions counted (SURVEY 8d tolerances)
+    assert good.mean() > 0.9
+    ns = P.nullspace_norm(torch.tensor(err, dtype=dt, device=cuda_device), tq).double().cpu().numpy()
+    assert np.abs(ns[good] - O.nullspace_norm(err, q)[good]).max() < tol * 5
+    dq = P.pinv_step(tq, torch.tensor(tw, dtype=dt, device=cuda_device)).double().cpu().numpy()
+    want = O.pinv_step(q, tw)
+    scale = np.abs(want).max(axis=1, keepdims=True) + 1e-3
+    assert (np.abs(dq - want) / scale)[good].max() < (1e-8 if dtype == "float64" else 2e-4)
+    pd = P.pose_diff(tq, torch.tensor(tgt, dtype=dt, device=cuda_device)).double().cpu().numpy()
+    assert np.abs(pd - O.pose_diff(q, tgt)).max() < (1e-10 if dtype == "float64" else 3e-6)
+    # D = 8 path
+    q8 = synth.random_configs(512, seed=5, D=8)
+    tw8 = rng.normal(0, 0.05, size=(512, 6))
+    dq8 = P.pinv_step(torch.tensor(q8, dtype=dt, device=cuda_device),
+                      torch.tensor(tw8, dtype=dt, device=cuda_device)).double().cpu().numpy()
+    w8 = O.pinv_step(q8, tw8)
+    g8 = O.manipulability(q8) > 1e-2
+    assert (np.abs(dq8 - w8) / (np.abs(w8).max(axis=1, keepdims=True) + 1e-3))[g8].max() < (1e-8 if dtype == "float64" else 2e-4)
+
+
+def test_pinv_singular_configuration(cuda_device):
+    """Rank-deficient J (arm stretched out): KDL's truncated SVD must be reproduced, not a blown-up solve."""
+    import torch
+    from oracle import oracle as O
+    from rlitg_b200 import pirl_env as P
+    q = np.zeros((4, 7)); q[1, 1] = 0.3; q[2, 3] = 1e-7; q[3, 5] = 1e-9
+    tw = np.tile(np.array([[0.01, 0.02, -0.01, 0.1, -0.05, 0.02]]), (4, 1))
+    want = O.pinv_step(q, tw)
+    for dtype, tol in (("float64", 1e-8), ("float32", 1e-3)):
+        dt = getattr(torch, dtype)
+        got = P.pinv_step(torch.tensor(q, dtype=dt, device=cuda_device),
+                          torch.tensor(tw, dtype=dt, device=cuda_device)).double().cpu().numpy()
+        assert np.isfinite(got).all() and np.abs(got - want).max() < tol, (dtype, got, want)
