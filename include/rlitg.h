@@ -187,6 +187,62 @@ RLITG_API int rlitg_pirl_obs(const RlitgPirlCfg* cfg, int64_t B, int dtype, cons
                              const int32_t* max_timestep, const void* targets, int Tmax, const void* latent,
                              void* obs, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * TORM path-following objective and gradient (TormOptimizer / TormCost / traj_evaluator)
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct RlitgTormParams {
+    int32_t T;              /* target poses = trajectory rows; row 0 = start configuration (fixed) */
+    int32_t D;              /* 7 */
+    double dt;              /* time_duration_ (torm/include/torm/torm_parameters.h:83) */
+    double rot_scale;       /* rotation_scale_factor_ 0.17 */
+    double jac_weight;      /* jacobian_update_weight_ */
+    double clearance;       /* min_clearence_ */
+    double pinv_ridge;      /* pseudo_inverse_ridge_factor_ 1e-4 */
+    double vik_eps;         /* KDL::ChainIkSolverVel_pinv eps 1e-5 */
+    int32_t use_pinv;       /* use_pseudo_inverse_ */
+    int32_t affine_axis_quirk; /* reproduce `axis = joint_transform * axis` (torm/src/torm_optimizer.cpp:1157) */
+    double base_off[3];     /* chain base -> planning frame (torm/launch/config/robot/fetch.yaml:18) */
+    int32_t cjoint[8];      /* 1 = continuous joint */
+    double vel_limit[8];    /* fetch_moveit_assistant/config/joint_limits.yaml:5-39 */
+} RlitgTormParams;
+
+/* stage_mask bits */
+#define RLITG_STAGE_POSE 1       /* getEndPoseCost(false): end-pose cost sums (torm/src/torm_optimizer.cpp:1399-1425) */
+#define RLITG_STAGE_POSE_GRAD 2  /* getEndPoseCost(true) + calculateEndPoseIncrements (:1475-1482) */
+#define RLITG_STAGE_SMOOTH 4     /* calculateSmoothnessIncrements (:1466-1473) */
+#define RLITG_STAGE_COLL 8       /* performForwardKinematics (:1302-1382) + calculateCollisionIncrements (:1484-1553)
+                                    + getCollisionCost (:1448-1463) */
+#define RLITG_STAGE_EVAL 16      /* traj_evaluator::getCost (torm/src/utils/traj_evaluator.cpp:104-132) */
+#define RLITG_TORM_NCOST 10
+/* costs [N,10]: 0 eval position, 1 eval rotation, 2 velocity, 3 acceleration, 4 jerk (traj_evaluator means),
+ *   5 collision cost (mean over the T rows of the summed sphere potentials), 6 weighted = [0] + 0.17 [1]
+ *   (getWeightedPoseCost, the optimiser's cur_Cost), 7 velocity-limit violations, 8 / 9 end-pose position /
+ *   rotation error SUMS over the free waypoints (getEndPoseCost = [8] + rot_scale [9]). */
+
+/* Smoothness operator of TormCost (torm/src/torm_cost.cpp:46-77) with the scaling of
+ * torm/src/torm_optimizer.cpp:211-236, built once per (T, dt, weights) on the host in FP64 and kept on device:
+ * the 13-banded quad_cost_full_ over the T+10 padded rows and the inverse of its free block. */
+typedef struct RlitgSmooth RlitgSmooth;
+RLITG_API int rlitg_smooth_create(int T, double dt, const double* w3 /*vel, acc, jerk*/, double ridge,
+                                  RlitgSmooth** out);
+RLITG_API int rlitg_smooth_destroy(RlitgSmooth* s);
+/* HOST read-back: Aband [(T+10),13] (A(i, i+k-6)), scale = max coeff of the unscaled inverse (the reference's
+ * `// 96.77624`), Ainv [(T-1),(T-1)] (nullable). */
+RLITG_API int rlitg_smooth_get(const RlitgSmooth* s, double* Aband, double* scale, double* Ainv);
+
+/* Cost terms and increments for N candidate trajectories at once (one CTA per trajectory).
+ *   traj [N,T,D] (row 0 = start, rows 1..T-1 free); targets [T,7] shared by all N;
+ *   stochastic_idx [N] int32 (nullable): use_stochastic_descent_ -- the single free-waypoint index (0..T-2) whose
+ *   spheres contribute to the collision increment (:1502-1515); NULL = every free waypoint;
+ *   inc_smooth / inc_coll / inc_pose [N,T-1,D] (nullable when the stage is off); costs [N,10];
+ *   active [N] float32 (nullable): mean number of active spheres (potential >= 1e-4) per evaluated waypoint.
+ * Replaces the per-waypoint loops of TormOptimizer (in-process calls, one trajectory at a time) and
+ * traj_evaluator; see the stage bits for the exact members. */
+RLITG_API int rlitg_torm_cost_grad(const void* traj, const void* targets, int64_t N, int dtype,
+                                   const RlitgScene* scene, const RlitgSmooth* smooth, const RlitgTormParams* p,
+                                   int stage_mask, const int32_t* stochastic_idx, void* inc_smooth, void* inc_coll,
+                                   void* inc_pose, void* costs, float* active, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,9 @@ int launch_fk_jac(const T* q, int64_t B, int D, int flags, T* pos, T* rot, T* qu
 template <typename T>
 int launch_allfk(const T* q, int64_t B, int D, int flags, T* out, cudaStream_t st);
 
+struct Smooth;    // torm.cu
+const double* smooth_inv_host(const Smooth* s);
+int smooth_T(const Smooth* s);
 struct Scene;     // scene.cu
 struct SceneDev;  // scene.cuh
 bool scene_ready(const Scene* s, bool need_grid, bool need_spheres);

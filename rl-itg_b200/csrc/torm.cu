@@ -1,0 +1,669 @@
+// Kernel 3: TORM path-following objective and gradient over N candidate trajectories x T waypoints
+// (SURVEY.md 8a rows A4-A8).  One CTA per trajectory, one thread per waypoint.
+//
+// What one launch replaces in the reference (all serial, one trajectory at a time, FP64, KDL + MoveIt):
+//   getEndPoseCost(grad)              torm/src/torm_optimizer.cpp:1399-1425   FK + KDL::diff + pinv velocity IK
+//   calculateEndPoseIncrements        :1475-1482
+//   performForwardKinematics          :1302-1382   sphere positions, distance-field queries, 7-point stencils
+//   calculateCollisionIncrements      :1484-1553   CHOMP gradient per sphere through J^T (J J^T + ridge I)^-1
+//   getCollisionCost                  :1448-1463
+//   calculateSmoothnessIncrements     :1466-1473   -2 A_full x (TormCost, torm/src/torm_cost.cpp:46-77)
+//   traj_evaluator::getCost           torm/src/utils/traj_evaluator.cpp:65-85,104-132,164-205,261-281
+//
+// Data movement per trajectory: the [T,7] rows are read once into shared memory (window with 6 halo rows for
+// the 13-tap smoothness band and the 7-point stencils); sphere positions [T,S,3] live only in shared memory;
+// the distance volume is gathered as one 16-byte record per sphere from L2; three [T-1,7] increment tiles and
+// ten cost scalars are written.  Long paths (T > 256) are walked in 256-row chunks with recomputed halo rows.
+// FP32-FMA bound on paper, L2-gather latency bound in practice.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "fetch_chain.cuh"
+#include "linalg.cuh"
+#include "rlitg_internal.h"
+#include "scene.cuh"
+
+namespace rlitg {
+
+constexpr int kTormMaxThreads = 256;
+constexpr int kNRed = 13;
+enum { R_WP_POS = 0, R_WP_ROT, R_MID_POS, R_MID_ROT, R_COLL, R_VEL_C, R_ACC_C, R_JERK_C, R_VEL_N, R_ACC_N, R_JERK_N,
+       R_NVIOL, R_NACTIVE };
+
+// torm/include/torm/torm_utils.h:49-57
+template <typename T> RLITG_DEV T diff_rule(int d, int k) {
+    constexpr double R[3][7] = {{-1.0 / 60, 3.0 / 20, -3.0 / 4, 0.0, 3.0 / 4, -3.0 / 20, 1.0 / 60},
+                                {1.0 / 90, -3.0 / 20, 3.0 / 2, -49.0 / 18, 3.0 / 2, -3.0 / 20, 1.0 / 90},
+                                {1.0 / 8, -1.0, 13.0 / 8, 0.0, -13.0 / 8, 1.0, -1.0 / 8}};
+    return T(R[d][k]);
+}
+
+template <typename T>
+struct TormP {
+    int Tn;
+    T dt, inv_dt, inv_dt2, rot_scale, jac_w, clearance;
+    double ridge, vik_eps;
+    int use_pinv, quirk;
+    T off[3];
+    int cj[7];
+    T vlim[7];
+    T rule_v[7], rule_a[7], rule_j[7];  // DIFF_RULES / dt^(k+1) for the evaluator's finite differences
+};
+
+RLITG_DEV float fmod_t(float a, float b) { return fmodf(a, b); }
+RLITG_DEV double fmod_t(double a, double b) { return fmod(a, b); }
+
+// torm/include/torm/torm_utils.h:79-100
+template <typename T> RLITG_DEV T normalize_angle_positive(T a) {
+    const T two_pi = T(2.0 * 3.14159265358979323846);
+    return fmod_t(fmod_t(a, two_pi) + two_pi, two_pi);
+}
+template <typename T> RLITG_DEV T shortest_angular_distance(T start, T end) {
+    const T pi = T(3.14159265358979323846), two_pi = T(2.0 * 3.14159265358979323846);
+    T res = normalize_angle_positive(normalize_angle_positive(end) - normalize_angle_positive(start));
+    if (res > pi) res = -(two_pi - res);
+    T a = normalize_angle_positive(res);
+    if (a > pi) a -= two_pi;
+    return a;
+}
+
+// getPotential torm/include/torm/torm_optimizer.h:146-168 (diff * clearance)
+template <typename T> RLITG_DEV T get_potential(T field_distance, T radius, T clearance) {
+    const T d = field_distance - radius;
+    if (d >= clearance) return T(0);
+    if (d >= T(0)) {
+        const T diff = d - clearance;
+        const T gm = diff * clearance;
+        return T(0.5) * gm * diff;
+    }
+    return -d + T(0.5) * clearance;
+}
+
+template <typename T>
+struct TormVisit {
+    FkJac<T, 7> fj;
+    T* sph_row;  // shared-memory row [S][3] of this waypoint's sphere centres (planning frame); nullptr = skip
+    const float4* sph;
+    const int* link_start;
+    V3<T> off;
+    template <int K>
+    RLITG_DEV void operator()(jidx<K> k, const FrameC<T>& f) {
+        fj(k, f);
+        if (sph_row != nullptr) {
+            for (int s = link_start[K]; s < link_start[K + 1]; s++) {
+                const float4 c = sph[s];
+                sph_row[3 * s + 0] = off.x + f.p.x + f.c0.x * T(c.x) + f.c1.x * T(c.y) + f.c2.x * T(c.z);
+                sph_row[3 * s + 1] = off.y + f.p.y + f.c0.y * T(c.x) + f.c1.y * T(c.y) + f.c2.y * T(c.z);
+                sph_row[3 * s + 2] = off.z + f.p.z + f.c0.z * T(c.x) + f.c1.z * T(c.y) + f.c2.z * T(c.z);
+            }
+        }
+    }
+};
+
+template <typename T>
+struct EeOnly {  // midpoint FK needs the end-effector frame only
+    FrameC<T> ee;
+    template <int K>
+    RLITG_DEV void operator()(jidx<K>, const FrameC<T>& f) {
+        if constexpr (K == 7) ee = f;
+    }
+};
+
+template <typename T>
+RLITG_DEV void target_frame(const T* __restrict__ t7, V3<T>& p, V3<T>& c0, V3<T>& c1, V3<T>& c2) {
+    p = {t7[0], t7[1], t7[2]};
+    quat_to_rot_kdl(t7[3], t7[4], t7[5], t7[6], c0, c1, c2);
+}
+
+// setInterTargetPoses torm/src/utils/traj_evaluator.cpp:244-257: mean position, R_a * Rot2(axis, angle / 2)
+template <typename T>
+RLITG_DEV void inter_target(const T* __restrict__ a7, const T* __restrict__ b7, V3<T>& p, V3<T>& c0, V3<T>& c1, V3<T>& c2) {
+    V3<T> pa, a0, a1, a2, pb, b0, b1, b2;
+    target_frame(a7, pa, a0, a1, a2);
+    target_frame(b7, pb, b0, b1, b2);
+    p = {(pb.x + pa.x) / T(2), (pb.y + pa.y) / T(2), (pb.z + pa.z) / T(2)};
+    // rel = A^T B ; axis-angle by the same GetRotAngle branches as rot_diff_kdl
+    const T m00 = dot(a0, b0), m01 = dot(a0, b1), m02 = dot(a0, b2);
+    const T m10 = dot(a1, b0), m11 = dot(a1, b1), m12 = dot(a1, b2);
+    const T m20 = dot(a2, b0), m21 = dot(a2, b1), m22 = dot(a2, b2);
+    T x = m21 - m12, y = m02 - m20, z = m10 - m01, angle;
+    const T eps = T(1e-6), eps2 = T(1e-5);
+    if (abs_t(x) < eps && abs_t(y) < eps && abs_t(z) < eps) {
+        if (abs_t(m01 + m10) < eps2 && abs_t(m02 + m20) < eps2 && abs_t(m12 + m21) < eps2 &&
+            abs_t(m00 + m11 + m22 - T(3)) < eps2) {
+            x = T(0); y = T(0); z = T(1); angle = T(0);
+        } else {
+            const T xx = (m00 + T(1)) / T(2), yy = (m11 + T(1)) / T(2), zz = (m22 + T(1)) / T(2);
+            const T xy = (m01 + m10) / T(4), xz = (m02 + m20) / T(4), yz = (m12 + m21) / T(4);
+            if (xx > yy && xx > zz) { x = sqrt_t(xx); y = xy / x; z = xz / x; }
+            else if (yy > zz) { y = sqrt_t(yy); x = xy / y; z = yz / y; }
+            else { z = sqrt_t(zz); x = xz / z; y = yz / z; }
+            angle = T(3.14159265358979323846);
+        }
+    } else {
+        const T f = (m00 + m11 + m22 - T(1)) / T(2);
+        const T r = sqrt_t(x * x + y * y + z * z);
+        angle = atan2_t(r / T(2), f);
+        x /= r; y /= r; z /= r;
+    }
+    // KDL Rotation::Rot2(axis, angle / 2)
+    T st, ct;
+    sincos_joint(angle / T(2), st, ct);
+    const T vt = T(1) - ct;
+    const T h00 = ct + vt * x * x, h01 = -z * st + vt * x * y, h02 = y * st + vt * x * z;
+    const T h10 = z * st + vt * x * y, h11 = ct + vt * y * y, h12 = -x * st + vt * y * z;
+    const T h20 = -y * st + vt * x * z, h21 = x * st + vt * y * z, h22 = ct + vt * z * z;
+    // C = A * H : column j of C = a0 h0j + a1 h1j + a2 h2j
+    c0 = {a0.x * h00 + a1.x * h10 + a2.x * h20, a0.y * h00 + a1.y * h10 + a2.y * h20, a0.z * h00 + a1.z * h10 + a2.z * h20};
+    c1 = {a0.x * h01 + a1.x * h11 + a2.x * h21, a0.y * h01 + a1.y * h11 + a2.y * h21, a0.z * h01 + a1.z * h11 + a2.z * h21};
+    c2 = {a0.x * h02 + a1.x * h12 + a2.x * h22, a0.y * h02 + a1.y * h12 + a2.y * h22, a0.z * h02 + a1.z * h12 + a2.z * h22};
+}
+
+RLITG_DEV void mat3_inverse_d(const double (&m)[9], double (&inv)[9]) {
+    const double det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) +
+                       m[2] * (m[3] * m[7] - m[4] * m[6]);
+    const double id = 1.0 / det;
+    inv[0] = (m[4] * m[8] - m[5] * m[7]) * id; inv[1] = (m[2] * m[7] - m[1] * m[8]) * id; inv[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+    inv[3] = (m[5] * m[6] - m[3] * m[8]) * id; inv[4] = (m[0] * m[8] - m[2] * m[6]) * id; inv[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+    inv[6] = (m[3] * m[7] - m[4] * m[6]) * id; inv[7] = (m[1] * m[6] - m[0] * m[7]) * id; inv[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kTormMaxThreads, 2)
+torm_kernel(TormP<T> P, const T* __restrict__ traj, const T* __restrict__ targets, SceneDev sc, int S,
+            const T* __restrict__ Aband, int stage_mask, const int32_t* __restrict__ stoch,
+            T* __restrict__ inc_smooth, T* __restrict__ inc_coll, T* __restrict__ inc_pose, T* __restrict__ costs,
+            float* __restrict__ active) {
+    const int CH = blockDim.x, tid = threadIdx.x, Tn = P.Tn;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* s_traj = reinterpret_cast<T*>(smem_raw);       // [(CH + 12)][7]  rows c0-6 .. c0+CH+5, clamped
+    T* s_v = s_traj + (CH + 12) * 7;                  // [(CH + 3)][7]   first differences of continuous joints
+    T* s_red = s_v + (CH + 3) * 7;                    // [8][kNRed]
+    T* s_pos = s_red + 8 * kNRed;                     // [(CH + 6)][S][3] rows c0-3 .. c0+CH+2
+    __shared__ float4 s_sph[kMaxSpheres];
+    __shared__ int s_start[kNumLinks + 1];
+
+    const bool do_coll = (stage_mask & RLITG_STAGE_COLL) != 0;
+    const bool do_pose = (stage_mask & (RLITG_STAGE_POSE | RLITG_STAGE_POSE_GRAD | RLITG_STAGE_EVAL)) != 0;
+    const bool do_pgrad = (stage_mask & RLITG_STAGE_POSE_GRAD) != 0;
+    const bool do_smooth = (stage_mask & RLITG_STAGE_SMOOTH) != 0;
+    const bool do_eval = (stage_mask & RLITG_STAGE_EVAL) != 0;
+    if (do_coll) {
+        for (int i = tid; i < S; i += CH) s_sph[i] = sc.spheres[i];
+        if (tid <= kNumLinks) s_start[tid] = sc.link_start[tid];
+    }
+    const int64_t n = blockIdx.x;
+    const T* tr = traj + n * (int64_t)Tn * 7;
+    const int F = Tn - 1;
+    T* o_smooth = inc_smooth ? inc_smooth + n * (int64_t)F * 7 : nullptr;
+    T* o_coll = inc_coll ? inc_coll + n * (int64_t)F * 7 : nullptr;
+    T* o_pose = inc_pose ? inc_pose + n * (int64_t)F * 7 : nullptr;
+    const int stoch_row = stoch ? stoch[n] + 1 : -1;  // full-trajectory row of the single stochastic waypoint
+    const V3<T> off = {P.off[0], P.off[1], P.off[2]};
+    const GridMap<T> gm(sc);
+
+    T red[kNRed];
+#pragma unroll
+    for (int k = 0; k < kNRed; k++) red[k] = T(0);
+
+    for (int c0 = 0; c0 < Tn; c0 += CH) {
+        __syncthreads();
+        for (int idx = tid; idx < (CH + 12) * 7; idx += CH) {
+            const int r = idx / 7, j = idx - r * 7;
+            const int src = min(max(c0 - 6 + r, 0), Tn - 1);
+            s_traj[idx] = tr[src * 7 + j];
+        }
+        __syncthreads();
+        const int i = c0 + tid;
+        const bool valid = i < Tn;
+#define TROW(row) (s_traj + (min(max((row), 0), Tn - 1) - c0 + 6) * 7)
+#define PROW(row) (s_pos + (size_t)(min(max((row), 0), Tn - 1) - c0 + 3) * S * 3)
+
+        // ---- phase 1: FK of this row (+ halo rows for the sphere stencils of a chunked path)
+        TormVisit<T> v;
+        v.sph = s_sph; v.link_start = s_start; v.off = off;
+        v.sph_row = nullptr;
+        T q[7];
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < 7; j++) q[j] = TROW(i)[j];
+            v.sph_row = do_coll ? PROW(i) : nullptr;
+            walk_chain<T, 7>(q, v);
+        }
+        if (do_coll && tid < 6) {
+            const int hr = tid < 3 ? c0 - 3 + tid : c0 + CH + (tid - 3);
+            if (hr >= 0 && hr < Tn) {
+                TormVisit<T> hv;
+                hv.sph = s_sph; hv.link_start = s_start; hv.off = off;
+                hv.sph_row = PROW(hr);
+                T hq[7];
+#pragma unroll
+                for (int j = 0; j < 7; j++) hq[j] = TROW(hr)[j];
+                walk_chain<T, 7>(hq, hv);
+            }
+        }
+
+        // ---- end-pose error at the waypoint: getEndPoseCost :1399-1425
+        if (do_pose && valid && i >= 1) {
+            V3<T> tp, t0, t1, t2;
+            target_frame(targets + i * 7, tp, t0, t1, t2);
+            T angle;
+            const V3<T> rv = rot_diff_kdl(v.fj.ee.c0, v.fj.ee.c1, v.fj.ee.c2, t0, t1, t2, angle);
+            const V3<T> dp = tp - v.fj.ee.p;
+            red[R_WP_POS] += sqrt_t(dot(dp, dp));
+            red[R_WP_ROT] += sqrt_t(dot(rv, rv));
+            if (do_pgrad && o_pose) {
+                T J[42], dq[7];
+                fill_jac<T, 7>(v.fj, J);
+                const T tw[6] = {dp.x, dp.y, dp.z, rv.x, rv.y, rv.z};
+                pinv_apply<T, 7, sizeof(T) == 8>(J, tw, P.vik_eps, dq);
+#pragma unroll
+                for (int j = 0; j < 7; j++) o_pose[(i - 1) * 7 + j] = P.jac_w * dq[j];
+            }
+        }
+
+        // ---- first differences of continuous joints for the evaluator (:164-181), shared with neighbours
+        if (do_eval) {
+            for (int e = tid; e < CH + 3; e += CH) {
+                const int r = c0 + e;
+#pragma unroll
+                for (int j = 0; j < 7; j++) {
+                    T val = T(0);
+                    if (P.cj[j] && r < Tn - 1) val = shortest_angular_distance(TROW(r)[j], TROW(r + 1)[j]) / P.dt;
+                    s_v[e * 7 + j] = val;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 2: collision potentials, cost, CHOMP increments
+        if (do_coll && valid) {
+            T acc[7];
+#pragma unroll
+            for (int j = 0; j < 7; j++) acc[j] = T(0);
+            const bool inc_row = (i >= 1) && (stoch_row < 0 || stoch_row == i) && (o_coll != nullptr);
+            const T* prow = PROW(i);
+            T csum = T(0);
+            int nact = 0;
+            for (int K = 0; K < kNumLinks; K++) {
+                const int nanc = K + 1 < 7 ? K + 1 : 7;
+                for (int s = s_start[K]; s < s_start[K + 1]; s++) {
+                    const V3<T> x = {prow[3 * s], prow[3 * s + 1], prow[3 * s + 2]};
+                    T d;
+                    V3<T> g;
+                    if (!field_lookup(sc, gm, x, d, g)) continue;
+                    const T pot = get_potential(d, T(s_sph[s].w), P.clearance);
+                    csum += pot;
+                    if (!inc_row || pot < T(0.0001)) continue;
+                    nact++;
+                    V3<T> vel = {T(0), T(0), T(0)}, ac = {T(0), T(0), T(0)};
+#pragma unroll
+                    for (int k = -3; k <= 3; k++) {
+                        const T* pr = PROW(i + k) + 3 * s;
+                        const V3<T> xk = {pr[0], pr[1], pr[2]};
+                        vel = axpy(vel, P.inv_dt * diff_rule<T>(0, k + 3), xk);
+                        ac = axpy(ac, P.inv_dt2 * diff_rule<T>(1, k + 3), xk);
+                    }
+                    const T vel_mag = sqrt_t(dot(vel, vel));
+                    const T vel_mag_sq = vel_mag * vel_mag;
+                    const V3<T> nv = vel * (T(1) / vel_mag);
+                    const V3<T> pg = {-g.x, -g.y, -g.z};
+                    // orthogonal projector P = I - nv nv^T
+                    const V3<T> Pa = axpy(ac, -dot(nv, ac), nv);
+                    const V3<T> Pg = axpy(pg, -dot(nv, pg), nv);
+                    const V3<T> curv = Pa * (T(1) / vel_mag_sq);
+                    const V3<T> cg = (Pg - curv * pot) * vel_mag;
+                    // 3 x nanc positional Jacobian (getJacobian :1164-1187)
+                    V3<T> col[7];
+#pragma unroll
+                    for (int j = 0; j < 7; j++) {
+                        const V3<T> oj = v.fj.o[j] + off;
+                        const V3<T> ax = P.quirk ? v.fj.z[j] + oj : v.fj.z[j];
+                        col[j] = (j < nanc) ? cross(ax, x - oj) : V3<T>{T(0), T(0), T(0)};
+                    }
+                    if (P.use_pinv) {
+                        // calculatePseudoInverse :767-772 : J^T (J J^T + ridge I)^-1, 3x3 algebra in FP64
+                        double M[9] = {P.ridge, 0, 0, 0, P.ridge, 0, 0, 0, P.ridge}, Mi[9];
+#pragma unroll
+                        for (int j = 0; j < 7; j++) {
+                            const double cx = (double)col[j].x, cy = (double)col[j].y, cz = (double)col[j].z;
+                            M[0] += cx * cx; M[1] += cx * cy; M[2] += cx * cz;
+                            M[4] += cy * cy; M[5] += cy * cz; M[8] += cz * cz;
+                        }
+                        M[3] = M[1]; M[6] = M[2]; M[7] = M[5];
+                        mat3_inverse_d(M, Mi);
+                        const double y0 = Mi[0] * (double)cg.x + Mi[1] * (double)cg.y + Mi[2] * (double)cg.z;
+                        const double y1 = Mi[3] * (double)cg.x + Mi[4] * (double)cg.y + Mi[5] * (double)cg.z;
+                        const double y2 = Mi[6] * (double)cg.x + Mi[7] * (double)cg.y + Mi[8] * (double)cg.z;
+#pragma unroll
+                        for (int j = 0; j < 7; j++)
+                            acc[j] -= (T)((double)col[j].x * y0 + (double)col[j].y * y1 + (double)col[j].z * y2);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 7; j++) acc[j] -= dot(col[j], cg);
+                    }
+                }
+            }
+            red[R_COLL] += csum;
+            red[R_NACTIVE] += T(nact);
+            if (i >= 1 && o_coll) {
+#pragma unroll
+                for (int j = 0; j < 7; j++) o_coll[(i - 1) * 7 + j] = acc[j];
+            }
+        }
+
+        // ---- smoothness increments: -(2 A_full x) on the free rows (:1466-1473); group row g = i + 5
+        if (do_smooth && valid && i >= 1 && o_smooth) {
+            const T* ab = Aband + (size_t)(i + 5) * 13;
+            T coef[13];
+#pragma unroll
+            for (int k = 0; k < 13; k++) coef[k] = ab[k];
+#pragma unroll
+            for (int j = 0; j < 7; j++) {
+                T s = T(0);
+#pragma unroll
+                for (int k = 0; k < 13; k++) s += coef[k] * (T(2) * TROW(i + k - 6)[j]);
+                o_smooth[(i - 1) * 7 + j] = -s;
+            }
+        }
+
+        // ---- evaluator: midpoint pose error + joint derivative costs + velocity violations
+        if (do_eval && valid) {
+            if (i < Tn - 1) {
+                T qm[7];
+#pragma unroll
+                for (int j = 0; j < 7; j++) qm[j] = (TROW(i + 1)[j] + q[j]) / T(2);
+                EeOnly<T> ev;
+                walk_chain<T, 7>(qm, ev);
+                V3<T> ip, i0, i1, i2;
+                inter_target(targets + i * 7, targets + (i + 1) * 7, ip, i0, i1, i2);
+                T angle;
+                const V3<T> rv = rot_diff_kdl(ev.ee.c0, ev.ee.c1, ev.ee.c2, i0, i1, i2, angle);
+                const V3<T> dp = ip - ev.ee.p;
+                red[R_MID_POS] += sqrt_t(dot(dp, dp));
+                red[R_MID_ROT] += sqrt_t(dot(rv, rv));
+            }
+            bool viol = false;
+#pragma unroll
+            for (int j = 0; j < 7; j++) {
+                if (P.cj[j]) {
+                    const T* sv = s_v + tid * 7 + j;
+                    const T v0 = sv[0], v1 = sv[7], v2 = sv[14];
+                    const T a0 = (v1 - v0) / P.dt, a1 = (v2 - v1) / P.dt;
+                    if (i < Tn - 1) red[R_VEL_C] += abs_t(v0);
+                    if (i < Tn - 2) red[R_ACC_C] += abs_t(a0);
+                    if (i < Tn - 3) red[R_JERK_C] += abs_t((a1 - a0) / P.dt);
+                    if (i < Tn - 1 && abs_t(v0) > P.vlim[j]) viol = true;
+                } else {
+                    T sv = T(0), sa = T(0), sj = T(0);
+#pragma unroll
+                    for (int k = -3; k <= 3; k++) {
+                        const T xk = TROW(i + k)[j];
+                        sv += P.rule_v[k + 3] * xk; sa += P.rule_a[k + 3] * xk; sj += P.rule_j[k + 3] * xk;
+                    }
+                    red[R_VEL_N] += abs_t(sv); red[R_ACC_N] += abs_t(sa); red[R_JERK_N] += abs_t(sj);
+                    if (i < Tn - 1 && abs_t(TROW(i + 1)[j] - q[j]) / P.dt > P.vlim[j]) viol = true;
+                }
+            }
+            if (viol) red[R_NVIOL] += T(1);
+        }
+#undef TROW
+#undef PROW
+    }
+
+    // ---- block reduction of the cost sums
+#pragma unroll
+    for (int k = 0; k < kNRed; k++) {
+        T x = red[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        red[k] = x;
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31, nwarps = (CH + 31) >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < kNRed; k++) s_red[warp * kNRed + k] = red[k];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        T tot[kNRed];
+        for (int k = 0; k < kNRed; k++) {
+            T x = T(0);
+            for (int w = 0; w < nwarps; w++) x += s_red[w * kNRed + k];
+            tot[k] = x;
+        }
+        T* c = costs + n * RLITG_TORM_NCOST;
+        const T tm1 = T(Tn - 1);
+        T ev_pos = T(0), ev_rot = T(0), cvel = T(0), cacc = T(0), cjerk = T(0), nviol = T(0);
+        if (do_eval) {
+            ev_pos = (tot[R_WP_POS] + tot[R_MID_POS]) / (tm1 * T(2));
+            ev_rot = (tot[R_WP_ROT] + tot[R_MID_ROT]) / (tm1 * T(2));
+            cvel = (tot[R_VEL_C] / tm1 + tot[R_VEL_N] / T(Tn)) / T(7);
+            cacc = (tot[R_ACC_C] / T(Tn - 2) + tot[R_ACC_N] / T(Tn)) / T(7);
+            cjerk = (tot[R_JERK_C] / T(Tn - 3) + tot[R_JERK_N] / T(Tn)) / T(7);
+            nviol = tot[R_NVIOL];
+        }
+        c[0] = ev_pos; c[1] = ev_rot; c[2] = cvel; c[3] = cacc; c[4] = cjerk;
+        c[5] = do_coll ? tot[R_COLL] / T(Tn) : T(0);
+        c[6] = do_eval ? ev_pos + T(0.17) * ev_rot : T(0);  // getWeightedPoseCost :59-63
+        c[7] = nviol;
+        c[8] = do_pose ? tot[R_WP_POS] : T(0);
+        c[9] = do_pose ? tot[R_WP_ROT] : T(0);
+        if (active) {
+            const int rows = (stoch_row >= 0) ? 1 : Tn - 1;
+            active[n] = do_coll ? (float)(tot[R_NACTIVE] / T(rows)) : 0.f;
+        }
+    }
+}
+
+// ---- smoothness operator (host, FP64): TormCost ctor + scaling -------------------------------------------
+struct Smooth {
+    int T = 0;
+    double scale = 0;               // max coefficient of the unscaled inverse
+    std::vector<double> band;       // [(T+10)][13], scaled
+    std::vector<double> inv;        // [(T-1)][(T-1)], scaled
+    double* d_band64 = nullptr;
+    float* d_band32 = nullptr;
+    double* d_inv64 = nullptr;      // device copies of the inverse, made on demand by the update step
+    float* d_inv32 = nullptr;
+};
+
+static const double kRules[3][7] = {{-1.0 / 60, 3.0 / 20, -3.0 / 4, 0.0, 3.0 / 4, -3.0 / 20, 1.0 / 60},
+                                    {1.0 / 90, -3.0 / 20, 3.0 / 2, -49.0 / 18, 3.0 / 2, -3.0 / 20, 1.0 / 90},
+                                    {1.0 / 8, -1.0, 13.0 / 8, 0.0, -13.0 / 8, 1.0, -1.0 / 8}};
+
+static int smooth_build(Smooth& sm, int T, double dt, const double* w3, double ridge) {
+    const int G = T + 10, F = T - 1, o = 6;
+    // A_full = sum_d w_d dt^(d+1) D_d^T D_d + ridge I, kept as a 13-band (half bandwidth 6)
+    std::vector<double> band((size_t)G * 13, 0.0);
+    auto B = [&](int i, int j) -> double& { return band[(size_t)i * 13 + (j - i + 6)]; };
+    double mult = 1.0;
+    for (int d = 0; d < 3; d++) {
+        mult *= dt;
+        const double coef = w3[d] * mult;
+        if (coef == 0.0) continue;
+        for (int r = 0; r < G; r++)
+            for (int a = -3; a <= 3; a++) {
+                const int ca = r + a;
+                if (ca < 0 || ca >= G) continue;
+                for (int b = -3; b <= 3; b++) {
+                    const int cb = r + b;
+                    if (cb < 0 || cb >= G) continue;
+                    B(ca, cb) += coef * (kRules[d][a + 3] * kRules[d][b + 3]);
+                }
+            }
+    }
+    for (int i = 0; i < G; i++) B(i, i) += ridge;
+    // banded Cholesky of the free block A_free = A_full[6 : 6+F, 6 : 6+F] (SPD, half bandwidth 6)
+    const int hb = 6;
+    std::vector<double> L((size_t)F * (hb + 1), 0.0);  // L(i, j) for i-hb <= j <= i at L[i*(hb+1) + (j - i + hb)]
+    auto Lr = [&](int i, int j) -> double& { return L[(size_t)i * (hb + 1) + (j - i + hb)]; };
+    for (int i = 0; i < F; i++) {
+        for (int j = std::max(0, i - hb); j <= i; j++) {
+            double s = B(i + o, j + o);
+            for (int k = std::max(0, i - hb); k < j; k++)
+                if (k >= j - hb) s -= Lr(i, k) * Lr(j, k);
+            if (i == j) {
+                if (!(s > 0.0)) return set_error(RLITG_ERR_ARG, "smoothness matrix is not positive definite (all weights zero?)");
+                Lr(i, i) = std::sqrt(s);
+            } else {
+                Lr(i, j) = s / Lr(j, j);
+            }
+        }
+    }
+    sm.inv.assign((size_t)F * F, 0.0);
+    std::vector<double> y(F);
+    double mx = -1e300;
+    for (int c = 0; c < F; c++) {
+        for (int i = 0; i < F; i++) {
+            double s = (i == c) ? 1.0 : 0.0;
+            for (int k = std::max(0, i - hb); k < i; k++) s -= Lr(i, k) * y[k];
+            y[i] = s / Lr(i, i);
+        }
+        for (int i = F - 1; i >= 0; i--) {
+            double s = y[i];
+            for (int k = i + 1; k <= std::min(F - 1, i + hb); k++) s -= Lr(k, i) * y[k];
+            y[i] = s / Lr(i, i);
+        }
+        for (int i = 0; i < F; i++) {
+            sm.inv[(size_t)i * F + c] = y[i];
+            mx = std::max(mx, y[i]);
+        }
+    }
+    sm.scale = mx;
+    const double mcs = std::max(1.0, mx);  // max_cost_scale starts at 1.0 (torm_optimizer.cpp:211)
+    for (auto& x : band) x *= mcs;
+    for (auto& x : sm.inv) x /= mcs;
+    sm.band.swap(band);
+    sm.T = T;
+    return RLITG_OK;
+}
+
+const double* smooth_inv_host(const Smooth* s) { return s->inv.data(); }
+int smooth_T(const Smooth* s) { return s->T; }
+
+template <typename T>
+static TormP<T> convert_params(const RlitgTormParams& p) {
+    TormP<T> o;
+    o.Tn = p.T;
+    o.dt = (T)p.dt; o.inv_dt = (T)(1.0 / p.dt); o.inv_dt2 = (T)((1.0 / p.dt) * (1.0 / p.dt));
+    o.rot_scale = (T)p.rot_scale; o.jac_w = (T)p.jac_weight; o.clearance = (T)p.clearance;
+    o.ridge = p.pinv_ridge; o.vik_eps = p.vik_eps;
+    o.use_pinv = p.use_pinv; o.quirk = p.affine_axis_quirk;
+    for (int k = 0; k < 3; k++) o.off[k] = (T)p.base_off[k];
+    for (int j = 0; j < 7; j++) { o.cj[j] = p.cjoint[j]; o.vlim[j] = (T)p.vel_limit[j]; }
+    for (int k = 0; k < 7; k++) {
+        o.rule_v[k] = (T)(kRules[0][k] / std::pow(p.dt, 1));
+        o.rule_a[k] = (T)(kRules[1][k] / std::pow(p.dt, 2));
+        o.rule_j[k] = (T)(kRules[2][k] / std::pow(p.dt, 3));
+    }
+    return o;
+}
+
+template <typename T>
+static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* scene, const Smooth* smooth,
+                       const RlitgTormParams* p, int stage_mask, const int32_t* stoch, T* inc_smooth, T* inc_coll,
+                       T* inc_pose, T* costs, float* active, cudaStream_t st) {
+    TormP<T> P = convert_params<T>(*p);
+    SceneDev sd{};
+    int S = 0;
+    if (stage_mask & RLITG_STAGE_COLL) {
+        sd = scene_dev(scene);
+        S = sd.S;
+    }
+    const int CH = std::min(kTormMaxThreads, ((p->T + 31) / 32) * 32);
+    const size_t smem = sizeof(T) * ((size_t)(CH + 12) * 7 + (size_t)(CH + 3) * 7 + 8 * kNRed + (size_t)(CH + 6) * S * 3);
+    if (smem > 220 * 1024) return set_error(RLITG_ERR_SHAPE, "too many spheres for the shared-memory tile");
+    auto kern = torm_kernel<T>;
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return set_cuda_error("cudaFuncSetAttribute(torm_kernel)");
+        attr_smem = smem;
+    }
+    const T* band = nullptr;
+    if (stage_mask & RLITG_STAGE_SMOOTH)
+        band = reinterpret_cast<const T*>(sizeof(T) == 4 ? (const void*)smooth->d_band32 : (const void*)smooth->d_band64);
+    kern<<<(unsigned)N, CH, smem, st>>>(P, traj, targets, sd, S, band, stage_mask, stoch, inc_smooth, inc_coll, inc_pose,
+                                        costs, active);
+    return check_launch("torm_kernel");
+}
+
+}  // namespace rlitg
+
+using namespace rlitg;
+
+extern "C" {
+
+RLITG_API int rlitg_smooth_create(int T, double dt, const double* w3, double ridge, RlitgSmooth** out) {
+    if (!out || !w3) return set_error(RLITG_ERR_NULL, "out / w3 is NULL");
+    if (T < 5 || T > 8192) return set_error(RLITG_ERR_SHAPE, "T must be in 5..8192");
+    if (!(dt > 0)) return set_error(RLITG_ERR_ARG, "dt must be > 0");
+    Smooth* s = new Smooth();
+    int rc = smooth_build(*s, T, dt, w3, ridge);
+    if (rc) { delete s; return rc; }
+    const size_t nb = s->band.size();
+    std::vector<float> b32(nb);
+    for (size_t i = 0; i < nb; i++) b32[i] = (float)s->band[i];
+    if (cudaMalloc(&s->d_band64, nb * 8) != cudaSuccess || cudaMalloc(&s->d_band32, nb * 4) != cudaSuccess ||
+        cudaMemcpy(s->d_band64, s->band.data(), nb * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(s->d_band32, b32.data(), nb * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+        rc = set_cuda_error("rlitg_smooth_create");
+        rlitg_smooth_destroy(reinterpret_cast<RlitgSmooth*>(s));
+        return rc;
+    }
+    *out = reinterpret_cast<RlitgSmooth*>(s);
+    return RLITG_OK;
+}
+
+RLITG_API int rlitg_smooth_destroy(RlitgSmooth* h) {
+    Smooth* s = reinterpret_cast<Smooth*>(h);
+    if (!s) return RLITG_OK;
+    if (s->d_band64) cudaFree(s->d_band64);
+    if (s->d_band32) cudaFree(s->d_band32);
+    if (s->d_inv64) cudaFree(s->d_inv64);
+    if (s->d_inv32) cudaFree(s->d_inv32);
+    delete s;
+    return RLITG_OK;
+}
+
+RLITG_API int rlitg_smooth_get(const RlitgSmooth* h, double* Aband, double* scale, double* Ainv) {
+    const Smooth* s = reinterpret_cast<const Smooth*>(h);
+    if (!s) return set_error(RLITG_ERR_NULL, "smooth handle is NULL");
+    if (Aband) std::copy(s->band.begin(), s->band.end(), Aband);
+    if (scale) *scale = s->scale;
+    if (Ainv) std::copy(s->inv.begin(), s->inv.end(), Ainv);
+    return RLITG_OK;
+}
+
+RLITG_API int rlitg_torm_cost_grad(const void* traj, const void* targets, int64_t N, int dtype,
+                                   const RlitgScene* scene, const RlitgSmooth* smooth, const RlitgTormParams* p,
+                                   int stage_mask, const int32_t* stochastic_idx, void* inc_smooth, void* inc_coll,
+                                   void* inc_pose, void* costs, float* active, void* stream) {
+    if (!p) return set_error(RLITG_ERR_NULL, "params is NULL");
+    if (p->D != 7) return set_error(RLITG_ERR_SHAPE, "TORM runs the 7-joint arm chain (D = 7)");
+    if (p->T < 5 || p->T > 8192) return set_error(RLITG_ERR_SHAPE, "T must be in 5..8192");
+    if (N < 0 || N > 0x7fffffff) return set_error(RLITG_ERR_SHAPE, "N out of range");
+    if (dtype != RLITG_F32 && dtype != RLITG_F64) return set_error(RLITG_ERR_DTYPE, "dtype must be RLITG_F32 or RLITG_F64");
+    if (N == 0) return RLITG_OK;
+    if (!traj || !targets || !costs) return set_error(RLITG_ERR_NULL, "traj / targets / costs is NULL");
+    const Scene* sc = reinterpret_cast<const Scene*>(scene);
+    const Smooth* sm = reinterpret_cast<const Smooth*>(smooth);
+    if ((stage_mask & RLITG_STAGE_COLL) && !scene_ready(sc, true, true))
+        return set_error(RLITG_ERR_ARG, "the collision stage needs a scene with a grid and a sphere table");
+    if (stage_mask & RLITG_STAGE_SMOOTH) {
+        if (!sm || !inc_smooth) return set_error(RLITG_ERR_NULL, "the smoothness stage needs a smooth handle and inc_smooth");
+        if (smooth_T(sm) != p->T) return set_error(RLITG_ERR_SHAPE, "smooth handle was built for a different T");
+    }
+    if ((stage_mask & RLITG_STAGE_POSE_GRAD) && !inc_pose) return set_error(RLITG_ERR_NULL, "inc_pose is NULL");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == RLITG_F32)
+        return launch_torm<float>((const float*)traj, (const float*)targets, N, sc, sm, p, stage_mask, stochastic_idx,
+                                  (float*)inc_smooth, (float*)inc_coll, (float*)inc_pose, (float*)costs, active, st);
+    return launch_torm<double>((const double*)traj, (const double*)targets, N, sc, sm, p, stage_mask, stochastic_idx,
+                               (double*)inc_smooth, (double*)inc_coll, (double*)inc_pose, (double*)costs, active, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,206 @@
+"""TORM path-following cost / gradient terms on the GPU, batched over N candidate trajectories.
+
+Python facade with the reference's member names (TormOptimizer, torm/include/torm/torm_optimizer.h:295-312;
+traj_evaluator, torm/include/torm/traj_evaluator.h:12-41; TormCost, torm/include/torm/torm_cost.h:49-77), each
+taking / returning tensors with a leading batch axis N.  All of them run rlitg_torm_cost_grad (one kernel launch,
+one CTA per trajectory) with the matching stage mask.
+
+Trajectories are [N,T,7] with row 0 the (fixed) start configuration -- the reference's full_trajectory_; its padded
+group_trajectory_ ([T+10,7], five clamped rows each side, torm/src/torm_trajectory.cpp:59-97) is implicit.
+Increments are [N,T-1,7] over the free waypoints, like the reference's *_increments_ matrices."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib, fetch
+from ._lib import check, lib
+
+STAGE_POSE, STAGE_POSE_GRAD, STAGE_SMOOTH, STAGE_COLL, STAGE_EVAL = 1, 2, 4, 8, 16
+NCOST = 10
+COST_NAMES = ("pose", "rot", "vel", "acc", "jerk", "collision", "weighted", "n_vel_violation", "endpose_pos_sum",
+              "endpose_rot_sum")
+
+
+class RlitgTormParams(C.Structure):
+    _fields_ = [("T", C.c_int32), ("D", C.c_int32), ("dt", C.c_double), ("rot_scale", C.c_double),
+                ("jac_weight", C.c_double), ("clearance", C.c_double), ("pinv_ridge", C.c_double),
+                ("vik_eps", C.c_double), ("use_pinv", C.c_int32), ("affine_axis_quirk", C.c_int32),
+                ("base_off", C.c_double * 3), ("cjoint", C.c_int32 * 8), ("vel_limit", C.c_double * 8)]
+
+
+_vp = C.c_void_p
+lib.rlitg_smooth_create.argtypes = [C.c_int, C.c_double, _vp, C.c_double, C.POINTER(_vp)]
+lib.rlitg_smooth_destroy.argtypes = [_vp]
+lib.rlitg_smooth_get.argtypes = [_vp, _vp, C.POINTER(C.c_double), _vp]
+lib.rlitg_torm_cost_grad.argtypes = [_vp, _vp, C.c_int64, C.c_int, _vp, _vp, C.POINTER(RlitgTormParams), C.c_int, _vp,
+                                     _vp, _vp, _vp, _vp, _vp, _vp]
+
+
+@dataclass
+class TormParameters:
+    """torm/include/torm/torm_parameters.h:53-85; defaults = torm/src/torm_main.cpp:50-92."""
+    planning_time_limit_: float = 1.0
+    smoothness_update_weight_: float = 30.0  # divided by T by the mains
+    obstacle_update_weight_: float = 1.0
+    jacobian_update_weight_: float = 1.0
+    learning_rate_: float = 0.01
+    pose_cost_weight_: float = 1.0
+    collision_cost_weight_: float = 0.05
+    rotation_scale_factor_: float = 0.17
+    smoothness_cost_velocity_: float = 1.0
+    smoothness_cost_acceleration_: float = 0.0
+    smoothness_cost_jerk_: float = 0.0
+    use_stochastic_descent_: bool = True
+    use_velocity_check_: bool = True
+    use_singularity_check_: bool = False
+    use_collision_check_: bool = True
+    ridge_factor_: float = 0.0
+    use_pseudo_inverse_: bool = True
+    pseudo_inverse_ridge_factor_: float = 1e-4
+    joint_update_limit_: float = 0.17
+    min_clearence_: float = 0.001
+    exploration_iter_: int = 100
+    traj_generation_iter_: int = 50
+    time_duration_: float = 0.1
+    singularity_lower_bound_: float = 0.005
+    # build-side switches
+    affine_axis_quirk: bool = True
+    vik_eps: float = 1e-5
+    base_offset: tuple = tuple(fetch.BASE_OFFSET)
+    continuous: tuple = tuple(int(v) for v in fetch.CONTINUOUS)
+    vel_limit: tuple = tuple(fetch.VEL_LIMIT)
+
+    def to_c(self, T: int) -> RlitgTormParams:
+        p = RlitgTormParams()
+        p.T, p.D = int(T), 7
+        p.dt, p.rot_scale, p.jac_weight = self.time_duration_, self.rotation_scale_factor_, self.jacobian_update_weight_
+        p.clearance, p.pinv_ridge, p.vik_eps = self.min_clearence_, self.pseudo_inverse_ridge_factor_, self.vik_eps
+        p.use_pinv, p.affine_axis_quirk = int(self.use_pseudo_inverse_), int(self.affine_axis_quirk)
+        p.base_off = (C.c_double * 3)(*self.base_offset)
+        p.cjoint = (C.c_int32 * 8)(*(list(self.continuous) + [0]))
+        p.vel_limit = (C.c_double * 8)(*(list(self.vel_limit) + [0.0]))
+        return p
+
+
+class TormCost:
+    """Smoothness operator (TormCost + the scaling in TormOptimizer::initialize), device resident."""
+
+    def __init__(self, T, dt, weights=(1.0, 0.0, 0.0), ridge=0.0, device="cuda:0"):
+        self.T, self.device = int(T), torch.device(device)
+        self._h = _vp()
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        with torch.cuda.device(self.device):
+            check(lib.rlitg_smooth_create(self.T, float(dt), w.ctypes.data, float(ridge), C.byref(self._h)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def get(self, want_inverse=False):
+        G, F = self.T + 10, self.T - 1
+        band = np.empty((G, 13)); scale = C.c_double(0)
+        inv = np.empty((F, F)) if want_inverse else None
+        check(lib.rlitg_smooth_get(self._h, band.ctypes.data, C.byref(scale), None if inv is None else inv.ctypes.data))
+        return band, scale.value, inv
+
+    def getMaxQuadCostInvValue(self):
+        return self.get()[1]
+
+    def close(self):
+        if self._h:
+            lib.rlitg_smooth_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class TormBatch:
+    """N candidate trajectories against one target path: the cost / increment members of TormOptimizer."""
+
+    def __init__(self, end_poses, parameters: TormParameters | None = None, scene=None, device="cuda:0",
+                 dtype=torch.float32):
+        """end_poses: [T,7] target path (x y z qx qy qz qw, chain-base frame) -- endPoses_desired_."""
+        self.device, self.dtype = torch.device(device), dtype
+        self.parameters = parameters or TormParameters()
+        self.scene = scene
+        self.endPoses_desired_ = torch.as_tensor(end_poses).to(self.device, dtype).contiguous()
+        self.T = int(self.endPoses_desired_.shape[0])
+        self.num_vars_free_ = self.T - 1
+        pr = self.parameters
+        self.joint_costs_ = TormCost(self.T, pr.time_duration_, (pr.smoothness_cost_velocity_,
+                                     pr.smoothness_cost_acceleration_, pr.smoothness_cost_jerk_), pr.ridge_factor_,
+                                     self.device)
+        self._cp = pr.to_c(self.T)
+        self._buf = {}
+
+    def _out(self, name, shape, dtype=None):
+        t = self._buf.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, device=self.device, dtype=dtype or self.dtype)
+            self._buf[name] = t
+        return t
+
+    def cost_grad(self, traj, stage_mask, stochastic_idx=None, want_active=False):
+        """One launch of rlitg_torm_cost_grad.  Returns dict(costs [N,10], inc_smooth, inc_coll, inc_pose
+        [N,T-1,7] or None, active [N] or None).  Output tensors are reused between calls."""
+        traj = traj.contiguous()
+        N, T, D = traj.shape
+        if T != self.T or D != 7:
+            raise ValueError("traj must be [N,%d,7]" % self.T)
+        F = T - 1
+        inc_s = self._out("inc_smooth", (N, F, 7)) if stage_mask & STAGE_SMOOTH else None
+        inc_c = self._out("inc_coll", (N, F, 7)) if stage_mask & STAGE_COLL else None
+        inc_p = self._out("inc_pose", (N, F, 7)) if stage_mask & STAGE_POSE_GRAD else None
+        costs = self._out("costs", (N, NCOST))
+        active = self._out("active", (N,), torch.float32) if want_active else None
+        st = None
+        if stochastic_idx is not None:
+            st = torch.as_tensor(stochastic_idx).to(self.device, torch.int32).contiguous()
+        p = lambda t: None if t is None else t.data_ptr()
+        code = _lib.F32 if traj.dtype == torch.float32 else _lib.F64
+        with torch.cuda.device(self.device):
+            check(lib.rlitg_torm_cost_grad(traj.data_ptr(), self.endPoses_desired_.data_ptr(), N, code,
+                                           None if self.scene is None else self.scene.handle,
+                                           self.joint_costs_.handle, C.byref(self._cp), int(stage_mask), p(st),
+                                           p(inc_s), p(inc_c), p(inc_p), costs.data_ptr(), p(active),
+                                           torch.cuda.current_stream().cuda_stream))
+        return dict(costs=costs, inc_smooth=inc_s, inc_coll=inc_c, inc_pose=inc_p, active=active)
+
+    # ---- reference member names (leading batch axis) ------------------------------------------------------
+    def getEndPoseCost(self, traj, grad=False):
+        """torm/src/torm_optimizer.cpp:1399-1425: returns [N] = sum ||dp|| + rotation_scale_factor_ sum ||drot||;
+        with grad=True also fills endPose_increments_ (returned as second value)."""
+        r = self.cost_grad(traj, STAGE_POSE_GRAD if grad else STAGE_POSE)
+        c = r["costs"][:, 8] + self.parameters.rotation_scale_factor_ * r["costs"][:, 9]
+        return (c, r["inc_pose"]) if grad else c
+
+    def calculateEndPoseIncrements(self, traj):
+        return self.cost_grad(traj, STAGE_POSE_GRAD)["inc_pose"]
+
+    def calculateSmoothnessIncrements(self, traj):
+        return self.cost_grad(traj, STAGE_SMOOTH)["inc_smooth"]
+
+    def calculateCollisionIncrements(self, traj, stochastic_idx=None):
+        """performForwardKinematics + calculateCollisionIncrements (:1302-1382, :1484-1553)."""
+        return self.cost_grad(traj, STAGE_COLL, stochastic_idx)["inc_coll"]
+
+    def getCollisionCost(self, traj):
+        """:1448-1463 over rows start_idx-1 .. end_idx (the T real rows): [N]."""
+        return self.cost_grad(traj, STAGE_COLL)["costs"][:, 5]
+
+    def evaluate(self, traj):
+        """traj_evaluator::getCost (torm/src/utils/traj_evaluator.cpp:104-132): dict of [N] tensors."""
+        c = self.cost_grad(traj, STAGE_EVAL)["costs"]
+        return {"cost_pose": c[:, 0], "cost_rot": c[:, 1], "cost_vel": c[:, 2], "cost_acc": c[:, 3],
+                "cost_jerk": c[:, 4], "weighted": c[:, 6], "n_vel_violation": c[:, 7]}
+
+    def getWeightedPoseCost(self, traj):
+        return self.cost_grad(traj, STAGE_EVAL)["costs"][:, 6]

@@ -1,0 +1,178 @@
+"""GPU parity: kernel 3 (TORM cost + gradient) through the C ABI vs the CPU oracle.
+
+Stated tolerances.  FP64 build: 1e-9 relative on costs and increments (SVD / summation order).
+FP32: costs <= 1e-4 relative; increments <= 1e-4 relative to the row's largest component with a 1e-6 floor,
+excluding (and counting) waypoints whose pinv is ill-conditioned (sqrt(det(J J^T)) < 1e-3 for the end-pose step)
+or whose active-sphere set differs because an FP32 sphere centre fell into the neighbouring voxel."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def make_problem(N, T, seed, cuda_device, clearance=0.3, grid=(64, 96, 64), origin=(-0.3, -0.96, 0.0), res=0.025):
+    from oracle import oracle as O
+    from rlitg_b200 import fetch, scene as S, synth
+    traj = synth.linear_trajectories(N, T, seed=seed, noise=0.03)
+    targets = np.round(synth.random_ee_paths(1, T, seed=seed + 1)[0], 6)
+    occ, _ = synth.random_box_scene(grid, origin, res, seed=seed, n_clutter=3)
+    link, center, radius = fetch.default_spheres()
+    osc = O.Scene(O.build_field(occ, res, 1.0), origin, res, link, center, radius)
+    gsc = S.Scene(cuda_device)
+    gsc.set_occupancy(occ, origin, res, 1.0)
+    return traj, targets, osc, gsc
+
+
+def rel_rows(got, want, floor):
+    scale = np.abs(want).max(axis=-1, keepdims=True)
+    return np.abs(got - want).max(axis=-1) / (scale[..., 0] + floor)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("T,N,dt,clearance,quirk,use_pinv", [(100, 6, 0.1, 0.3, True, True), (37, 5, 0.2, 0.5, False, True),
+                                                             (64, 4, 1.0, 0.3, True, False), (300, 3, 0.1, 0.3, True, True)])
+def test_cost_grad_parity(cuda_device, dtype, T, N, dt, clearance, quirk, use_pinv):
+    import torch
+    from oracle import oracle as O
+    from rlitg_b200 import torm as TM
+    traj, targets, osc, gsc = make_problem(N, T, 7 + T, cuda_device)
+    op = O.torm_params(T, dt=dt, clearance=clearance, affine_axis_quirk=quirk, use_pinv=use_pinv)
+    Aband, scale, _ = O.smooth_setup(T, dt, (1.0, 0.0, 0.0), 0.0)
+    mask = O.STAGE_POSE_GRAD | O.STAGE_SMOOTH | O.STAGE_COLL | O.STAGE_EVAL
+    want = O.torm_cost_grad(traj, targets, osc, op, Aband, mask)
+    pr = TM.TormParameters(time_duration_=dt, min_clearence_=clearance, affine_axis_quirk=quirk, use_pseudo_inverse_=use_pinv)
+    tb = TM.TormBatch(targets, pr, gsc, cuda_device, getattr(torch, dtype))
+    band, gscale, _ = tb.joint_costs_.get()
+    assert abs(gscale - scale) < 1e-9 * scale and np.abs(band - Aband).max() < 1e-9 * np.abs(Aband).max()
+    got = tb.cost_grad(torch.tensor(traj, dtype=getattr(torch, dtype), device=cuda_device), mask, want_active=True)
+    torch.cuda.synchronize()
+    f64 = dtype == "float64"
+    costs = got["costs"].double().cpu().numpy()
+    ctol = 1e-9 if f64 else 1e-4
+    assert np.isfinite(costs).all()
+    for k in (0, 1, 2, 3, 4, 6, 8, 9):
+        assert np.abs(costs[:, k] - want["costs"][:, k]).max() <= ctol * np.abs(want["costs"][:, k]).max() + 1e-12, k
+    assert np.array_equal(costs[:, 7], want["costs"][:, 7])
+    # smoothness: pure banded matvec
+    gs = got["inc_smooth"].double().cpu().numpy()
+    assert rel_rows(gs, want["inc_smooth"], 1e-9).max() < (1e-10 if f64 else 2e-5)
+    # end-pose increments: exclude ill-conditioned waypoints (counted)
+    man = O.manipulability(traj[:, 1:].reshape(-1, 7)).reshape(N, T - 1)
+    good = man > 1e-3
+    assert good.mean() > 0.97
+    gp = got["inc_pose"].double().cpu().numpy()
+    assert rel_rows(gp, want["inc_pose"], 1e-6)[good].max() < (1e-8 if f64 else 1e-4)
+    # collision: cost and increments; rows whose active set differs (voxel-boundary flips) are counted
+    gc = got["inc_coll"].double().cpu().numpy()
+    assert want["active"].mean() > 1.0  # the scene is actually in the way
+    rr = rel_rows(gc, want["inc_coll"], 1e-6)
+    if f64:
+        assert rr.max() < 1e-8
+        assert np.abs(costs[:, 5] - want["costs"][:, 5]).max() < 1e-10
+        assert np.abs(got["active"].cpu().numpy() - want["active"]).max() < 1e-6
+    else:
+        bad = rr > 1e-4
+        assert bad.mean() < 0.01, (int(bad.sum()), rr.max())
+        assert np.abs(costs[:, 5] - want["costs"][:, 5]).max() <= 2e-3 * np.abs(want["costs"][:, 5]).max()
+    gsc.close()
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_stochastic_index_and_stage_masks(cuda_device, dtype):
+    import torch
+    from oracle import oracle as O
+    from rlitg_b200 import torm as TM
+    N, T = 8, 60
+    traj, targets, osc, gsc = make_problem(N, T, 3, cuda_device)
+    op = O.torm_params(T, dt=0.1, clearance=0.3)
+    rng = np.random.default_rng(0)
+    st = rng.integers(0, T - 1, size=N).astype(np.int32)
+    want = O.torm_cost_grad(traj, targets, osc, op, None, O.STAGE_COLL, st)
+    tb = TM.TormBatch(targets, TM.TormParameters(min_clearence_=0.3), gsc, cuda_device, getattr(torch, dtype))
+    tt = torch.tensor(traj, dtype=getattr(torch, dtype), device=cuda_device)
+    got = tb.calculateCollisionIncrements(tt, st).double().cpu().numpy()
+    nz = np.abs(want["inc_coll"]).max(axis=-1) > 0
+    assert (nz.sum(axis=1) <= 1).all() and nz.any()  # one waypoint per trajectory contributes
+    assert rel_rows(got, want["inc_coll"], 1e-6).max() < (1e-8 if dtype == "float64" else 2e-4)
+    # facade members agree with the fused call
+    c = tb.getEndPoseCost(tt).double().cpu().numpy()
+    w = O.torm_cost_grad(traj, targets, None, op, None, O.STAGE_POSE)["costs"]
+    assert np.abs(c - (w[:, 8] + 0.17 * w[:, 9])).max() < (1e-9 if dtype == "float64" else 1e-4) * np.abs(c).max()
+    ev = tb.evaluate(tt)
+    we = O.traj_eval(traj, targets, op)
+    assert np.abs(ev["cost_pose"].double().cpu().numpy() - we[:, 0]).max() < (1e-10 if dtype == "float64" else 1e-5)
+    gsc.close()
+
+
+def test_traj_evaluator_anchors_on_gpu(cuda_device, init_traj):
+    """SURVEY 8c regression anchors through the kernel (FP64 and FP32): real reference paths + saved initial
+    trajectories (T = 553, 227, 209, 320 -> exercises the chunked path for T > 256)."""
+    import torch
+    from rlitg_b200 import torm as TM
+    from test_oracle_golden import ANCHORS
+    for prob, methods in ANCHORS.items():
+        path = init_traj[prob + "_path"]
+        for dtype, tol in ((torch.float64, 2e-6), (torch.float32, 2e-5)):
+            tb = TM.TormBatch(path, TM.TormParameters(time_duration_=0.1), None, cuda_device, dtype)
+            names = list(methods)
+            traj = torch.tensor(np.stack([init_traj["%s_%s" % (prob, m)] for m in names]), dtype=dtype, device=cuda_device)
+            w = tb.getWeightedPoseCost(traj).double().cpu().numpy()
+            for k, m in enumerate(names):
+                assert abs(w[k] - methods[m]) < tol + 1e-4 * methods[m] * (dtype == torch.float32), (prob, m, w[k])
+
+
+def test_smoothness_known_answer_on_gpu(cuda_device):
+    from rlitg_b200 import torm as TM
+    tc = TM.TormCost(320, 1.0, (1.0, 0.0, 0.0), 0.0, cuda_device)
+    assert abs(tc.getMaxQuadCostInvValue() - 96.77624) < 2e-5  # torm/src/torm_optimizer.cpp:235
+    band, scale, inv = tc.get(want_inverse=True)
+    assert abs(inv.max() - 1.0) < 1e-12
+    tc.close()
+
+
+def test_full_size_properties(cuda_device):
+    """BASELINE config 4 (1,024 x 200, 128^3 grid): size-independent properties instead of an oracle sweep:
+    linearity of the smoothness increment, invariance of per-trajectory results to batch position, a 16-trajectory
+    oracle sample, and the < 1 ms iteration target is measured by bench.py."""
+    import torch
+    from oracle import oracle as O
+    from rlitg_b200 import torm as TM
+    N, T = 1024, 200
+    traj, targets, osc, gsc = make_problem(N, T, 0, cuda_device, grid=(128, 128, 128), origin=(-0.64, -1.28, -0.20), res=0.02)
+    tb = TM.TormBatch(targets, TM.TormParameters(min_clearence_=0.3), gsc, cuda_device, torch.float32)
+    tt = torch.tensor(traj, dtype=torch.float32, device=cuda_device)
+    mask = TM.STAGE_POSE_GRAD | TM.STAGE_SMOOTH | TM.STAGE_COLL | TM.STAGE_EVAL
+    r = tb.cost_grad(tt, mask)
+    costs = r["costs"].clone(); inc_s = r["inc_smooth"].clone(); inc_c = r["inc_coll"].clone(); inc_p = r["inc_pose"].clone()
+    assert torch.isfinite(costs).all() and torch.isfinite(inc_c).all()
+    # permutation invariance
+    perm = torch.randperm(N, device=cuda_device)
+    r2 = tb.cost_grad(tt[perm].contiguous(), mask)
+    assert torch.equal(r2["costs"], costs[perm]) and torch.equal(r2["inc_coll"], inc_c[perm]) and torch.equal(r2["inc_pose"], inc_p[perm])
+    # linearity of the smoothness operator
+    a = tb.calculateSmoothnessIncrements((2.0 * tt).contiguous()).clone()
+    assert (a - 2.0 * inc_s).abs().max().item() <= 1e-5 * inc_s.abs().max().item()
+    # oracle sample
+    idx = np.arange(0, N, 64)
+    op = O.torm_params(T, dt=0.1, clearance=0.3)
+    Aband, _, _ = O.smooth_setup(T, 0.1, (1.0, 0.0, 0.0), 0.0)
+    want = O.torm_cost_grad(traj[idx], targets, osc, op, Aband, mask)
+    g = costs[idx].double().cpu().numpy()
+    for k in (0, 1, 2, 3, 4, 5, 6, 8, 9):
+        assert np.abs(g[:, k] - want["costs"][:, k]).max() <= 2e-3 * np.abs(want["costs"][:, k]).max() + 1e-9, k
+    rr = rel_rows(inc_c[idx].double().cpu().numpy(), want["inc_coll"], 1e-6)
+    assert (rr > 1e-4).mean() < 0.01
+    gsc.close()
+
+
+def test_torm_errors(cuda_device):
+    import torch
+    from rlitg_b200 import torm as TM
+    from rlitg_b200._lib import RlitgError
+    targets = np.zeros((20, 7)); targets[:, 6] = 1
+    tb = TM.TormBatch(targets, None, None, cuda_device)
+    tt = torch.zeros(2, 20, 7, device=cuda_device)
+    with pytest.raises(RlitgError):
+        tb.cost_grad(tt, TM.STAGE_COLL)  # no scene
+    with pytest.raises(ValueError):
+        tb.cost_grad(torch.zeros(2, 21, 7, device=cuda_device), TM.STAGE_POSE)
