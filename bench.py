@@ -101,7 +101,7 @@ def cpu_reference_fk_jac(seconds_target=12.0, threads=None):
     O.fk_jac(q[:1024])
     t0 = time.perf_counter(); O.fk_jac(q); t1 = time.perf_counter()
     reps = max(1, int(seconds_target / max(t1 - t0, 1e-6)))
-    reps = min(reps, 64)
+    reps = min(reps, 2048)
     t0 = time.perf_counter()
     for _ in range(reps):
         O.fk_jac(q)

@@ -243,6 +243,11 @@ RLITG_API int rlitg_torm_cost_grad(const void* traj, const void* targets, int64_
                                    int stage_mask, const int32_t* stochastic_idx, void* inc_smooth, void* inc_coll,
                                    void* inc_pose, void* costs, float* active, void* stream);
 
+/* Measurement aid: launches `ctas` x 256 threads each running 16 independent FFMA chains of `iters` steps
+ * (2 * ctas * 256 * iters * 16 flops); bench.py times it with CUDA events to get the FP32 FMA-pipe peak that
+ * the TORM kernel's roofline fraction is quoted against. */
+RLITG_API int rlitg_fma_probe(int ctas, int iters, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -160,3 +160,27 @@ RLITG_API int rlitg_fk_jac_host(const void* q, int64_t B, int D, int dtype, int 
 }
 
 }  // extern "C"
+
+// ---- FP32 FMA-pipe probe: the denominator of the TORM kernel's roofline is measured, not nominal -----------
+namespace rlitg {
+__global__ void __launch_bounds__(256) fma_probe_kernel(int iters, float* out) {
+    float a[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) a[k] = 1.0f + 1e-3f * (threadIdx.x + k);
+    const float b = 0.999f, c = 1e-4f;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) a[k] = fmaf(a[k], b, c);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; k++) s += a[k];
+    if (s == 123.456f) *out = s;  // keeps the chains alive without a store in the common case
+}
+}  // namespace rlitg
+
+extern "C" RLITG_API int rlitg_fma_probe(int ctas, int iters, float* out, void* stream) {
+    if (ctas < 1 || iters < 1 || !out) return rlitg::set_error(RLITG_ERR_ARG, "bad fma probe arguments");
+    rlitg::fma_probe_kernel<<<ctas, 256, 0, static_cast<cudaStream_t>(stream)>>>(iters, out);
+    return rlitg::check_launch("fma_probe_kernel");
+}

@@ -53,4 +53,7 @@ def default_spheres():
             c = mid.copy()
             c[ax] = t
             link.append(lk); center.append(c); radius.append(r)
-    return np.array(link, dtype=np.int32), np.array(center), np.array(radius)
+    # the device table is stored as float32 (cx, cy, cz, r): return exactly representable values so that a
+    # double-precision consumer (the oracle) sees the same table
+    f32 = lambda a: np.asarray(a, dtype=np.float32).astype(np.float64)
+    return np.array(link, dtype=np.int32), f32(center), f32(radius)
