@@ -39,3 +39,24 @@ def check(rc: int) -> None:
 
 def launch_count() -> int:
     return int(lib.rlitg_launch_count())
+
+
+class on_device:
+    """`with on_device(dev):` -- like torch.cuda.device(dev) but free when dev is already current (hot loops)."""
+    __slots__ = ("idx", "ctx")
+
+    def __init__(self, device):
+        self.idx = device.index if device.index is not None else 0
+        self.ctx = None
+
+    def __enter__(self):
+        import torch
+        if torch.cuda.current_device() != self.idx:
+            self.ctx = torch.cuda.device(self.idx)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False

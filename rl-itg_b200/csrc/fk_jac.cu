@@ -10,6 +10,9 @@
 // 42-word thread stride are bank-conflict free -- and drained with TMA bulk stores (cp.async.bulk
 // shared::cta -> global), one per output array, so the write-back is fully coalesced and asynchronous to the
 // threads.  Struct-of-arrays outputs ([3,B], [9,B], [6D,B]) are stored directly (already coalesced).
+#include <algorithm>
+#include <cstdlib>
+
 #include "fetch_chain.cuh"
 #include "rlitg_internal.h"
 
@@ -133,6 +136,81 @@ __global__ void __launch_bounds__(kTile) fk_jac_kernel(const T* __restrict__ q, 
     }
 }
 
+
+// ---- persistent variant for array-of-structs outputs ------------------------------------------------------
+// One CTA per SM slot loops over 128-configuration tiles: the next tile's joint vector is prefetched into
+// registers before the current tile is walked, and the staged outputs drain through TMA bulk stores while the
+// next tile computes (NSTAGE staging buffers; a buffer is reused once its bulk group has finished reading).
+// This removes the load -> compute -> store serialisation and the CTA launch gaps of the one-tile-per-CTA kernel.
+template <int N>
+RLITG_DEV void bulk_wait_read_pending() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+template <typename T, int D, bool QSOA, int NSTAGE>
+__global__ void __launch_bounds__(kTile) fk_jac_persist_kernel(const T* __restrict__ q, int64_t B, int64_t ntiles,
+                                                               T* __restrict__ pos, T* __restrict__ rot,
+                                                               T* __restrict__ quat, T* __restrict__ J) {
+    constexpr int kStageElems = kTile * (6 * D + 9 + 4 + 3);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* stage0 = reinterpret_cast<T*>(smem_raw);
+    const int tid = threadIdx.x;
+    int64_t tile = blockIdx.x;
+    T qn[D];
+    auto load_q = [&](int64_t t) {
+        const int64_t b = t * kTile + tid;
+#pragma unroll
+        for (int j = 0; j < D; j++) qn[j] = QSOA ? ld_stream(q + (int64_t)j * B + b) : ld_stream(q + b * D + j);
+    };
+    if (tile < ntiles) load_q(tile);
+    for (int it = 0; tile < ntiles; tile += gridDim.x, it++) {
+        T qv[D];
+#pragma unroll
+        for (int j = 0; j < D; j++) qv[j] = qn[j];
+        if (tile + gridDim.x < ntiles) load_q(tile + gridDim.x);
+
+        FkJac<T, D> fj;
+        walk_chain<T, D>(qv, fj);
+
+        T* sJ = stage0 + (it % NSTAGE) * kStageElems;
+        T* sRot = sJ + kTile * 6 * D;
+        T* sQuat = sRot + kTile * 9;
+        T* sPos = sQuat + kTile * 4;
+        if (it >= NSTAGE) {  // the bulk group that last read this buffer must have drained
+            if (tid == 0) bulk_wait_read_pending<NSTAGE - 1>();
+            __syncthreads();
+        }
+        if (J) {
+            T jv[6 * D];
+            fill_jac(fj, jv);
+            stage_row<T, 6 * D>(sJ, tid, jv);
+        }
+        if (rot) {
+            const T rv[9] = {fj.ee.c0.x, fj.ee.c1.x, fj.ee.c2.x, fj.ee.c0.y, fj.ee.c1.y,
+                             fj.ee.c2.y, fj.ee.c0.z, fj.ee.c1.z, fj.ee.c2.z};
+            stage_row<T, 9>(sRot, tid, rv);
+        }
+        if (quat) {
+            T qq[4];
+            rot_to_quat_kdl(fj.ee.c0, fj.ee.c1, fj.ee.c2, qq[0], qq[1], qq[2], qq[3]);
+            stage_row<T, 4>(sQuat, tid, qq);
+        }
+        if (pos) {
+            const T pv[3] = {fj.ee.p.x, fj.ee.p.y, fj.ee.p.z};
+            stage_row<T, 3>(sPos, tid, pv);
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            const int64_t base = tile * kTile;
+            if (J) bulk_store(J + base * 6 * D, sJ, (uint32_t)(kTile * 6 * D * sizeof(T)));
+            if (rot) bulk_store(rot + base * 9, sRot, (uint32_t)(kTile * 9 * sizeof(T)));
+            if (quat) bulk_store(quat + base * 4, sQuat, (uint32_t)(kTile * 4 * sizeof(T)));
+            if (pos) bulk_store(pos + base * 3, sPos, (uint32_t)(kTile * 3 * sizeof(T)));
+            bulk_commit();
+        }
+    }
+    if (tid == 0) bulk_wait_read_all();
+}
+
 // ---- all-link FK: [B, D+1, 7] = (pos, quat xyzw) per segment tip (allLinkfkSolver_srv) --------------------
 template <typename T, int D>
 struct AllFkVisit {
@@ -171,13 +249,40 @@ __global__ void __launch_bounds__(kTile) allfk_kernel(const T* __restrict__ q, i
     walk_chain<T, D>(qv, v);
     __syncthreads();
     T* dst = out + base * N;
-    for (int i = tid; i < n * N; i += kTile) {
+    for (int i = tid; i < n * N; i += kTile) {  // flat, fully coalesced; N is a compile-time constant
         const int r = i / N, c = i - r * N;
         dst[i] = sOut[r * NP + c];
     }
 }
 
 // ---- launchers -------------------------------------------------------------------------------------------
+static int fk_variant() {  // RLITG_FK_VARIANT: 0 = tile per CTA, 1 / 2 = persistent with 1 / 2 staging buffers
+    static int v = [] {
+        const char* e = getenv("RLITG_FK_VARIANT");
+        return e ? atoi(e) : 2;
+    }();
+    return v;
+}
+
+template <typename T, int D, bool QSOA, int NSTAGE>
+static int launch_fk_persist(const T* q, int64_t B, int64_t ntiles, T* pos, T* rot, T* quat, T* J, cudaStream_t st) {
+    const size_t smem = sizeof(T) * NSTAGE * kTile * (6 * D + 9 + 4 + 3);
+    auto kern = fk_jac_persist_kernel<T, D, QSOA, NSTAGE>;
+    static int ctas_per_sm = 0, num_sms = 0;
+    if (ctas_per_sm == 0) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return set_cuda_error("cudaFuncSetAttribute(fk_jac_persist_kernel)");
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kTile, smem) != cudaSuccess || ctas_per_sm < 1)
+            return set_cuda_error("cudaOccupancyMaxActiveBlocksPerMultiprocessor(fk_jac_persist_kernel)");
+    }
+    const int64_t grid = std::min<int64_t>(ntiles, (int64_t)num_sms * ctas_per_sm);
+    kern<<<(unsigned)grid, kTile, smem, st>>>(q, B, ntiles, pos, rot, quat, J);
+    return check_launch("fk_jac_persist_kernel");
+}
+
 template <typename T, int D, bool QSOA, bool OSOA>
 static int launch_fk_jac_t(const T* q, int64_t B, T* pos, T* rot, T* quat, T* J, cudaStream_t st) {
     const size_t smem = sizeof(T) * kTile * (6 * D + 9 + 4 + 3 + D);
@@ -191,6 +296,22 @@ static int launch_fk_jac_t(const T* q, int64_t B, T* pos, T* rot, T* quat, T* J,
     // TMA bulk stores need 16-byte aligned global addresses; tile offsets keep the alignment of the base
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     const int allow_bulk = al16(pos) && al16(rot) && al16(quat) && al16(J);
+    if constexpr (!OSOA) {
+        const int64_t ntiles = B / kTile;
+        const int variant = fk_variant();
+        // (an SoA input with a partial last tile stays on the tile-per-CTA kernel: its tail cannot be re-based)
+        if (allow_bulk && variant > 0 && ntiles >= 1024 && (!QSOA || ntiles * kTile == B)) {
+            int rc = variant == 1 ? launch_fk_persist<T, D, QSOA, 1>(q, B, ntiles, pos, rot, quat, J, st)
+                                  : launch_fk_persist<T, D, QSOA, 2>(q, B, ntiles, pos, rot, quat, J, st);
+            if (rc) return rc;
+            const int64_t done = ntiles * kTile;
+            if (done == B) return RLITG_OK;
+            kern<<<1, kTile, smem, st>>>(q + done * D, B - done, pos ? pos + done * 3 : nullptr,
+                                         rot ? rot + done * 9 : nullptr, quat ? quat + done * 4 : nullptr,
+                                         J ? J + done * 6 * D : nullptr, allow_bulk);
+            return check_launch("fk_jac_kernel");
+        }
+    }
     const int64_t grid = (B + kTile - 1) / kTile;
     kern<<<(unsigned)grid, kTile, smem, st>>>(q, B, pos, rot, quat, J, allow_bulk);
     return check_launch("fk_jac_kernel");

@@ -1,9 +1,12 @@
 // Small dense algebra for the pseudo-inverse steps of the hot path.
-//   * 6x6 SPD solve of (J J^T) y = b by Cholesky -- always in FP64: the normal equations square cond(J), and
-//     FP32 there would cost ~cond^2 * 6e-8; 6x6 in FP64 is ~300 DFMA per configuration.
-//   * one-sided Jacobi SVD pseudo-inverse with KDL's singular-value truncation (ChainIkSolverVel_pinv, eps 1e-5,
-//     torm/src/torm_ik_solver.cpp:169-171), used when the Cholesky pivots say J is near rank-deficient and by the
-//     FP64 verification build.
+//   * FP32 build: modified Gram-Schmidt QR of J^T (D x 6) held in registers.  pinv(J) v = Q R^-T v and the
+//     null-space projector I - Q Q^T come out with error ~ cond(J) * eps -- not cond^2 as the normal equations
+//     J J^T would give in FP32 -- and without any FP64 instruction on the hot path.
+//   * FP64 build (verification): the literal algorithms -- one-sided Jacobi SVD with KDL's singular-value
+//     truncation (ChainIkSolverVel_pinv, eps 1e-5, torm/src/torm_ik_solver.cpp:169-171) for the velocity step,
+//     a 6x6 Cholesky solve of J J^T for the null-space norm (pirl/src/kinematic_solver.cpp:347).
+//   * The FP32 build falls back to the FP64 SVD when a diagonal entry of R says a singular value may be near
+//     KDL's truncation threshold, so the truncated-SVD semantics hold at singular configurations.
 #pragma once
 #include "rlitg_common.cuh"
 
@@ -66,6 +69,37 @@ RLITG_DEV void chol6_solve(const double (&L)[21], double (&b)[6]) {
     }
 }
 
+
+// Modified Gram-Schmidt on the rows of Q (in: the 6 rows of J, each of length D; out: orthonormal rows).
+// R is upper triangular, packed R[k][j] (j >= k) at R[k * 6 + j].  Returns min_k R_kk / max_k R_kk.
+template <typename T, int D>
+RLITG_DEV T mgs_rows(T (&Q)[6 * D], T (&R)[36]) {
+    T rmin = T(1e30), rmax = T(0);
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        T n2 = T(0);
+#pragma unroll
+        for (int i = 0; i < D; i++) n2 += Q[k * D + i] * Q[k * D + i];
+        const T r = sqrt_t(n2);
+        R[k * 6 + k] = r;
+        rmin = r < rmin ? r : rmin;
+        rmax = r > rmax ? r : rmax;
+        const T inv = T(1) / (r > T(1e-30) ? r : T(1e-30));
+#pragma unroll
+        for (int i = 0; i < D; i++) Q[k * D + i] *= inv;
+#pragma unroll
+        for (int j = k + 1; j < 6; j++) {
+            T d = T(0);
+#pragma unroll
+            for (int i = 0; i < D; i++) d += Q[k * D + i] * Q[j * D + i];
+            R[k * 6 + j] = d;
+#pragma unroll
+            for (int i = 0; i < D; i++) Q[j * D + i] -= d * Q[k * D + i];
+        }
+    }
+    return rmin / (rmax > T(1e-30) ? rmax : T(1e-30));
+}
+
 // dq = pinv(J) v with singular values below eps zeroed: one-sided Jacobi on A = J^T (D x 6), FP64.
 // (A V = U S  =>  pinv(J) = A S^-2 V^T.)  Not inlined: it is the rare path of the FP32 build.
 template <typename T, int D>
@@ -118,32 +152,49 @@ __device__ __noinline__ void pinv_svd_apply(const T* J, const T* v6, double eps,
     for (int i = 0; i < D; i++) dq[i] = (T)acc[i];
 }
 
-// dq = pinv(J) v.  Fast path J^T (J J^T)^-1 v (equal to the Moore-Penrose result for full row rank); falls back
-// to the truncated SVD when the smallest Cholesky pivot ratio says a singular value may be near KDL's eps.
-// kAlwaysSvd = literal path for the verification build.
+// dq = pinv(J) v.  FP32: min-norm solution through the QR of J^T (J = R^T Q, so dq = Q^T-rows * y with
+// R^T y = v); equal to the Moore-Penrose result for full row rank.  When the smallest diagonal of R is below
+// 1e-4 of the largest (a singular value may be near KDL's 1e-5 truncation) the truncated FP64 SVD runs instead.
+// FP64 (kAlwaysSvd): the literal SVD path.
 template <typename T, int D, bool kAlwaysSvd>
 RLITG_DEV void pinv_apply(const T (&J)[6 * D], const T (&v6)[6], double eps, T (&dq)[D]) {
     if constexpr (kAlwaysSvd) {
-        pinv_svd_apply<T, D>(J, v6, eps, dq);
+        T Jc[6 * D], vc[6];
+#pragma unroll
+        for (int i = 0; i < 6 * D; i++) Jc[i] = J[i];
+#pragma unroll
+        for (int i = 0; i < 6; i++) vc[i] = v6[i];
+        pinv_svd_apply<T, D>(Jc, vc, eps, dq);
     } else {
-        double A[21];
-        jjt6<T, D>(J, A);
-        const double ratio = chol6(A);
-        // sigma_min^2 / sigma_max^2 >~ ratio; KDL truncates sigma < 1e-5 with sigma_max = O(1): be conservative
-        if (ratio < 1e-8) {
-            pinv_svd_apply<T, D>(J, v6, eps, dq);
+        T Q[6 * D], R[36];
+#pragma unroll
+        for (int i = 0; i < 6 * D; i++) Q[i] = J[i];
+        const T ratio = mgs_rows<T, D>(Q, R);
+        if (ratio < T(1e-4)) {  // rare: copies keep J / v6 out of local memory on the common path
+            T Jc[6 * D], vc[6], out[D];
+#pragma unroll
+            for (int i = 0; i < 6 * D; i++) Jc[i] = J[i];
+#pragma unroll
+            for (int i = 0; i < 6; i++) vc[i] = v6[i];
+            pinv_svd_apply<T, D>(Jc, vc, eps, out);
+#pragma unroll
+            for (int i = 0; i < D; i++) dq[i] = out[i];
             return;
         }
-        double y[6];
+        T y[6];
 #pragma unroll
-        for (int i = 0; i < 6; i++) y[i] = (double)v6[i];
-        chol6_solve(A, y);
+        for (int k = 0; k < 6; k++) {
+            T sacc = v6[k];
 #pragma unroll
-        for (int k = 0; k < D; k++) {
-            double s = 0.0;
+            for (int i = 0; i < k; i++) sacc -= R[i * 6 + k] * y[i];
+            y[k] = sacc / R[k * 6 + k];
+        }
 #pragma unroll
-            for (int i = 0; i < 6; i++) s += (double)J[i * D + k] * y[i];
-            dq[k] = (T)s;
+        for (int i = 0; i < D; i++) {
+            T sacc = T(0);
+#pragma unroll
+            for (int k = 0; k < 6; k++) sacc += y[k] * Q[k * D + i];
+            dq[i] = sacc;
         }
     }
 }
@@ -151,27 +202,49 @@ RLITG_DEV void pinv_apply(const T (&J)[6 * D], const T (&v6)[6], double eps, T (
 // || (I - J^T (J J^T)^-1 J) e ||   (jaco_srv, pirl/src/kinematic_solver.cpp:332-351)
 template <typename T, int D>
 RLITG_DEV T nullspace_norm(const T (&J)[6 * D], const T (&e)[D]) {
-    double A[21];
-    jjt6<T, D>(J, A);
-    chol6(A);
-    double y[6];
+    if constexpr (sizeof(T) == 4) {
+        // e - Q^T Q e with the orthonormal rows of the QR of J^T, projected out one after the other
+        T Q[6 * D], R[36], r[D];
 #pragma unroll
-    for (int i = 0; i < 6; i++) {
-        double s = 0.0;
+        for (int i = 0; i < 6 * D; i++) Q[i] = J[i];
+        mgs_rows<T, D>(Q, R);
 #pragma unroll
-        for (int k = 0; k < D; k++) s += (double)J[i * D + k] * (double)e[k];
-        y[i] = s;
+        for (int i = 0; i < D; i++) r[i] = e[i];
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            T c = T(0);
+#pragma unroll
+            for (int i = 0; i < D; i++) c += Q[k * D + i] * r[i];
+#pragma unroll
+            for (int i = 0; i < D; i++) r[i] -= c * Q[k * D + i];
+        }
+        T n2 = T(0);
+#pragma unroll
+        for (int i = 0; i < D; i++) n2 += r[i] * r[i];
+        return sqrt_t(n2);
+    } else {
+        double A[21];
+        jjt6<T, D>(J, A);
+        chol6(A);
+        double y[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; k++) s += (double)J[i * D + k] * (double)e[k];
+            y[i] = s;
+        }
+        chol6_solve(A, y);
+        double n2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            double s = (double)e[k];
+#pragma unroll
+            for (int i = 0; i < 6; i++) s -= (double)J[i * D + k] * y[i];
+            n2 += s * s;
+        }
+        return (T)sqrt(n2);
     }
-    chol6_solve(A, y);
-    double n2 = 0.0;
-#pragma unroll
-    for (int k = 0; k < D; k++) {
-        double s = (double)e[k];
-#pragma unroll
-        for (int i = 0; i < 6; i++) s -= (double)J[i * D + k] * y[i];
-        n2 += s * s;
-    }
-    return (T)sqrt(n2);
 }
 
 }  // namespace rlitg

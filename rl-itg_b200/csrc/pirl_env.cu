@@ -117,7 +117,7 @@ struct PirlVisit {
 };
 
 template <typename T, bool kStep>
-__global__ void __launch_bounds__(kEnvTile) pirl_env_kernel(
+__global__ void __launch_bounds__(kEnvTile, sizeof(T) == 4 ? 4 : 1) pirl_env_kernel(
     PirlCfgT<T> cfg, int64_t B, T* __restrict__ q, const float* __restrict__ action, int32_t* __restrict__ timestep,
     const int32_t* __restrict__ max_timestep, const T* __restrict__ targets, const T* __restrict__ demos, int Tmax,
     const T* __restrict__ latent, SceneDev sc, int has_scene, double ox, double oy, double oz, T* __restrict__ obs,
@@ -312,10 +312,14 @@ __global__ void __launch_bounds__(kEnvTile) pirl_env_kernel(
         }
     }
     __syncthreads();
+    // flat coalesced copy-out; (row, column) advance incrementally instead of dividing by the runtime O
     T* dst = obs + base * O;
+    int r = tid / O, c = tid - r * O;
+    const int dr = kEnvTile / O, dc = kEnvTile - dr * O;
     for (int i = tid; i < n * O; i += kEnvTile) {
-        const int r = i / O, c = i - r * O;
         dst[i] = s_obs[r * OS + c];
+        r += dr; c += dc;
+        if (c >= O) { c -= O; r++; }
     }
 }
 

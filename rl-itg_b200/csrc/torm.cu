@@ -1,5 +1,7 @@
 // Kernel 3: TORM path-following objective and gradient over N candidate trajectories x T waypoints
-// (SURVEY.md 8a rows A4-A8).  One CTA per trajectory, one thread per waypoint.
+// (SURVEY.md 8a rows A4-A8).  One CTA per trajectory, one thread per waypoint, in two kernels with separate
+// register budgets: 3a end-pose error + pinv step + trajectory evaluator, 3b sphere potentials + CHOMP increments
+// + smoothness increments (both are launched by one rlitg_torm_cost_grad call, on the caller's stream).
 //
 // What one launch replaces in the reference (all serial, one trajectory at a time, FP64, KDL + MoveIt):
 //   getEndPoseCost(grad)              torm/src/torm_optimizer.cpp:1399-1425   FK + KDL::diff + pinv velocity IK
@@ -27,9 +29,7 @@
 namespace rlitg {
 
 constexpr int kTormMaxThreads = 256;
-constexpr int kNRed = 13;
-enum { R_WP_POS = 0, R_WP_ROT, R_MID_POS, R_MID_ROT, R_COLL, R_VEL_C, R_ACC_C, R_JERK_C, R_VEL_N, R_ACC_N, R_JERK_N,
-       R_NVIOL, R_NACTIVE };
+enum { R_WP_POS = 0, R_WP_ROT, R_MID_POS, R_MID_ROT, R_VEL_C, R_ACC_C, R_JERK_C, R_VEL_N, R_ACC_N, R_JERK_N, R_NVIOL_P };
 
 // torm/include/torm/torm_utils.h:49-57
 template <typename T> RLITG_DEV T diff_rule(int d, int k) {
@@ -101,6 +101,18 @@ struct TormVisit {
     }
 };
 
+// sphere centres of one halo row (chunked paths only): kept out of line so the chain walk is not inlined twice
+template <typename T>
+__device__ __noinline__ void halo_sphere_row(const T* qrow, T* sph_row, const float4* sph, const int* link_start, V3<T> off) {
+    TormVisit<T> hv;
+    hv.sph = sph; hv.link_start = link_start; hv.off = off;
+    hv.sph_row = sph_row;
+    T hq[7];
+#pragma unroll
+    for (int j = 0; j < 7; j++) hq[j] = qrow[j];
+    walk_chain<T, 7>(hq, hv);
+}
+
 template <typename T>
 struct EeOnly {  // midpoint FK needs the end-effector frame only
     FrameC<T> ee;
@@ -160,111 +172,104 @@ RLITG_DEV void inter_target(const T* __restrict__ a7, const T* __restrict__ b7, 
     c2 = {a0.x * h02 + a1.x * h12 + a2.x * h22, a0.y * h02 + a1.y * h12 + a2.y * h22, a0.z * h02 + a1.z * h12 + a2.z * h22};
 }
 
-RLITG_DEV void mat3_inverse_d(const double (&m)[9], double (&inv)[9]) {
-    const double det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) +
-                       m[2] * (m[3] * m[7] - m[4] * m[6]);
-    const double id = 1.0 / det;
+template <typename U>
+RLITG_DEV void mat3_inverse(const U (&m)[9], U (&inv)[9]) {
+    const U det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) +
+                  m[2] * (m[3] * m[7] - m[4] * m[6]);
+    const U id = U(1) / det;
     inv[0] = (m[4] * m[8] - m[5] * m[7]) * id; inv[1] = (m[2] * m[7] - m[1] * m[8]) * id; inv[2] = (m[1] * m[5] - m[2] * m[4]) * id;
     inv[3] = (m[5] * m[6] - m[3] * m[8]) * id; inv[4] = (m[0] * m[8] - m[2] * m[6]) * id; inv[5] = (m[2] * m[3] - m[0] * m[5]) * id;
     inv[6] = (m[3] * m[7] - m[4] * m[6]) * id; inv[7] = (m[1] * m[6] - m[0] * m[7]) * id; inv[8] = (m[0] * m[4] - m[1] * m[3]) * id;
 }
 
+// block-wide sum of NR per-thread scalars -> tot[] valid on thread 0 (warp shuffles, then one smem round)
+template <typename T, int NR>
+RLITG_DEV void block_reduce(T (&red)[NR], T* s_red, T (&tot)[NR]) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < NR; k++) {
+        T x = red[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        red[k] = x;
+    }
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NR; k++) s_red[warp * NR + k] = red[k];
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < NR; k++) {
+            T x = T(0);
+            for (int w = 0; w < nwarps; w++) x += s_red[w * NR + k];
+            tot[k] = x;
+        }
+    }
+}
+
+#define TROW(row) (s_traj + (min(max((row), 0), Tn - 1) - c0 + 6) * 7)
+#define PROW(row) (s_pos + (size_t)(min(max((row), 0), Tn - 1) - c0 + 3) * S * 3)
+
+// ---- kernel 3a: end-pose error / pinv step (A5) + trajectory evaluator (A8) -------------------------------
+// Writes costs[0..4], [6..9]; costs[5] (collision) is zeroed when the collision kernel does not run.
+constexpr int kNRedPose = 11;
 template <typename T>
 __global__ void __launch_bounds__(kTormMaxThreads, 2)
-torm_kernel(TormP<T> P, const T* __restrict__ traj, const T* __restrict__ targets, SceneDev sc, int S,
-            const T* __restrict__ Aband, int stage_mask, const int32_t* __restrict__ stoch,
-            T* __restrict__ inc_smooth, T* __restrict__ inc_coll, T* __restrict__ inc_pose, T* __restrict__ costs,
-            float* __restrict__ active) {
+torm_pose_eval_kernel(TormP<T> P, const T* __restrict__ traj, const T* __restrict__ targets, int stage_mask,
+                      int zero_coll_cost, T* __restrict__ inc_pose, T* __restrict__ costs) {
     const int CH = blockDim.x, tid = threadIdx.x, Tn = P.Tn;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* s_traj = reinterpret_cast<T*>(smem_raw);       // [(CH + 12)][7]  rows c0-6 .. c0+CH+5, clamped
-    T* s_v = s_traj + (CH + 12) * 7;                  // [(CH + 3)][7]   first differences of continuous joints
-    T* s_red = s_v + (CH + 3) * 7;                    // [8][kNRed]
-    T* s_pos = s_red + 8 * kNRed;                     // [(CH + 6)][S][3] rows c0-3 .. c0+CH+2
-    __shared__ float4 s_sph[kMaxSpheres];
-    __shared__ int s_start[kNumLinks + 1];
-
-    const bool do_coll = (stage_mask & RLITG_STAGE_COLL) != 0;
-    const bool do_pose = (stage_mask & (RLITG_STAGE_POSE | RLITG_STAGE_POSE_GRAD | RLITG_STAGE_EVAL)) != 0;
+    T* s_traj = reinterpret_cast<T*>(smem_raw);  // [(CH + 12)][7]  rows c0-6 .. c0+CH+5, clamped
+    T* s_v = s_traj + (CH + 12) * 7;             // [(CH + 3)][7]   first differences of continuous joints
+    T* s_red = s_v + (CH + 3) * 7;               // [8][kNRedPose]
     const bool do_pgrad = (stage_mask & RLITG_STAGE_POSE_GRAD) != 0;
-    const bool do_smooth = (stage_mask & RLITG_STAGE_SMOOTH) != 0;
     const bool do_eval = (stage_mask & RLITG_STAGE_EVAL) != 0;
-    if (do_coll) {
-        for (int i = tid; i < S; i += CH) s_sph[i] = sc.spheres[i];
-        if (tid <= kNumLinks) s_start[tid] = sc.link_start[tid];
-    }
     const int64_t n = blockIdx.x;
     const T* tr = traj + n * (int64_t)Tn * 7;
-    const int F = Tn - 1;
-    T* o_smooth = inc_smooth ? inc_smooth + n * (int64_t)F * 7 : nullptr;
-    T* o_coll = inc_coll ? inc_coll + n * (int64_t)F * 7 : nullptr;
-    T* o_pose = inc_pose ? inc_pose + n * (int64_t)F * 7 : nullptr;
-    const int stoch_row = stoch ? stoch[n] + 1 : -1;  // full-trajectory row of the single stochastic waypoint
-    const V3<T> off = {P.off[0], P.off[1], P.off[2]};
-    const GridMap<T> gm(sc);
+    T* o_pose = inc_pose ? inc_pose + n * (int64_t)(Tn - 1) * 7 : nullptr;
 
-    T red[kNRed];
+    T red[kNRedPose];
 #pragma unroll
-    for (int k = 0; k < kNRed; k++) red[k] = T(0);
+    for (int k = 0; k < kNRedPose; k++) red[k] = T(0);
 
     for (int c0 = 0; c0 < Tn; c0 += CH) {
         __syncthreads();
         for (int idx = tid; idx < (CH + 12) * 7; idx += CH) {
             const int r = idx / 7, j = idx - r * 7;
-            const int src = min(max(c0 - 6 + r, 0), Tn - 1);
-            s_traj[idx] = tr[src * 7 + j];
+            s_traj[idx] = tr[min(max(c0 - 6 + r, 0), Tn - 1) * 7 + j];
         }
         __syncthreads();
         const int i = c0 + tid;
         const bool valid = i < Tn;
-#define TROW(row) (s_traj + (min(max((row), 0), Tn - 1) - c0 + 6) * 7)
-#define PROW(row) (s_pos + (size_t)(min(max((row), 0), Tn - 1) - c0 + 3) * S * 3)
-
-        // ---- phase 1: FK of this row (+ halo rows for the sphere stencils of a chunked path)
-        TormVisit<T> v;
-        v.sph = s_sph; v.link_start = s_start; v.off = off;
-        v.sph_row = nullptr;
         T q[7];
         if (valid) {
 #pragma unroll
             for (int j = 0; j < 7; j++) q[j] = TROW(i)[j];
-            v.sph_row = do_coll ? PROW(i) : nullptr;
-            walk_chain<T, 7>(q, v);
         }
-        if (do_coll && tid < 6) {
-            const int hr = tid < 3 ? c0 - 3 + tid : c0 + CH + (tid - 3);
-            if (hr >= 0 && hr < Tn) {
-                TormVisit<T> hv;
-                hv.sph = s_sph; hv.link_start = s_start; hv.off = off;
-                hv.sph_row = PROW(hr);
-                T hq[7];
-#pragma unroll
-                for (int j = 0; j < 7; j++) hq[j] = TROW(hr)[j];
-                walk_chain<T, 7>(hq, hv);
-            }
-        }
-
         // ---- end-pose error at the waypoint: getEndPoseCost :1399-1425
-        if (do_pose && valid && i >= 1) {
+        if (valid && i >= 1) {
+            FkJac<T, 7> fj;
+            walk_chain<T, 7>(q, fj);
             V3<T> tp, t0, t1, t2;
             target_frame(targets + i * 7, tp, t0, t1, t2);
             T angle;
-            const V3<T> rv = rot_diff_kdl(v.fj.ee.c0, v.fj.ee.c1, v.fj.ee.c2, t0, t1, t2, angle);
-            const V3<T> dp = tp - v.fj.ee.p;
+            const V3<T> rv = rot_diff_kdl(fj.ee.c0, fj.ee.c1, fj.ee.c2, t0, t1, t2, angle);
+            const V3<T> dp = tp - fj.ee.p;
             red[R_WP_POS] += sqrt_t(dot(dp, dp));
             red[R_WP_ROT] += sqrt_t(dot(rv, rv));
             if (do_pgrad && o_pose) {
                 T J[42], dq[7];
-                fill_jac<T, 7>(v.fj, J);
+                fill_jac<T, 7>(fj, J);
                 const T tw[6] = {dp.x, dp.y, dp.z, rv.x, rv.y, rv.z};
                 pinv_apply<T, 7, sizeof(T) == 8>(J, tw, P.vik_eps, dq);
 #pragma unroll
                 for (int j = 0; j < 7; j++) o_pose[(i - 1) * 7 + j] = P.jac_w * dq[j];
             }
         }
-
-        // ---- first differences of continuous joints for the evaluator (:164-181), shared with neighbours
         if (do_eval) {
+            // first differences of continuous joints (:164-181), shared with the neighbouring rows
             for (int e = tid; e < CH + 3; e += CH) {
                 const int r = c0 + e;
 #pragma unroll
@@ -274,166 +279,51 @@ torm_kernel(TormP<T> P, const T* __restrict__ traj, const T* __restrict__ target
                     s_v[e * 7 + j] = val;
                 }
             }
-        }
-        __syncthreads();
-
-        // ---- phase 2: collision potentials, cost, CHOMP increments
-        if (do_coll && valid) {
-            T acc[7];
+            __syncthreads();
+            if (valid) {
+                if (i < Tn - 1) {  // midpoint pose error :76-82
+                    T qm[7];
 #pragma unroll
-            for (int j = 0; j < 7; j++) acc[j] = T(0);
-            const bool inc_row = (i >= 1) && (stoch_row < 0 || stoch_row == i) && (o_coll != nullptr);
-            const T* prow = PROW(i);
-            T csum = T(0);
-            int nact = 0;
-            for (int K = 0; K < kNumLinks; K++) {
-                const int nanc = K + 1 < 7 ? K + 1 : 7;
-                for (int s = s_start[K]; s < s_start[K + 1]; s++) {
-                    const V3<T> x = {prow[3 * s], prow[3 * s + 1], prow[3 * s + 2]};
-                    T d;
-                    V3<T> g;
-                    if (!field_lookup(sc, gm, x, d, g)) continue;
-                    const T pot = get_potential(d, T(s_sph[s].w), P.clearance);
-                    csum += pot;
-                    if (!inc_row || pot < T(0.0001)) continue;
-                    nact++;
-                    V3<T> vel = {T(0), T(0), T(0)}, ac = {T(0), T(0), T(0)};
+                    for (int j = 0; j < 7; j++) qm[j] = (TROW(i + 1)[j] + q[j]) / T(2);
+                    EeOnly<T> ev;
+                    walk_chain<T, 7>(qm, ev);
+                    V3<T> ip, i0, i1, i2;
+                    inter_target(targets + i * 7, targets + (i + 1) * 7, ip, i0, i1, i2);
+                    T angle;
+                    const V3<T> rv = rot_diff_kdl(ev.ee.c0, ev.ee.c1, ev.ee.c2, i0, i1, i2, angle);
+                    const V3<T> dp = ip - ev.ee.p;
+                    red[R_MID_POS] += sqrt_t(dot(dp, dp));
+                    red[R_MID_ROT] += sqrt_t(dot(rv, rv));
+                }
+                bool viol = false;
 #pragma unroll
-                    for (int k = -3; k <= 3; k++) {
-                        const T* pr = PROW(i + k) + 3 * s;
-                        const V3<T> xk = {pr[0], pr[1], pr[2]};
-                        vel = axpy(vel, P.inv_dt * diff_rule<T>(0, k + 3), xk);
-                        ac = axpy(ac, P.inv_dt2 * diff_rule<T>(1, k + 3), xk);
-                    }
-                    const T vel_mag = sqrt_t(dot(vel, vel));
-                    const T vel_mag_sq = vel_mag * vel_mag;
-                    const V3<T> nv = vel * (T(1) / vel_mag);
-                    const V3<T> pg = {-g.x, -g.y, -g.z};
-                    // orthogonal projector P = I - nv nv^T
-                    const V3<T> Pa = axpy(ac, -dot(nv, ac), nv);
-                    const V3<T> Pg = axpy(pg, -dot(nv, pg), nv);
-                    const V3<T> curv = Pa * (T(1) / vel_mag_sq);
-                    const V3<T> cg = (Pg - curv * pot) * vel_mag;
-                    // 3 x nanc positional Jacobian (getJacobian :1164-1187)
-                    V3<T> col[7];
-#pragma unroll
-                    for (int j = 0; j < 7; j++) {
-                        const V3<T> oj = v.fj.o[j] + off;
-                        const V3<T> ax = P.quirk ? v.fj.z[j] + oj : v.fj.z[j];
-                        col[j] = (j < nanc) ? cross(ax, x - oj) : V3<T>{T(0), T(0), T(0)};
-                    }
-                    if (P.use_pinv) {
-                        // calculatePseudoInverse :767-772 : J^T (J J^T + ridge I)^-1, 3x3 algebra in FP64
-                        double M[9] = {P.ridge, 0, 0, 0, P.ridge, 0, 0, 0, P.ridge}, Mi[9];
-#pragma unroll
-                        for (int j = 0; j < 7; j++) {
-                            const double cx = (double)col[j].x, cy = (double)col[j].y, cz = (double)col[j].z;
-                            M[0] += cx * cx; M[1] += cx * cy; M[2] += cx * cz;
-                            M[4] += cy * cy; M[5] += cy * cz; M[8] += cz * cz;
-                        }
-                        M[3] = M[1]; M[6] = M[2]; M[7] = M[5];
-                        mat3_inverse_d(M, Mi);
-                        const double y0 = Mi[0] * (double)cg.x + Mi[1] * (double)cg.y + Mi[2] * (double)cg.z;
-                        const double y1 = Mi[3] * (double)cg.x + Mi[4] * (double)cg.y + Mi[5] * (double)cg.z;
-                        const double y2 = Mi[6] * (double)cg.x + Mi[7] * (double)cg.y + Mi[8] * (double)cg.z;
-#pragma unroll
-                        for (int j = 0; j < 7; j++)
-                            acc[j] -= (T)((double)col[j].x * y0 + (double)col[j].y * y1 + (double)col[j].z * y2);
+                for (int j = 0; j < 7; j++) {
+                    if (P.cj[j]) {
+                        const T* sv = s_v + tid * 7 + j;
+                        const T v0 = sv[0], v1 = sv[7], v2 = sv[14];
+                        const T a0 = (v1 - v0) / P.dt, a1 = (v2 - v1) / P.dt;
+                        if (i < Tn - 1) red[R_VEL_C] += abs_t(v0);
+                        if (i < Tn - 2) red[R_ACC_C] += abs_t(a0);
+                        if (i < Tn - 3) red[R_JERK_C] += abs_t((a1 - a0) / P.dt);
+                        if (i < Tn - 1 && abs_t(v0) > P.vlim[j]) viol = true;
                     } else {
+                        T sv = T(0), sa = T(0), sj = T(0);
 #pragma unroll
-                        for (int j = 0; j < 7; j++) acc[j] -= dot(col[j], cg);
+                        for (int k = -3; k <= 3; k++) {
+                            const T xk = TROW(i + k)[j];
+                            sv += P.rule_v[k + 3] * xk; sa += P.rule_a[k + 3] * xk; sj += P.rule_j[k + 3] * xk;
+                        }
+                        red[R_VEL_N] += abs_t(sv); red[R_ACC_N] += abs_t(sa); red[R_JERK_N] += abs_t(sj);
+                        if (i < Tn - 1 && abs_t(TROW(i + 1)[j] - q[j]) / P.dt > P.vlim[j]) viol = true;
                     }
                 }
-            }
-            red[R_COLL] += csum;
-            red[R_NACTIVE] += T(nact);
-            if (i >= 1 && o_coll) {
-#pragma unroll
-                for (int j = 0; j < 7; j++) o_coll[(i - 1) * 7 + j] = acc[j];
+                if (viol) red[R_NVIOL_P] += T(1);
             }
         }
-
-        // ---- smoothness increments: -(2 A_full x) on the free rows (:1466-1473); group row g = i + 5
-        if (do_smooth && valid && i >= 1 && o_smooth) {
-            const T* ab = Aband + (size_t)(i + 5) * 13;
-            T coef[13];
-#pragma unroll
-            for (int k = 0; k < 13; k++) coef[k] = ab[k];
-#pragma unroll
-            for (int j = 0; j < 7; j++) {
-                T s = T(0);
-#pragma unroll
-                for (int k = 0; k < 13; k++) s += coef[k] * (T(2) * TROW(i + k - 6)[j]);
-                o_smooth[(i - 1) * 7 + j] = -s;
-            }
-        }
-
-        // ---- evaluator: midpoint pose error + joint derivative costs + velocity violations
-        if (do_eval && valid) {
-            if (i < Tn - 1) {
-                T qm[7];
-#pragma unroll
-                for (int j = 0; j < 7; j++) qm[j] = (TROW(i + 1)[j] + q[j]) / T(2);
-                EeOnly<T> ev;
-                walk_chain<T, 7>(qm, ev);
-                V3<T> ip, i0, i1, i2;
-                inter_target(targets + i * 7, targets + (i + 1) * 7, ip, i0, i1, i2);
-                T angle;
-                const V3<T> rv = rot_diff_kdl(ev.ee.c0, ev.ee.c1, ev.ee.c2, i0, i1, i2, angle);
-                const V3<T> dp = ip - ev.ee.p;
-                red[R_MID_POS] += sqrt_t(dot(dp, dp));
-                red[R_MID_ROT] += sqrt_t(dot(rv, rv));
-            }
-            bool viol = false;
-#pragma unroll
-            for (int j = 0; j < 7; j++) {
-                if (P.cj[j]) {
-                    const T* sv = s_v + tid * 7 + j;
-                    const T v0 = sv[0], v1 = sv[7], v2 = sv[14];
-                    const T a0 = (v1 - v0) / P.dt, a1 = (v2 - v1) / P.dt;
-                    if (i < Tn - 1) red[R_VEL_C] += abs_t(v0);
-                    if (i < Tn - 2) red[R_ACC_C] += abs_t(a0);
-                    if (i < Tn - 3) red[R_JERK_C] += abs_t((a1 - a0) / P.dt);
-                    if (i < Tn - 1 && abs_t(v0) > P.vlim[j]) viol = true;
-                } else {
-                    T sv = T(0), sa = T(0), sj = T(0);
-#pragma unroll
-                    for (int k = -3; k <= 3; k++) {
-                        const T xk = TROW(i + k)[j];
-                        sv += P.rule_v[k + 3] * xk; sa += P.rule_a[k + 3] * xk; sj += P.rule_j[k + 3] * xk;
-                    }
-                    red[R_VEL_N] += abs_t(sv); red[R_ACC_N] += abs_t(sa); red[R_JERK_N] += abs_t(sj);
-                    if (i < Tn - 1 && abs_t(TROW(i + 1)[j] - q[j]) / P.dt > P.vlim[j]) viol = true;
-                }
-            }
-            if (viol) red[R_NVIOL] += T(1);
-        }
-#undef TROW
-#undef PROW
     }
-
-    // ---- block reduction of the cost sums
-#pragma unroll
-    for (int k = 0; k < kNRed; k++) {
-        T x = red[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        red[k] = x;
-    }
-    __syncthreads();
-    const int warp = tid >> 5, lane = tid & 31, nwarps = (CH + 31) >> 5;
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < kNRed; k++) s_red[warp * kNRed + k] = red[k];
-    }
-    __syncthreads();
+    T tot[kNRedPose];
+    block_reduce<T, kNRedPose>(red, s_red, tot);
     if (tid == 0) {
-        T tot[kNRed];
-        for (int k = 0; k < kNRed; k++) {
-            T x = T(0);
-            for (int w = 0; w < nwarps; w++) x += s_red[w * kNRed + k];
-            tot[k] = x;
-        }
         T* c = costs + n * RLITG_TORM_NCOST;
         const T tm1 = T(Tn - 1);
         T ev_pos = T(0), ev_rot = T(0), cvel = T(0), cacc = T(0), cjerk = T(0), nviol = T(0);
@@ -443,20 +333,196 @@ torm_kernel(TormP<T> P, const T* __restrict__ traj, const T* __restrict__ target
             cvel = (tot[R_VEL_C] / tm1 + tot[R_VEL_N] / T(Tn)) / T(7);
             cacc = (tot[R_ACC_C] / T(Tn - 2) + tot[R_ACC_N] / T(Tn)) / T(7);
             cjerk = (tot[R_JERK_C] / T(Tn - 3) + tot[R_JERK_N] / T(Tn)) / T(7);
-            nviol = tot[R_NVIOL];
+            nviol = tot[R_NVIOL_P];
         }
         c[0] = ev_pos; c[1] = ev_rot; c[2] = cvel; c[3] = cacc; c[4] = cjerk;
-        c[5] = do_coll ? tot[R_COLL] / T(Tn) : T(0);
+        if (zero_coll_cost) c[5] = T(0);
         c[6] = do_eval ? ev_pos + T(0.17) * ev_rot : T(0);  // getWeightedPoseCost :59-63
         c[7] = nviol;
-        c[8] = do_pose ? tot[R_WP_POS] : T(0);
-        c[9] = do_pose ? tot[R_WP_ROT] : T(0);
+        c[8] = tot[R_WP_POS];
+        c[9] = tot[R_WP_ROT];
+    }
+}
+
+// ---- kernel 3b: sphere potentials + CHOMP increments (A6) + smoothness increments (A7) ---------------------
+// Writes costs[5] and active[]; the other cost entries are zeroed when the pose / evaluator kernel does not run.
+template <typename T>
+__global__ void __launch_bounds__(kTormMaxThreads, 2)
+torm_coll_smooth_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S, const T* __restrict__ Aband,
+                        int stage_mask, int zero_pose_costs, const int32_t* __restrict__ stoch,
+                        T* __restrict__ inc_smooth, T* __restrict__ inc_coll, T* __restrict__ costs,
+                        float* __restrict__ active) {
+    const int CH = blockDim.x, tid = threadIdx.x, Tn = P.Tn;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* s_traj = reinterpret_cast<T*>(smem_raw);  // [(CH + 12)][7]
+    T* s_red = s_traj + (CH + 12) * 7;           // [8][2]
+    T* s_pos = s_red + 8 * 2;                    // [(CH + 6)][S][3] rows c0-3 .. c0+CH+2
+    __shared__ float4 s_sph[kMaxSpheres];
+    __shared__ int s_start[kNumLinks + 1];
+    __shared__ int s_nanc[kMaxSpheres];  // joints that move sphere s: min(link + 1, 7) (torm_optimizer.cpp:263-309)
+
+    const bool do_coll = (stage_mask & RLITG_STAGE_COLL) != 0;
+    const bool do_smooth = (stage_mask & RLITG_STAGE_SMOOTH) != 0;
+    if (do_coll) {
+        for (int i = tid; i < S; i += CH) {
+            s_sph[i] = sc.spheres[i];
+            int link = 0;
+            while (link < kNumLinks - 1 && i >= sc.link_start[link + 1]) link++;
+            s_nanc[i] = link + 1 < 7 ? link + 1 : 7;
+        }
+        if (tid <= kNumLinks) s_start[tid] = sc.link_start[tid];
+    }
+    const int64_t n = blockIdx.x;
+    const T* tr = traj + n * (int64_t)Tn * 7;
+    const int F = Tn - 1;
+    T* o_smooth = inc_smooth ? inc_smooth + n * (int64_t)F * 7 : nullptr;
+    T* o_coll = inc_coll ? inc_coll + n * (int64_t)F * 7 : nullptr;
+    const int stoch_row = stoch ? stoch[n] + 1 : -1;  // full-trajectory row of the single stochastic waypoint
+    const V3<T> off = {P.off[0], P.off[1], P.off[2]};
+    const GridMap<T> gm(sc);
+    T red[2] = {T(0), T(0)};  // potential sum, active sphere count
+
+    for (int c0 = 0; c0 < Tn; c0 += CH) {
+        __syncthreads();
+        for (int idx = tid; idx < (CH + 12) * 7; idx += CH) {
+            const int r = idx / 7, j = idx - r * 7;
+            s_traj[idx] = tr[min(max(c0 - 6 + r, 0), Tn - 1) * 7 + j];
+        }
+        __syncthreads();
+        const int i = c0 + tid;
+        const bool valid = i < Tn;
+
+        // ---- smoothness increments: -(2 A_full x) on the free rows (:1466-1473); group row g = i + 5
+        if (do_smooth && valid && i >= 1 && o_smooth) {
+            const T* ab = Aband + (size_t)(i + 5) * 13;
+            T coef[13];
+#pragma unroll
+            for (int k = 0; k < 13; k++) coef[k] = ab[k];
+#pragma unroll
+            for (int j = 0; j < 7; j++) {
+                T sacc = T(0);
+#pragma unroll
+                for (int k = 0; k < 13; k++) sacc += coef[k] * (T(2) * TROW(i + k - 6)[j]);
+                o_smooth[(i - 1) * 7 + j] = -sacc;
+            }
+        }
+        if (!do_coll) continue;
+
+        // ---- phase 1: FK of this row -> sphere centres (+ halo rows of a chunked path)
+        TormVisit<T> v;
+        v.sph = s_sph; v.link_start = s_start; v.off = off;
+        v.sph_row = nullptr;
+        if (valid) {
+            T q[7];
+#pragma unroll
+            for (int j = 0; j < 7; j++) q[j] = TROW(i)[j];
+            v.sph_row = PROW(i);
+            walk_chain<T, 7>(q, v);
+        }
+        if (tid < 6) {
+            const int hr = tid < 3 ? c0 - 3 + tid : c0 + CH + (tid - 3);
+            if (hr >= 0 && hr < Tn) halo_sphere_row<T>(TROW(hr), PROW(hr), s_sph, s_start, off);
+        }
+        __syncthreads();
+
+        // ---- phase 2: potentials, cost, CHOMP increments
+        if (valid) {
+            T acc[7];
+#pragma unroll
+            for (int j = 0; j < 7; j++) acc[j] = T(0);
+            const bool inc_row = (i >= 1) && (stoch_row < 0 || stoch_row == i) && (o_coll != nullptr);
+            const T* prow = PROW(i);
+            T csum = T(0);
+            int nact = 0;
+            // distance-record gathers run two spheres ahead of the arithmetic (L2 latency off the critical path)
+            auto fetch = [&](int s) -> float4 {
+                const V3<T> x = {prow[3 * s], prow[3 * s + 1], prow[3 * s + 2]};
+                const int64_t c = gm.cell(x);
+                return c >= 0 ? __ldg(sc.field + c) : make_float4(1e30f, 0.f, 0.f, 0.f);
+            };
+            float4 r0 = fetch(0), r1 = S > 1 ? fetch(1) : make_float4(1e30f, 0.f, 0.f, 0.f);
+            for (int s = 0; s < S; s++) {
+                const float4 rec = r0;
+                r0 = r1;
+                if (s + 2 < S) r1 = fetch(s + 2);
+                if (!(rec.x < 1e29f)) continue;
+                const float4 sp = s_sph[s];
+                const T pot = get_potential(T(rec.x), T(sp.w), P.clearance);
+                csum += pot;
+                if (!inc_row || pot < T(0.0001)) continue;
+                nact++;
+                const int nanc = s_nanc[s];
+                const V3<T> x = {prow[3 * s], prow[3 * s + 1], prow[3 * s + 2]};
+                V3<T> vel = {T(0), T(0), T(0)}, ac = {T(0), T(0), T(0)};
+#pragma unroll
+                for (int k = -3; k <= 3; k++) {
+                    const T* pr = PROW(i + k) + 3 * s;
+                    const V3<T> xk = {pr[0], pr[1], pr[2]};
+                    vel = axpy(vel, P.inv_dt * diff_rule<T>(0, k + 3), xk);
+                    ac = axpy(ac, P.inv_dt2 * diff_rule<T>(1, k + 3), xk);
+                }
+                const T vel_mag = sqrt_t(dot(vel, vel));
+                const T vel_mag_sq = vel_mag * vel_mag;
+                const V3<T> nv = vel * (T(1) / vel_mag);
+                const V3<T> pg = {-T(rec.y), -T(rec.z), -T(rec.w)};
+                // orthogonal projector P = I - nv nv^T
+                const V3<T> Pa = axpy(ac, -dot(nv, ac), nv);
+                const V3<T> Pg = axpy(pg, -dot(nv, pg), nv);
+                const V3<T> curv = Pa * (T(1) / vel_mag_sq);
+                const V3<T> cg = (Pg - curv * pot) * vel_mag;
+                // 3 x nanc positional Jacobian (getJacobian :1164-1187)
+                V3<T> col[7];
+#pragma unroll
+                for (int j = 0; j < 7; j++) {
+                    const V3<T> oj = v.fj.o[j] + off;
+                    const V3<T> ax = P.quirk ? v.fj.z[j] + oj : v.fj.z[j];
+                    col[j] = (j < nanc) ? cross(ax, x - oj) : V3<T>{T(0), T(0), T(0)};
+                }
+                if (P.use_pinv) {
+                    // calculatePseudoInverse :767-772 : J^T (J J^T + ridge I)^-1 ; the ridge bounds cond <= ~1e4
+                    const T rdg = (T)P.ridge;
+                    T M[9] = {rdg, T(0), T(0), T(0), rdg, T(0), T(0), T(0), rdg}, Mi[9];
+#pragma unroll
+                    for (int j = 0; j < 7; j++) {
+                        M[0] += col[j].x * col[j].x; M[1] += col[j].x * col[j].y; M[2] += col[j].x * col[j].z;
+                        M[4] += col[j].y * col[j].y; M[5] += col[j].y * col[j].z; M[8] += col[j].z * col[j].z;
+                    }
+                    M[3] = M[1]; M[6] = M[2]; M[7] = M[5];
+                    mat3_inverse<T>(M, Mi);
+                    const V3<T> y = {Mi[0] * cg.x + Mi[1] * cg.y + Mi[2] * cg.z, Mi[3] * cg.x + Mi[4] * cg.y + Mi[5] * cg.z,
+                                     Mi[6] * cg.x + Mi[7] * cg.y + Mi[8] * cg.z};
+#pragma unroll
+                    for (int j = 0; j < 7; j++) acc[j] -= dot(col[j], y);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 7; j++) acc[j] -= dot(col[j], cg);
+                }
+            }
+            red[0] += csum;
+            red[1] += T(nact);
+            if (i >= 1 && o_coll) {
+#pragma unroll
+                for (int j = 0; j < 7; j++) o_coll[(i - 1) * 7 + j] = acc[j];
+            }
+        }
+    }
+    T tot[2];
+    block_reduce<T, 2>(red, s_red, tot);
+    if (tid == 0) {
+        T* c = costs + n * RLITG_TORM_NCOST;
+        c[5] = do_coll ? tot[0] / T(Tn) : T(0);
+        if (zero_pose_costs) {
+            c[0] = c[1] = c[2] = c[3] = c[4] = T(0);
+            c[6] = c[7] = c[8] = c[9] = T(0);
+        }
         if (active) {
             const int rows = (stoch_row >= 0) ? 1 : Tn - 1;
-            active[n] = do_coll ? (float)(tot[R_NACTIVE] / T(rows)) : 0.f;
+            active[n] = do_coll ? (float)(tot[1] / T(rows)) : 0.f;
         }
     }
 }
+#undef TROW
+#undef PROW
 
 // ---- smoothness operator (host, FP64): TormCost ctor + scaling -------------------------------------------
 struct Smooth {
@@ -567,28 +633,47 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
                        const RlitgTormParams* p, int stage_mask, const int32_t* stoch, T* inc_smooth, T* inc_coll,
                        T* inc_pose, T* costs, float* active, cudaStream_t st) {
     TormP<T> P = convert_params<T>(*p);
-    SceneDev sd{};
-    int S = 0;
-    if (stage_mask & RLITG_STAGE_COLL) {
-        sd = scene_dev(scene);
-        S = sd.S;
-    }
     const int CH = std::min(kTormMaxThreads, ((p->T + 31) / 32) * 32);
-    const size_t smem = sizeof(T) * ((size_t)(CH + 12) * 7 + (size_t)(CH + 3) * 7 + 8 * kNRed + (size_t)(CH + 6) * S * 3);
-    if (smem > 220 * 1024) return set_error(RLITG_ERR_SHAPE, "too many spheres for the shared-memory tile");
-    auto kern = torm_kernel<T>;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return set_cuda_error("cudaFuncSetAttribute(torm_kernel)");
-        attr_smem = smem;
+    const bool run_pose = (stage_mask & (RLITG_STAGE_POSE | RLITG_STAGE_POSE_GRAD | RLITG_STAGE_EVAL)) != 0;
+    const bool run_coll = (stage_mask & (RLITG_STAGE_COLL | RLITG_STAGE_SMOOTH)) != 0;
+    if (!run_pose && !run_coll) return set_error(RLITG_ERR_ARG, "stage_mask selects no stage");
+    if (run_pose) {
+        const size_t smem = sizeof(T) * ((size_t)(CH + 12) * 7 + (size_t)(CH + 3) * 7 + 8 * kNRedPose);
+        auto kern = torm_pose_eval_kernel<T>;
+        static size_t attr_smem = 0;
+        if (smem > attr_smem) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                return set_cuda_error("cudaFuncSetAttribute(torm_pose_eval_kernel)");
+            attr_smem = smem;
+        }
+        kern<<<(unsigned)N, CH, smem, st>>>(P, traj, targets, stage_mask, run_coll ? 0 : 1, inc_pose, costs);
+        int rc = check_launch("torm_pose_eval_kernel");
+        if (rc) return rc;
     }
-    const T* band = nullptr;
-    if (stage_mask & RLITG_STAGE_SMOOTH)
-        band = reinterpret_cast<const T*>(sizeof(T) == 4 ? (const void*)smooth->d_band32 : (const void*)smooth->d_band64);
-    kern<<<(unsigned)N, CH, smem, st>>>(P, traj, targets, sd, S, band, stage_mask, stoch, inc_smooth, inc_coll, inc_pose,
-                                        costs, active);
-    return check_launch("torm_kernel");
+    if (run_coll) {
+        SceneDev sd{};
+        int S = 0;
+        if (stage_mask & RLITG_STAGE_COLL) {
+            sd = scene_dev(scene);
+            S = sd.S;
+        }
+        const size_t smem = sizeof(T) * ((size_t)(CH + 12) * 7 + 8 * 2 + (size_t)(CH + 6) * S * 3);
+        if (smem > 220 * 1024) return set_error(RLITG_ERR_SHAPE, "too many spheres for the shared-memory tile");
+        auto kern = torm_coll_smooth_kernel<T>;
+        static size_t attr_smem = 0;
+        if (smem > attr_smem) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                return set_cuda_error("cudaFuncSetAttribute(torm_coll_smooth_kernel)");
+            attr_smem = smem;
+        }
+        const T* band = nullptr;
+        if (stage_mask & RLITG_STAGE_SMOOTH)
+            band = reinterpret_cast<const T*>(sizeof(T) == 4 ? (const void*)smooth->d_band32 : (const void*)smooth->d_band64);
+        kern<<<(unsigned)N, CH, smem, st>>>(P, traj, sd, S, band, stage_mask, run_pose ? 0 : 1, stoch, inc_smooth, inc_coll,
+                                            costs, active);
+        return check_launch("torm_coll_smooth_kernel");
+    }
+    return RLITG_OK;
 }
 
 }  // namespace rlitg

@@ -67,7 +67,7 @@ def fk_jac(q, want_pos=True, want_rot=True, want_quat=False, want_jac=True, q_so
     quat = alloc("quat", want_quat, (B, 4), (4, B))
     jac = alloc("jac", want_jac, (B, 6, D), (6 * D, B))
     flags = (_lib.Q_SOA if q_soa else 0) | (_lib.OUT_SOA if out_soa else 0)
-    with torch.cuda.device(q.device):
+    with _lib.on_device(q.device):
         check(lib.rlitg_fk_jac(q.data_ptr(), B, D, _dtype_code(q), flags, _ptr(pos), _ptr(rot), _ptr(quat),
                                _ptr(jac), _stream()))
     return dict(pos=pos, rot=rot, quat=quat, jac=jac)
@@ -86,7 +86,7 @@ def allfk(q, q_soa=False, out=None):
     q, B, D = _prep(q, q_soa)
     if out is None:
         out = torch.empty((B, D + 1, 7), device=q.device, dtype=q.dtype)
-    with torch.cuda.device(q.device):
+    with _lib.on_device(q.device):
         check(lib.rlitg_allfk(q.data_ptr(), B, D, _dtype_code(q), _lib.Q_SOA if q_soa else 0, out.data_ptr(),
                               _stream()))
     return out

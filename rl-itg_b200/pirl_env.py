@@ -83,7 +83,7 @@ def nullspace_norm(err, q):
     """jaco_srv(err, q).objective_value for a batch (pirl/src/kinematic_solver.cpp:332-351)."""
     err, q = err.contiguous(), q.contiguous()
     out = torch.empty(q.shape[0], device=q.device, dtype=q.dtype)
-    with torch.cuda.device(q.device):
+    with _lib.on_device(q.device):
         check(lib.rlitg_nullspace_norm(err.data_ptr(), q.data_ptr(), q.shape[0], _code(q), out.data_ptr(), _stream()))
     return out
 
@@ -92,7 +92,7 @@ def pinv_step(q, twist, eps=1e-5):
     """TormIKSolver::vikSolver for a batch (torm/src/torm_ik_solver.cpp:169-171)."""
     q, twist = q.contiguous(), twist.contiguous()
     dq = torch.empty_like(q)
-    with torch.cuda.device(q.device):
+    with _lib.on_device(q.device):
         check(lib.rlitg_pinv_step(q.data_ptr(), twist.data_ptr(), q.shape[0], q.shape[1], _code(q), float(eps),
                                   dq.data_ptr(), _stream()))
     return dq
@@ -102,7 +102,7 @@ def pose_diff(q, target):
     """KDL::diff(FK(q), target) for a batch -> twist [B,6]."""
     q, target = q.contiguous(), target.contiguous()
     tw = torch.empty(q.shape[0], 6, device=q.device, dtype=q.dtype)
-    with torch.cuda.device(q.device):
+    with _lib.on_device(q.device):
         check(lib.rlitg_pose_diff(q.data_ptr(), target.data_ptr(), q.shape[0], q.shape[1], _code(q), tw.data_ptr(),
                                   _stream()))
     return tw
@@ -140,6 +140,7 @@ class PirlVecEnv:
         self.errs = torch.empty(B, 4, dtype=dtype, **kw) if want_errs else None
         self.target_poses = self.demo_configs = self.latent = None
         self.Tmax = 0
+        self._pre = self._post = self._info = None
         self._base_off = np.ascontiguousarray(scene.base_offset if scene is not None else fetch.BASE_OFFSET, dtype=np.float64)
 
     # -- problems ------------------------------------------------------------------------------------------
@@ -154,6 +155,7 @@ class PirlVecEnv:
         self.latent = conv(latent)
         if self.cfg.z_dim > 0 and self.latent is None:
             self.latent = torch.zeros(self.B, self.cfg.z_dim, device=self.device, dtype=self.dtype)
+        self._pre = None
 
     def reset(self, start_conf=None, mode="train"):
         """PirlEnv_Fetch.reset (PirlEnv.py:352-392): cur_conf = demo_configs[0] (continuous joints refined to
@@ -175,10 +177,11 @@ class PirlVecEnv:
         self.cur_conf = q0.contiguous()
         self.timestep.zero_()
         self.counters.zero_()
+        self._pre = None
         return self._observe()
 
     def _observe(self):
-        with torch.cuda.device(self.device):
+        with _lib.on_device(self.device):
             check(lib.rlitg_pirl_obs(C.byref(self.cfg), self.B, _code(self.cur_conf), self.cur_conf.data_ptr(),
                                      self.timestep.data_ptr(), self.max_timestep.data_ptr(),
                                      self.target_poses.data_ptr(), self.Tmax,
@@ -186,24 +189,45 @@ class PirlVecEnv:
                                      _stream()))
         return self.obs
 
+    def _bind(self):
+        """argument tuple of rlitg_pirl_env_step for the current buffers (pointers as python ints: hot path)"""
+        p = lambda t: None if t is None else t.data_ptr()
+        self._info = {"task_suc_count": self.counters[:, 0], "dist_suc_count": self.counters[:, 1],
+                      "rot_suc_count": self.counters[:, 2], "imitate_suc_count": self.counters[:, 3],
+                      "is_col": self.flags[:, 0], "is_jlimit": self.flags[:, 1], "is_early_stop": self.flags[:, 2],
+                      "is_timeout": self.flags[:, 3]}
+        self._pre = (C.byref(self.cfg), self.B, _code(self.cur_conf), self.cur_conf.data_ptr())
+        self._post = (self.timestep.data_ptr(), self.max_timestep.data_ptr(), self.target_poses.data_ptr(),
+                      p(self.demo_configs), self.Tmax, p(self.latent),
+                      None if self.scene is None else self.scene.handle, self._base_off.ctypes.data,
+                      self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(), self.flags.data_ptr(),
+                      self.counters.data_ptr(), p(self.errs))
+
     def step(self, action):
         """action: [B,7] tensor (any float dtype; converted to float32 like the policy output).
-        Returns obs [B,O], reward [B], done [B] (uint8), info dict of tensors (keys of PirlEnv.py:273-282)."""
-        a = torch.as_tensor(action, device=self.device).to(torch.float32).contiguous()
-        with torch.cuda.device(self.device):
-            check(lib.rlitg_pirl_env_step(
-                C.byref(self.cfg), self.B, _code(self.cur_conf), self.cur_conf.data_ptr(), a.data_ptr(),
-                self.timestep.data_ptr(), self.max_timestep.data_ptr(), self.target_poses.data_ptr(),
-                None if self.demo_configs is None else self.demo_configs.data_ptr(), self.Tmax,
-                None if self.latent is None else self.latent.data_ptr(),
-                None if self.scene is None else self.scene.handle, self._base_off.ctypes.data, self.obs.data_ptr(),
-                self.reward.data_ptr(), self.done.data_ptr(), self.flags.data_ptr(), self.counters.data_ptr(),
-                None if self.errs is None else self.errs.data_ptr(), _stream()))
-        info = {"task_suc_count": self.counters[:, 0], "dist_suc_count": self.counters[:, 1],
-                "rot_suc_count": self.counters[:, 2], "imitate_suc_count": self.counters[:, 3],
-                "is_col": self.flags[:, 0], "is_jlimit": self.flags[:, 1], "is_early_stop": self.flags[:, 2],
-                "is_timeout": self.flags[:, 3]}
-        return self.obs, self.reward, self.done, info
+        Returns obs [B,O], reward [B], done [B] (uint8), info dict of tensors (keys of PirlEnv.py:273-282).
+        The returned tensors are the env's own buffers (overwritten by the next step)."""
+        a = action
+        if not (torch.is_tensor(a) and a.dtype == torch.float32 and a.is_cuda and a.is_contiguous()):
+            a = torch.as_tensor(action, device=self.device).to(torch.float32).contiguous()
+        if self._pre is None:
+            self._bind()
+        with _lib.on_device(self.device):
+            rc = lib.rlitg_pirl_env_step(*self._pre, a.data_ptr(), *self._post, _stream())
+        if rc:
+            check(rc)
+        return self.obs, self.reward, self.done, self._info
+
+    def capture_step_graph(self, action_buffer):
+        """CUDA-graph the step for launch-bound batch sizes: returns (graph, outputs).  `action_buffer` is a
+        persistent float32 [B,7] CUDA tensor the caller overwrites before each `graph.replay()`."""
+        assert action_buffer.dtype == torch.float32 and action_buffer.is_cuda and action_buffer.is_contiguous()
+        self.step(action_buffer)  # warm-up outside capture (sets kernel attributes)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = self.step(action_buffer)
+        return g, out
 
     def random_action(self):
         lo = torch.tensor(self.act_ll, device=self.device, dtype=torch.float32)

@@ -32,7 +32,7 @@ class Scene:
         self.device = torch.device(device)
         self.base_offset = np.ascontiguousarray(base_offset, dtype=np.float64)
         self._h = C.c_void_p()
-        with torch.cuda.device(self.device):
+        with _lib.on_device(self.device):
             check(lib.rlitg_scene_create(C.byref(self._h)))
         self.shape = None
         self.origin = None
@@ -51,7 +51,7 @@ class Scene:
         link = np.ascontiguousarray(link, dtype=np.int32)
         center = np.ascontiguousarray(center, dtype=np.float64)
         radius = np.ascontiguousarray(radius, dtype=np.float64)
-        with torch.cuda.device(self.device):
+        with _lib.on_device(self.device):
             check(lib.rlitg_scene_set_spheres(self._h, int(link.shape[0]), link.ctypes.data, center.ctypes.data,
                                               radius.ctypes.data))
         self.spheres = (link, center, radius)
@@ -61,7 +61,7 @@ class Scene:
         occ = np.ascontiguousarray(np.asarray(occ) != 0, dtype=np.uint8)
         nz, ny, nx = occ.shape
         org = np.ascontiguousarray(origin, dtype=np.float64)
-        with torch.cuda.device(self.device):
+        with _lib.on_device(self.device):
             check(lib.rlitg_scene_set_occupancy(self._h, occ.ctypes.data, nx, ny, nz, org.ctypes.data, float(res),
                                                 float(max_prop)))
         self.shape, self.origin, self.res = (nz, ny, nx), org, float(res)
@@ -77,21 +77,21 @@ class Scene:
         nz, ny, nx, four = field.shape
         assert four == 4
         org = np.ascontiguousarray(origin, dtype=np.float64)
-        with torch.cuda.device(self.device):
+        with _lib.on_device(self.device):
             check(lib.rlitg_scene_set_field(self._h, field.ctypes.data, nx, ny, nz, org.ctypes.data, float(res)))
         self.shape, self.origin, self.res = (nz, ny, nx), org, float(res)
 
     def get_field(self):
         nz, ny, nx = self.shape
         out = np.empty((nz, ny, nx, 4), dtype=np.float32)
-        with torch.cuda.device(self.device):
+        with _lib.on_device(self.device):
             check(lib.rlitg_scene_get_field(self._h, out.ctypes.data))
         return out
 
     def get_bits(self):
         nz, ny, nx = self.shape
         out = np.empty((nz, ny, (nx + 31) // 32), dtype=np.uint32)
-        with torch.cuda.device(self.device):
+        with _lib.on_device(self.device):
             check(lib.rlitg_scene_get_bits(self._h, out.ctypes.data))
         return out
 
@@ -101,7 +101,7 @@ class Scene:
         B = q.shape[0]
         out = torch.empty(B, dtype=torch.uint8, device=q.device)
         dt = _lib.F32 if q.dtype == torch.float32 else _lib.F64
-        with torch.cuda.device(q.device):
+        with _lib.on_device(q.device):
             check(lib.rlitg_sphere_grid_collide(q.data_ptr(), B, dt, self._h, self.base_offset.ctypes.data,
                                                 out.data_ptr(), torch.cuda.current_stream().cuda_stream))
         return out

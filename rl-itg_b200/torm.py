@@ -93,7 +93,7 @@ class TormCost:
         self.T, self.device = int(T), torch.device(device)
         self._h = _vp()
         w = np.ascontiguousarray(weights, dtype=np.float64)
-        with torch.cuda.device(self.device):
+        with _lib.on_device(self.device):
             check(lib.rlitg_smooth_create(self.T, float(dt), w.ctypes.data, float(ridge), C.byref(self._h)))
 
     @property
@@ -166,7 +166,7 @@ class TormBatch:
             st = torch.as_tensor(stochastic_idx).to(self.device, torch.int32).contiguous()
         p = lambda t: None if t is None else t.data_ptr()
         code = _lib.F32 if traj.dtype == torch.float32 else _lib.F64
-        with torch.cuda.device(self.device):
+        with _lib.on_device(self.device):
             check(lib.rlitg_torm_cost_grad(traj.data_ptr(), self.endPoses_desired_.data_ptr(), N, code,
                                            None if self.scene is None else self.scene.handle,
                                            self.joint_costs_.handle, C.byref(self._cp), int(stage_mask), p(st),
