@@ -100,56 +100,76 @@ RLITG_DEV T mgs_rows(T (&Q)[6 * D], T (&R)[36]) {
     return rmin / (rmax > T(1e-30) ? rmax : T(1e-30));
 }
 
-// dq = pinv(J) v with singular values below eps zeroed: one-sided Jacobi on A = J^T (D x 6), FP64.
-// (A V = U S  =>  pinv(J) = A S^-2 V^T.)  Not inlined: it is the rare path of the FP32 build.
+// dq = pinv(J) v with singular values below eps zeroed: one-sided (Hestenes) Jacobi SVD of A = J^T (D x 6).
+// (A V = U S  =>  pinv(J) = A S^-2 V^T.)  Every loop has compile-time bounds, so A and V live in registers; the
+// function is kept out of line because it is the rare path of the FP32 build (a warp that takes it must not
+// stretch the kernel's tail: ~6 sweeps of 15 rotations in FP32).  Arithmetic in T.
 template <typename T, int D>
-__device__ __noinline__ void pinv_svd_apply(const T* J, const T* v6, double eps, T* dq) {
-    double A[D][6], V[6][6];
+__device__ __noinline__ void pinv_svd_apply(const T* Jin, const T* v6, double eps, T* dq) {
+    T A[D][6], V[6][6];
+#pragma unroll
     for (int i = 0; i < D; i++)
-        for (int c = 0; c < 6; c++) A[i][c] = (double)J[c * D + i];
+#pragma unroll
+        for (int c = 0; c < 6; c++) A[i][c] = Jin[c * D + i];
+#pragma unroll
     for (int i = 0; i < 6; i++)
-        for (int c = 0; c < 6; c++) V[i][c] = (i == c) ? 1.0 : 0.0;
-    for (int sweep = 0; sweep < 60; sweep++) {
-        double off = 0.0;
-        for (int p = 0; p < 5; p++)
+#pragma unroll
+        for (int c = 0; c < 6; c++) V[i][c] = (i == c) ? T(1) : T(0);
+    const T tol = sizeof(T) == 4 ? T(1e-7) : T(1e-15);
+    for (int sweep = 0; sweep < 40; sweep++) {
+        T off = T(0);
+#pragma unroll
+        for (int p = 0; p < 5; p++) {
+#pragma unroll
             for (int r = p + 1; r < 6; r++) {
-                double alpha = 0, beta = 0, gamma = 0;
+                T alpha = T(0), beta = T(0), gamma = T(0);
+#pragma unroll
                 for (int i = 0; i < D; i++) {
                     alpha += A[i][p] * A[i][p];
                     beta += A[i][r] * A[i][r];
                     gamma += A[i][p] * A[i][r];
                 }
-                if (gamma == 0.0) continue;
-                const double ab = alpha * beta;
-                const double lim = fabs(gamma) / sqrt(ab > 0 ? ab : 1e-300);
-                off = fmax(off, lim);
-                const double zeta = (beta - alpha) / (2.0 * gamma);
-                const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                const double c = 1.0 / sqrt(1.0 + tt * tt), s = c * tt;
-                for (int i = 0; i < D; i++) {
-                    const double ap = A[i][p], ar = A[i][r];
-                    A[i][p] = c * ap - s * ar;
-                    A[i][r] = s * ap + c * ar;
-                }
-                for (int i = 0; i < 6; i++) {
-                    const double vp = V[i][p], vr = V[i][r];
-                    V[i][p] = c * vp - s * vr;
-                    V[i][r] = s * vp + c * vr;
+                const T ab = alpha * beta;
+                const T lim = abs_t(gamma) * rsqrt_t(ab > T(0) ? ab : T(1e-30));
+                if (gamma != T(0)) {
+                    off = lim > off ? lim : off;
+                    const T zeta = (beta - alpha) / (T(2) * gamma);
+                    const T tt = (zeta >= T(0) ? T(1) : T(-1)) / (abs_t(zeta) + sqrt_t(T(1) + zeta * zeta));
+                    const T c = rsqrt_t(T(1) + tt * tt), sn = c * tt;
+#pragma unroll
+                    for (int i = 0; i < D; i++) {
+                        const T ap = A[i][p], ar = A[i][r];
+                        A[i][p] = c * ap - sn * ar;
+                        A[i][r] = sn * ap + c * ar;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 6; i++) {
+                        const T vp = V[i][p], vr = V[i][r];
+                        V[i][p] = c * vp - sn * vr;
+                        V[i][r] = sn * vp + c * vr;
+                    }
                 }
             }
-        if (off < 1e-15) break;
+        }
+        if (off < tol) break;
     }
-    double acc[D];
-    for (int i = 0; i < D; i++) acc[i] = 0.0;
+    T acc[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) acc[i] = T(0);
+#pragma unroll
     for (int c = 0; c < 6; c++) {
-        double s2 = 0;
+        T s2 = T(0);
+#pragma unroll
         for (int i = 0; i < D; i++) s2 += A[i][c] * A[i][c];
-        if (sqrt(s2) < eps) continue;
-        double proj = 0;
-        for (int r = 0; r < 6; r++) proj += V[r][c] * (double)v6[r];
-        for (int i = 0; i < D; i++) acc[i] += A[i][c] * (proj / s2);
+        T proj = T(0);
+#pragma unroll
+        for (int r = 0; r < 6; r++) proj += V[r][c] * v6[r];
+        const T w = (sqrt_t(s2) < T(eps)) ? T(0) : proj / s2;  // truncated SVD: singular values below eps dropped
+#pragma unroll
+        for (int i = 0; i < D; i++) acc[i] += A[i][c] * w;
     }
-    for (int i = 0; i < D; i++) dq[i] = (T)acc[i];
+#pragma unroll
+    for (int i = 0; i < D; i++) dq[i] = acc[i];
 }
 
 // dq = pinv(J) v.  FP32: min-norm solution through the QR of J^T (J = R^T Q, so dq = Q^T-rows * y with

@@ -19,6 +19,7 @@
 // FP32-FMA bound on paper, L2-gather latency bound in practice.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "fetch_chain.cuh"
@@ -61,6 +62,12 @@ template <typename T> RLITG_DEV T normalize_angle_positive(T a) {
 }
 template <typename T> RLITG_DEV T shortest_angular_distance(T start, T end) {
     const T pi = T(3.14159265358979323846), two_pi = T(2.0 * 3.14159265358979323846);
+    if constexpr (sizeof(T) == 4) {
+        // same value as the fmod chain below (the difference wrapped into [-pi, pi]) without five fmodf calls;
+        // differs only in which of +-pi is returned for an exact half turn
+        const float d = end - start;
+        return fmaf(-rintf(d * 0.15915494309189535f), two_pi, d);
+    }
     T res = normalize_angle_positive(normalize_angle_positive(end) - normalize_angle_positive(start));
     if (res > pi) res = -(two_pi - res);
     T a = normalize_angle_positive(res);
@@ -210,13 +217,13 @@ RLITG_DEV void block_reduce(T (&red)[NR], T* s_red, T (&tot)[NR]) {
 }
 
 #define TROW(row) (s_traj + (min(max((row), 0), Tn - 1) - c0 + 6) * 7)
-#define PROW(row) (s_pos + (size_t)(min(max((row), 0), Tn - 1) - c0 + 3) * S * 3)
+#define PROW(row) (s_pos + (size_t)(min(max((row), 0), Tn - 1) - c0 + 3) * PS)
 
 // ---- kernel 3a: end-pose error / pinv step (A5) + trajectory evaluator (A8) -------------------------------
 // Writes costs[0..4], [6..9]; costs[5] (collision) is zeroed when the collision kernel does not run.
 constexpr int kNRedPose = 11;
-template <typename T>
-__global__ void __launch_bounds__(kTormMaxThreads, 2)
+template <typename T, int MINB>
+__global__ void __launch_bounds__(kTormMaxThreads, MINB)
 torm_pose_eval_kernel(TormP<T> P, const T* __restrict__ traj, const T* __restrict__ targets, int stage_mask,
                       int zero_coll_cost, T* __restrict__ inc_pose, T* __restrict__ costs) {
     const int CH = blockDim.x, tid = threadIdx.x, Tn = P.Tn;
@@ -356,7 +363,8 @@ torm_coll_smooth_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* s_traj = reinterpret_cast<T*>(smem_raw);  // [(CH + 12)][7]
     T* s_red = s_traj + (CH + 12) * 7;           // [8][2]
-    T* s_pos = s_red + 8 * 2;                    // [(CH + 6)][S][3] rows c0-3 .. c0+CH+2
+    T* s_pos = s_red + 8 * 2;                    // [(CH + 6)][PS] rows c0-3 .. c0+CH+2, PS = 3 S padded to odd
+    const int PS = (3 * S) | 1;                  // odd row stride: thread-per-row accesses are bank-conflict free
     __shared__ float4 s_sph[kMaxSpheres];
     __shared__ int s_start[kNumLinks + 1];
     __shared__ int s_nanc[kMaxSpheres];  // joints that move sphere s: min(link + 1, 7) (torm_optimizer.cpp:263-309)
@@ -432,6 +440,16 @@ torm_coll_smooth_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int
             for (int j = 0; j < 7; j++) acc[j] = T(0);
             const bool inc_row = (i >= 1) && (stoch_row < 0 || stoch_row == i) && (o_coll != nullptr);
             const T* prow = PROW(i);
+            const T* nrow[7];  // the seven stencil rows (clamped), resolved once per waypoint
+#pragma unroll
+            for (int k = 0; k < 7; k++) nrow[k] = PROW(i + k - 3);
+            // joint origins / "axes" in the planning frame (computeJointProperties :1125-1162), once per waypoint
+            V3<T> jo[7], ja[7];
+#pragma unroll
+            for (int j = 0; j < 7; j++) {
+                jo[j] = v.fj.o[j] + off;
+                ja[j] = P.quirk ? v.fj.z[j] + jo[j] : v.fj.z[j];  // axis = joint_transform * axis (:1157)
+            }
             T csum = T(0);
             int nact = 0;
             // distance-record gathers run two spheres ahead of the arithmetic (L2 latency off the critical path)
@@ -451,52 +469,55 @@ torm_coll_smooth_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int
                 csum += pot;
                 if (!inc_row || pot < T(0.0001)) continue;
                 nact++;
-                const int nanc = s_nanc[s];
+                const int nanc = s_nanc[s];  // uniform over the warp: every lane is on sphere s
                 const V3<T> x = {prow[3 * s], prow[3 * s + 1], prow[3 * s + 2]};
                 V3<T> vel = {T(0), T(0), T(0)}, ac = {T(0), T(0), T(0)};
 #pragma unroll
-                for (int k = -3; k <= 3; k++) {
-                    const T* pr = PROW(i + k) + 3 * s;
+                for (int k = 0; k < 7; k++) {
+                    const T* pr = nrow[k] + 3 * s;
                     const V3<T> xk = {pr[0], pr[1], pr[2]};
-                    vel = axpy(vel, P.inv_dt * diff_rule<T>(0, k + 3), xk);
-                    ac = axpy(ac, P.inv_dt2 * diff_rule<T>(1, k + 3), xk);
+                    if (k != 3) vel = axpy(vel, P.inv_dt * diff_rule<T>(0, k), xk);
+                    ac = axpy(ac, P.inv_dt2 * diff_rule<T>(1, k), xk);
                 }
-                const T vel_mag = sqrt_t(dot(vel, vel));
-                const T vel_mag_sq = vel_mag * vel_mag;
-                const V3<T> nv = vel * (T(1) / vel_mag);
+                T vel_mag, inv_vm;
+                if constexpr (sizeof(T) == 4) {
+                    inv_vm = rsqrtf(dot(vel, vel));
+                    vel_mag = dot(vel, vel) * inv_vm;
+                } else {
+                    vel_mag = sqrt_t(dot(vel, vel));
+                    inv_vm = T(1) / vel_mag;
+                }
+                const V3<T> nv = vel * inv_vm;
                 const V3<T> pg = {-T(rec.y), -T(rec.z), -T(rec.w)};
                 // orthogonal projector P = I - nv nv^T
                 const V3<T> Pa = axpy(ac, -dot(nv, ac), nv);
                 const V3<T> Pg = axpy(pg, -dot(nv, pg), nv);
-                const V3<T> curv = Pa * (T(1) / vel_mag_sq);
+                const V3<T> curv = Pa * (inv_vm * inv_vm);
                 const V3<T> cg = (Pg - curv * pot) * vel_mag;
-                // 3 x nanc positional Jacobian (getJacobian :1164-1187)
+                // 3 x nanc positional Jacobian (getJacobian :1164-1187); columns past nanc are zero and skipped
                 V3<T> col[7];
+                const T rdg = (T)P.ridge;
+                T M[9] = {rdg, T(0), T(0), T(0), rdg, T(0), T(0), T(0), rdg};
 #pragma unroll
                 for (int j = 0; j < 7; j++) {
-                    const V3<T> oj = v.fj.o[j] + off;
-                    const V3<T> ax = P.quirk ? v.fj.z[j] + oj : v.fj.z[j];
-                    col[j] = (j < nanc) ? cross(ax, x - oj) : V3<T>{T(0), T(0), T(0)};
-                }
-                if (P.use_pinv) {
-                    // calculatePseudoInverse :767-772 : J^T (J J^T + ridge I)^-1 ; the ridge bounds cond <= ~1e4
-                    const T rdg = (T)P.ridge;
-                    T M[9] = {rdg, T(0), T(0), T(0), rdg, T(0), T(0), T(0), rdg}, Mi[9];
-#pragma unroll
-                    for (int j = 0; j < 7; j++) {
+                    if (j < nanc) {
+                        col[j] = cross(ja[j], x - jo[j]);
                         M[0] += col[j].x * col[j].x; M[1] += col[j].x * col[j].y; M[2] += col[j].x * col[j].z;
                         M[4] += col[j].y * col[j].y; M[5] += col[j].y * col[j].z; M[8] += col[j].z * col[j].z;
                     }
+                }
+                V3<T> y = cg;
+                if (P.use_pinv) {
+                    // calculatePseudoInverse :767-772 : J^T (J J^T + ridge I)^-1 ; the ridge bounds cond <= ~1e4
+                    T Mi[9];
                     M[3] = M[1]; M[6] = M[2]; M[7] = M[5];
                     mat3_inverse<T>(M, Mi);
-                    const V3<T> y = {Mi[0] * cg.x + Mi[1] * cg.y + Mi[2] * cg.z, Mi[3] * cg.x + Mi[4] * cg.y + Mi[5] * cg.z,
-                                     Mi[6] * cg.x + Mi[7] * cg.y + Mi[8] * cg.z};
-#pragma unroll
-                    for (int j = 0; j < 7; j++) acc[j] -= dot(col[j], y);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 7; j++) acc[j] -= dot(col[j], cg);
+                    y = {Mi[0] * cg.x + Mi[1] * cg.y + Mi[2] * cg.z, Mi[3] * cg.x + Mi[4] * cg.y + Mi[5] * cg.z,
+                         Mi[6] * cg.x + Mi[7] * cg.y + Mi[8] * cg.z};
                 }
+#pragma unroll
+                for (int j = 0; j < 7; j++)
+                    if (j < nanc) acc[j] -= dot(col[j], y);
             }
             red[0] += csum;
             red[1] += T(nact);
@@ -639,7 +660,10 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
     if (!run_pose && !run_coll) return set_error(RLITG_ERR_ARG, "stage_mask selects no stage");
     if (run_pose) {
         const size_t smem = sizeof(T) * ((size_t)(CH + 12) * 7 + (size_t)(CH + 3) * 7 + 8 * kNRedPose);
-        auto kern = torm_pose_eval_kernel<T>;
+        // register budget of the pose kernel: 2 CTAs/SM (128 regs) or 3 (80 regs, some spills); RLITG_TORM_POSE_OCC
+        static const int occ = [] { const char* e = getenv("RLITG_TORM_POSE_OCC"); return e ? atoi(e) : 2; }();
+        auto kern = (sizeof(T) == 4 && occ == 3) ? torm_pose_eval_kernel<T, (sizeof(T) == 4 ? 3 : 1)>
+                                                 : torm_pose_eval_kernel<T, (sizeof(T) == 4 ? 2 : 1)>;
         static size_t attr_smem = 0;
         if (smem > attr_smem) {
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -657,7 +681,7 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
             sd = scene_dev(scene);
             S = sd.S;
         }
-        const size_t smem = sizeof(T) * ((size_t)(CH + 12) * 7 + 8 * 2 + (size_t)(CH + 6) * S * 3);
+        const size_t smem = sizeof(T) * ((size_t)(CH + 12) * 7 + 8 * 2 + (size_t)(CH + 6) * ((3 * S) | 1));
         if (smem > 220 * 1024) return set_error(RLITG_ERR_SHAPE, "too many spheres for the shared-memory tile");
         auto kern = torm_coll_smooth_kernel<T>;
         static size_t attr_smem = 0;

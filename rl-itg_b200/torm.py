@@ -140,39 +140,55 @@ class TormBatch:
                                      self.device)
         self._cp = pr.to_c(self.T)
         self._buf = {}
+        self._call_cache = {}
 
     def _out(self, name, shape, dtype=None):
         t = self._buf.get(name)
         if t is None or tuple(t.shape) != tuple(shape):
             t = torch.empty(shape, device=self.device, dtype=dtype or self.dtype)
             self._buf[name] = t
+            self._call_cache.clear()
         return t
 
     def cost_grad(self, traj, stage_mask, stochastic_idx=None, want_active=False):
-        """One launch of rlitg_torm_cost_grad.  Returns dict(costs [N,10], inc_smooth, inc_coll, inc_pose
+        """One call of rlitg_torm_cost_grad.  Returns dict(costs [N,10], inc_smooth, inc_coll, inc_pose
         [N,T-1,7] or None, active [N] or None).  Output tensors are reused between calls."""
-        traj = traj.contiguous()
-        N, T, D = traj.shape
-        if T != self.T or D != 7:
-            raise ValueError("traj must be [N,%d,7]" % self.T)
-        F = T - 1
-        inc_s = self._out("inc_smooth", (N, F, 7)) if stage_mask & STAGE_SMOOTH else None
-        inc_c = self._out("inc_coll", (N, F, 7)) if stage_mask & STAGE_COLL else None
-        inc_p = self._out("inc_pose", (N, F, 7)) if stage_mask & STAGE_POSE_GRAD else None
-        costs = self._out("costs", (N, NCOST))
-        active = self._out("active", (N,), torch.float32) if want_active else None
+        if not traj.is_contiguous():
+            traj = traj.contiguous()
         st = None
         if stochastic_idx is not None:
-            st = torch.as_tensor(stochastic_idx).to(self.device, torch.int32).contiguous()
-        p = lambda t: None if t is None else t.data_ptr()
-        code = _lib.F32 if traj.dtype == torch.float32 else _lib.F64
+            st = stochastic_idx if (torch.is_tensor(stochastic_idx) and stochastic_idx.dtype == torch.int32
+                                    and stochastic_idx.is_cuda) else \
+                torch.as_tensor(stochastic_idx).to(self.device, torch.int32).contiguous()
+        key = (traj.data_ptr(), tuple(traj.shape), traj.dtype, int(stage_mask), None if st is None else st.data_ptr(),
+               bool(want_active))
+        hit = self._call_cache.get(key)
+        if hit is None:
+            N, T, D = traj.shape
+            if T != self.T or D != 7:
+                raise ValueError("traj must be [N,%d,7]" % self.T)
+            if traj.dtype != self.dtype:
+                raise TypeError("traj dtype %s does not match the batch dtype %s" % (traj.dtype, self.dtype))
+            F = T - 1
+            inc_s = self._out("inc_smooth", (N, F, 7)) if stage_mask & STAGE_SMOOTH else None
+            inc_c = self._out("inc_coll", (N, F, 7)) if stage_mask & STAGE_COLL else None
+            inc_p = self._out("inc_pose", (N, F, 7)) if stage_mask & STAGE_POSE_GRAD else None
+            costs = self._out("costs", (N, NCOST))
+            active = self._out("active", (N,), torch.float32) if want_active else None
+            p = lambda t: None if t is None else t.data_ptr()
+            code = _lib.F32 if traj.dtype == torch.float32 else _lib.F64
+            args = (traj.data_ptr(), self.endPoses_desired_.data_ptr(), N, code,
+                    None if self.scene is None else self.scene.handle, self.joint_costs_.handle, C.byref(self._cp),
+                    int(stage_mask), p(st), p(inc_s), p(inc_c), p(inc_p), costs.data_ptr(), p(active))
+            hit = (args, dict(costs=costs, inc_smooth=inc_s, inc_coll=inc_c, inc_pose=inc_p, active=active))
+            if len(self._call_cache) > 64:
+                self._call_cache.clear()
+            self._call_cache[key] = hit
         with _lib.on_device(self.device):
-            check(lib.rlitg_torm_cost_grad(traj.data_ptr(), self.endPoses_desired_.data_ptr(), N, code,
-                                           None if self.scene is None else self.scene.handle,
-                                           self.joint_costs_.handle, C.byref(self._cp), int(stage_mask), p(st),
-                                           p(inc_s), p(inc_c), p(inc_p), costs.data_ptr(), p(active),
-                                           torch.cuda.current_stream().cuda_stream))
-        return dict(costs=costs, inc_smooth=inc_s, inc_coll=inc_c, inc_pose=inc_p, active=active)
+            rc = lib.rlitg_torm_cost_grad(*hit[0], torch.cuda.current_stream().cuda_stream)
+        if rc:
+            check(rc)
+        return hit[1]
 
     # ---- reference member names (leading batch axis) ------------------------------------------------------
     def getEndPoseCost(self, traj, grad=False):
