@@ -215,7 +215,7 @@ def main():
     peak, peak_src = measured_peaks()
     achieved = BYTES_PER_CONFIG * B / (ms_local / args.steps * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "fk_jac_kernel<float,7,aos,aos>", "bytes_per_launch": BYTES_PER_CONFIG * B,
+                "traffic": None, "kernel": "fk_jac_persist_kernel<float,7,aos,2 stages>", "bytes_per_launch": BYTES_PER_CONFIG * B,
                 "peak_source": peak_src}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):

@@ -248,6 +248,12 @@ RLITG_API int rlitg_torm_cost_grad(const void* traj, const void* targets, int64_
  * the TORM kernel's roofline fraction is quoted against. */
 RLITG_API int rlitg_fma_probe(int ctas, int iters, float* out, void* stream);
 
+/* Measurement aid: streams `ntiles` tiles of `tile_bytes` from shared memory to `dst` with TMA bulk stores from
+ * `ctas` persistent CTAs (the drain path of rlitg_fk_jac without arithmetic), optionally reading `read_floats`
+ * floats per tile from `src` first.  Gives the HBM ceiling for fk_jac's 1 : 7.7 read : write mix. */
+RLITG_API int rlitg_write_probe(void* dst, const void* src, int64_t ntiles, int tile_bytes, int read_floats,
+                                int ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -184,3 +184,50 @@ extern "C" RLITG_API int rlitg_fma_probe(int ctas, int iters, float* out, void* 
     rlitg::fma_probe_kernel<<<ctas, 256, 0, static_cast<cudaStream_t>(stream)>>>(iters, out);
     return rlitg::check_launch("fma_probe_kernel");
 }
+
+// ---- HBM write-stream probe: the ceiling for a kernel that, like fk_jac, writes ~8x what it reads -----------
+// Persistent CTAs drain `tile_bytes` shared-memory tiles to consecutive global addresses with TMA bulk stores
+// (the fk_jac drain path, no arithmetic) and optionally read `read_bytes_per_tile` first.
+namespace rlitg {
+__global__ void __launch_bounds__(128) write_probe_kernel(char* __restrict__ dst, const float* __restrict__ src,
+                                                          int64_t ntiles, int tile_bytes, int read_floats) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float acc = 0.f;
+    int it = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
+        if (read_floats > 0) {
+            const float* s = src + t * read_floats;
+            for (int i = threadIdx.x; i < read_floats; i += blockDim.x) acc += __ldg(s + i);
+        }
+        unsigned char* stage = smem_raw + (it & 1) * tile_bytes;
+        if (it >= 2) {
+            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncthreads();
+        }
+        reinterpret_cast<float*>(stage)[threadIdx.x] = acc;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + t * tile_bytes),
+                         "r"((uint32_t)__cvta_generic_to_shared(stage)), "r"(tile_bytes)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+}  // namespace rlitg
+
+extern "C" RLITG_API int rlitg_write_probe(void* dst, const void* src, int64_t ntiles, int tile_bytes, int read_floats,
+                                           int ctas, void* stream) {
+    if (!dst || ntiles < 1 || tile_bytes < 512 || (tile_bytes & 15) || tile_bytes > 100 * 1024 || ctas < 1 ||
+        (read_floats > 0 && !src))
+        return rlitg::set_error(RLITG_ERR_ARG, "bad write probe arguments");
+    auto kern = rlitg::write_probe_kernel;
+    const size_t smem = 2 * (size_t)tile_bytes;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return rlitg::set_cuda_error("cudaFuncSetAttribute(write_probe_kernel)");
+    kern<<<ctas, 128, smem, static_cast<cudaStream_t>(stream)>>>((char*)dst, (const float*)src, ntiles, tile_bytes,
+                                                                 read_floats);
+    return rlitg::check_launch("write_probe_kernel");
+}

@@ -148,7 +148,7 @@ RLITG_DEV void bulk_wait_read_pending() { asm volatile("cp.async.bulk.wait_group
 template <typename T, int D, bool QSOA, int NSTAGE>
 __global__ void __launch_bounds__(kTile) fk_jac_persist_kernel(const T* __restrict__ q, int64_t B, int64_t ntiles,
                                                                T* __restrict__ pos, T* __restrict__ rot,
-                                                               T* __restrict__ quat, T* __restrict__ J) {
+                                                               T* __restrict__ quat, T* __restrict__ J, int dbg) {
     constexpr int kStageElems = kTile * (6 * D + 9 + 4 + 3);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* stage0 = reinterpret_cast<T*>(smem_raw);
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kTile) fk_jac_persist_kernel(const T* __restri
         }
         fence_proxy_async_smem();
         __syncthreads();
-        if (tid == 0) {
+        if (tid == 0 && !(dbg & 1)) {
             const int64_t base = tile * kTile;
             if (J) bulk_store(J + base * 6 * D, sJ, (uint32_t)(kTile * 6 * D * sizeof(T)));
             if (rot) bulk_store(rot + base * 9, sRot, (uint32_t)(kTile * 9 * sizeof(T)));
@@ -279,7 +279,12 @@ static int launch_fk_persist(const T* q, int64_t B, int64_t ntiles, T* pos, T* r
             return set_cuda_error("cudaOccupancyMaxActiveBlocksPerMultiprocessor(fk_jac_persist_kernel)");
     }
     const int64_t grid = std::min<int64_t>(ntiles, (int64_t)num_sms * ctas_per_sm);
-    kern<<<(unsigned)grid, kTile, smem, st>>>(q, B, ntiles, pos, rot, quat, J);
+    static const int dbg = [] { const char* e = getenv("RLITG_FK_DBG"); return e ? atoi(e) : 0; }();  // 1 = no stores
+    // Two CTAs per SM measured best on B200 (1M configs: 45.9 us vs 48-49 us with 3-7 CTAs/SM; 8M: 6.14 TB/s):
+    // the round-robin tile order keeps the set of tiles in flight -- the HBM write window -- narrow.
+    static const int mult = [] { const char* e = getenv("RLITG_FK_CTAS"); return e ? atoi(e) : 2; }();
+    const int64_t g2 = std::min<int64_t>(std::min<int64_t>(ntiles, (int64_t)num_sms * mult), grid);
+    kern<<<(unsigned)g2, kTile, smem, st>>>(q, B, ntiles, pos, rot, quat, J, dbg);
     return check_launch("fk_jac_persist_kernel");
 }
 

@@ -312,14 +312,28 @@ __global__ void __launch_bounds__(kEnvTile, sizeof(T) == 4 ? 4 : 1) pirl_env_ker
         }
     }
     __syncthreads();
-    // flat coalesced copy-out; (row, column) advance incrementally instead of dividing by the runtime O
+    // coalesced copy-out of the staged rows
     T* dst = obs + base * O;
-    int r = tid / O, c = tid - r * O;
-    const int dr = kEnvTile / O, dc = kEnvTile - dr * O;
-    for (int i = tid; i < n * O; i += kEnvTile) {
-        dst[i] = s_obs[r * OS + c];
-        r += dr; c += dc;
-        if (c >= O) { c -= O; r++; }
+    if (sizeof(T) == 4 && (O & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        // 128-bit stores: a row holds O / 4 whole float4 groups, so a group never straddles two rows
+        const int G = O >> 2;
+        int r = tid / G, g = tid - r * G;
+        const int dr = kEnvTile / G, dg = kEnvTile - dr * G;
+        for (int i = tid; i < n * G; i += kEnvTile) {
+            const T* sp = s_obs + r * OS + 4 * g;
+            reinterpret_cast<float4*>(dst)[i] = make_float4((float)sp[0], (float)sp[1], (float)sp[2], (float)sp[3]);
+            r += dr; g += dg;
+            if (g >= G) { g -= G; r++; }
+        }
+    } else {
+        // (row, column) advance incrementally instead of dividing by the runtime O
+        int r = tid / O, c = tid - r * O;
+        const int dr = kEnvTile / O, dc = kEnvTile - dr * O;
+        for (int i = tid; i < n * O; i += kEnvTile) {
+            dst[i] = s_obs[r * OS + c];
+            r += dr; c += dc;
+            if (c >= O) { c -= O; r++; }
+        }
     }
 }
 

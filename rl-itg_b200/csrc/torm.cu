@@ -353,8 +353,8 @@ torm_pose_eval_kernel(TormP<T> P, const T* __restrict__ traj, const T* __restric
 
 // ---- kernel 3b: sphere potentials + CHOMP increments (A6) + smoothness increments (A7) ---------------------
 // Writes costs[5] and active[]; the other cost entries are zeroed when the pose / evaluator kernel does not run.
-template <typename T>
-__global__ void __launch_bounds__(kTormMaxThreads, 2)
+template <typename T, int MAXREG>
+__global__ void __launch_bounds__(kTormMaxThreads) __maxnreg__(MAXREG)
 torm_coll_smooth_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S, const T* __restrict__ Aband,
                         int stage_mask, int zero_pose_costs, const int32_t* __restrict__ stoch,
                         T* __restrict__ inc_smooth, T* __restrict__ inc_coll, T* __restrict__ costs,
@@ -363,7 +363,7 @@ torm_coll_smooth_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* s_traj = reinterpret_cast<T*>(smem_raw);  // [(CH + 12)][7]
     T* s_red = s_traj + (CH + 12) * 7;           // [8][2]
-    T* s_pos = s_red + 8 * 2;                    // [(CH + 6)][PS] rows c0-3 .. c0+CH+2, PS = 3 S padded to odd
+    T* s_pos = s_red + 8 * 2;                    // [(min(CH, T) + 6)][PS] rows c0-3 .. c0+CH+2, PS = 3 S padded to odd
     const int PS = (3 * S) | 1;                  // odd row stride: thread-per-row accesses are bank-conflict free
     __shared__ float4 s_sph[kMaxSpheres];
     __shared__ int s_start[kNumLinks + 1];
@@ -681,9 +681,12 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
             sd = scene_dev(scene);
             S = sd.S;
         }
-        const size_t smem = sizeof(T) * ((size_t)(CH + 12) * 7 + 8 * 2 + (size_t)(CH + 6) * ((3 * S) | 1));
+        const size_t smem = sizeof(T) * ((size_t)(CH + 12) * 7 + 8 * 2 + (size_t)(std::min(CH, (int)p->T) + 6) * ((3 * S) | 1));
         if (smem > 220 * 1024) return set_error(RLITG_ERR_SHAPE, "too many spheres for the shared-memory tile");
-        auto kern = torm_coll_smooth_kernel<T>;
+        // register budget of the collision kernel: 2 CTAs/SM (128 regs) or 3 (<= 96 regs); RLITG_TORM_COLL_OCC
+        static const int cocc = [] { const char* e = getenv("RLITG_TORM_COLL_OCC"); return e ? atoi(e) : 2; }();
+        auto kern = (sizeof(T) == 4 && cocc == 3) ? torm_coll_smooth_kernel<T, (sizeof(T) == 4 ? 96 : 255)>
+                                                  : torm_coll_smooth_kernel<T, (sizeof(T) == 4 ? 128 : 255)>;
         static size_t attr_smem = 0;
         if (smem > attr_smem) {
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
