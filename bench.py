@@ -91,8 +91,8 @@ def cpu_reference_fk_jac(seconds_target=12.0, threads=None):
     """times the CPU oracle (FP64 restatement of the reference's KDL calls) on a bounded sample"""
     import numpy as np
     from oracle import oracle as O
-    if threads:
-        O.set_num_threads(threads)
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1: override it explicitly)
+    O.set_num_threads(threads or len(os.sched_getaffinity(0)))
     cores = O.num_threads()
     n = 1 << 18
     rng = np.random.default_rng(0)
@@ -117,6 +117,7 @@ def run_reference(args):
     steps, warm = args.steps, args.warmup
     import numpy as np
     from oracle import oracle as O
+    O.set_num_threads(len(os.sched_getaffinity(0)))  # torchrun exports OMP_NUM_THREADS=1: use every host thread
     cores = O.num_threads()
     n = 1 << 18  # bounded sample of the 1M-config workload per step
     rng = np.random.default_rng(0)

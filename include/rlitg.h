@@ -243,6 +243,25 @@ RLITG_API int rlitg_torm_cost_grad(const void* traj, const void* targets, int64_
                                    int stage_mask, const int32_t* stochastic_idx, void* inc_smooth, void* inc_coll,
                                    void* inc_pose, void* costs, float* active, void* stream);
 
+/* Update step of the two-stage gradient descent, for N trajectories in place:
+ * calculateFeasibleIncrements (torm/src/torm_optimizer.cpp:1555-1609) or calculateEndPoseIncrements (:1475-1482),
+ * then addIncrementsToTrajectory (:1611-1639) and handleJointLimits (:1189-1268). */
+typedef struct RlitgTormUpdate {
+    int32_t stage;             /* 0 = feasible stage (smoothness + collision), 1 = end-pose stage */
+    int32_t lr_schedule_mode;  /* lr_schedule_mode_: 0 = fixed weights, otherwise max-abs normalisation + alpha blend */
+    double smoothness_update_weight; /* mode 0 only */
+    double obstacle_update_weight;   /* mode 0 only */
+    double joint_update_limit;       /* joint_update_limit_ */
+    double joint_min[7], joint_max[7]; /* position bounds; entries of continuous joints are ignored */
+} RlitgTormUpdate;
+/*   traj [N,T,7] in/out (row 0 untouched); inc_* [N,T-1,7] from rlitg_torm_cost_grad (inc_pose already carries
+ *   jacobian_update_weight_); alpha [N] (may be NULL = 0.5) and lr [N] = per-trajectory alpha_ / learning_rate_
+ *   (for mode 0 pass parameters_->learning_rate_ in every entry).  Floating tensors share dtype. */
+RLITG_API int rlitg_torm_update(void* traj, int64_t N, int dtype, const RlitgSmooth* smooth,
+                                const RlitgTormParams* p, const RlitgTormUpdate* u, const void* inc_smooth,
+                                const void* inc_coll, const void* inc_pose, const void* alpha, const void* lr,
+                                void* stream);
+
 /* Measurement aid: launches `ctas` x 256 threads each running 16 independent FFMA chains of `iters` steps
  * (2 * ctas * 256 * iters * 16 flops); bench.py times it with CUDA events to get the FP32 FMA-pipe peak that
  * the TORM kernel's roofline fraction is quoted against. */

@@ -246,6 +246,24 @@ def traj_eval(traj, targets, p):
     return out
 
 
+def torm_update(traj, Ainv, stage, mode, inc_smooth, inc_coll, inc_pose, alpha, lr, sw=0.15, ow=1.0, limit=0.17,
+                cjoint=(0, 0, 1, 0, 1, 0, 1), jmin=None, jmax=None):
+    """-> updated copy of traj [N,T,D]"""
+    traj = _f64(traj).copy(); N, T, D = traj.shape
+    Ainv = _f64(Ainv)
+    f = lambda a: None if a is None else _f64(a)
+    inc_smooth, inc_coll, inc_pose = f(inc_smooth), f(inc_coll), f(inc_pose)
+    alpha = f(np.broadcast_to(alpha, (N,))); lr = f(np.broadcast_to(lr, (N,)))
+    cj = np.ascontiguousarray(cjoint, dtype=np.int32)
+    jmin = _f64([-1.6056, -1.221, -3.141592, -2.251, -3.141592, -2.16, -3.141592] if jmin is None else jmin)
+    jmax = _f64([1.6056, 1.518, 3.141592, 2.251, 3.141592, 2.16, 3.141592] if jmax is None else jmax)
+    rc = lib().orc_torm_update(_p(traj), C.c_int64(N), T, D, _p(Ainv), int(stage), int(mode), _p(inc_smooth),
+                               _p(inc_coll), _p(inc_pose), _p(alpha), _p(lr), C.c_double(sw), C.c_double(ow),
+                               C.c_double(limit), _p(cj, C.c_int32), _p(jmin), _p(jmax))
+    assert rc == 0
+    return traj
+
+
 # ---------------------------------------------------------------------------------- PIRL
 def pirl_cfg(reward_type="Task+NullSpaceImitation", obs_type="Conf+LinkPoses", n_future=1, z_dim=0,
              train_mode=True, refine_flag=False):

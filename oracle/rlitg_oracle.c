@@ -1232,6 +1232,107 @@ int orc_pirl_env_step(const OrcPirlCfg* c, int64_t B, double* q, const float* ac
     return 0;
 }
 
+
+/* ================================================================================================
+ * TORM update step: calculateFeasibleIncrements torm/src/torm_optimizer.cpp:1555-1609,
+ * calculateEndPoseIncrements :1475-1482 (already weighted by the caller), addIncrementsToTrajectory
+ * :1611-1639, handleJointLimits :1189-1268.  updateGoalConfiguration / updateFullTrajectory are implicit
+ * in the [N,T,D] representation (padded rows are clamped copies).  Ainv is the scaled inverse of the free
+ * block (getQuadraticCostInverse).  stage 0 = feasible (smoothness + collision), 1 = end-pose.
+ * ============================================================================================== */
+static void torm_update_one(double* traj, int T, int D, const double* Ainv, int stage, int mode,
+                            const double* inc_smooth, const double* inc_coll, const double* inc_pose, double alpha,
+                            double lr, double sw, double ow, double limit, const int* cjoint, const double* jmin,
+                            const double* jmax) {
+    const int F = T - 1;
+    double* fin = (double*)malloc(sizeof(double) * F * D);
+    double* tmp = (double*)malloc(sizeof(double) * F);
+    if (stage == 0) {
+        double* sm = (double*)malloc(sizeof(double) * F * D);
+        double* co = (double*)malloc(sizeof(double) * F * D);
+        memcpy(sm, inc_smooth, sizeof(double) * F * D);
+        memcpy(co, inc_coll, sizeof(double) * F * D);
+        if (mode != 0) {
+            double mx = -DBL_MAX, mn = DBL_MAX;
+            for (int k = 0; k < F * D; k++) { if (sm[k] > mx) mx = sm[k]; if (sm[k] < mn) mn = sm[k]; }
+            double scale = fmax(fabs(mx), fabs(mn));
+            if (scale > 0) for (int k = 0; k < F * D; k++) sm[k] /= scale;
+            mx = -DBL_MAX; mn = DBL_MAX;
+            for (int k = 0; k < F * D; k++) { if (co[k] > mx) mx = co[k]; if (co[k] < mn) mn = co[k]; }
+            scale = fmax(fabs(mx), fabs(mn));
+            if (scale > 0) for (int k = 0; k < F * D; k++) co[k] /= scale;
+        }
+        for (int j = 0; j < D; j++) {
+            for (int i = 0; i < F; i++)
+                tmp[i] = (mode != 0) ? (alpha * co[i * D + j] + (1 - alpha) * sm[i * D + j])
+                                     : (sw * sm[i * D + j] + ow * co[i * D + j]);
+            for (int i = 0; i < F; i++) {
+                double acc = 0;
+                for (int k = 0; k < F; k++) acc += Ainv[(size_t)i * F + k] * tmp[k];
+                fin[i * D + j] = lr * acc;
+            }
+        }
+        free(sm); free(co);
+    } else {
+        memcpy(fin, inc_pose, sizeof(double) * F * D);
+    }
+    /* addIncrementsToTrajectory */
+    if (mode != 0) {
+        double mx = -DBL_MAX, mn = DBL_MAX;
+        for (int k = 0; k < F * D; k++) { if (fin[k] > mx) mx = fin[k]; if (fin[k] < mn) mn = fin[k]; }
+        double scale = fmax(fabs(mx), fabs(mn));
+        if (scale > limit && scale > 0) for (int k = 0; k < F * D; k++) fin[k] = fin[k] / scale * limit;
+        for (int i = 0; i < F; i++) for (int j = 0; j < D; j++) traj[(i + 1) * D + j] += fin[i * D + j];
+    } else {
+        for (int j = 0; j < D; j++) {
+            double scale = 1.0, mx = -DBL_MAX, mn = DBL_MAX;
+            for (int i = 0; i < F; i++) { double v = fin[i * D + j]; if (v > mx) mx = v; if (v < mn) mn = v; }
+            double max_scale = limit / fabs(mx), min_scale = limit / fabs(mn);
+            if (max_scale < scale) scale = max_scale;
+            if (min_scale < scale) scale = min_scale;
+            for (int i = 0; i < F; i++) traj[(i + 1) * D + j] += scale * fin[i * D + j];
+        }
+    }
+    /* handleJointLimits */
+    for (int j = 0; j < D; j++) {
+        if (cjoint[j]) continue;
+        int count = 0, violation;
+        do {
+            double max_abs_violation = 1e-6, max_violation = 0.0;
+            int max_violation_index = 0;
+            violation = 0;
+            for (int i = 0; i < F; i++) {
+                double amount = 0.0, absolute_amount = 0.0, v = traj[(i + 1) * D + j];
+                if (v > jmax[j]) { amount = jmax[j] - v; absolute_amount = fabs(amount); }
+                else if (v < jmin[j]) { amount = jmin[j] - v; absolute_amount = fabs(amount); }
+                if (absolute_amount > max_abs_violation) {
+                    max_abs_violation = absolute_amount; max_violation = amount; max_violation_index = i; violation = 1;
+                }
+            }
+            if (violation) {
+                int k = max_violation_index;
+                double multiplier = max_violation / Ainv[(size_t)k * F + k];
+                for (int i = 0; i < F; i++) traj[(i + 1) * D + j] += multiplier * Ainv[(size_t)i * F + k];
+            }
+            if (++count > 10) break;
+        } while (violation);
+    }
+    free(fin); free(tmp);
+}
+
+int orc_torm_update(double* traj, int64_t N, int T, int D, const double* Ainv, int stage, int mode,
+                    const double* inc_smooth, const double* inc_coll, const double* inc_pose, const double* alpha,
+                    const double* lr, double sw, double ow, double limit, const int* cjoint, const double* jmin,
+                    const double* jmax) {
+    const size_t FD = (size_t)(T - 1) * D;
+#pragma omp parallel for schedule(dynamic)
+    for (int64_t n = 0; n < N; n++)
+        torm_update_one(traj + n * T * D, T, D, Ainv, stage, mode, inc_smooth ? inc_smooth + n * FD : 0,
+                        inc_coll ? inc_coll + n * FD : 0, inc_pose ? inc_pose + n * FD : 0, alpha ? alpha[n] : 0.5,
+                        lr[n], sw, ow, limit, cjoint, jmin, jmax);
+    return 0;
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -99,6 +99,12 @@ int orc_torm_cost_grad(const double* traj /*[N,T,D]*/, const double* targets /*[
 int orc_traj_eval(const double* traj, const double* targets, const OrcTormParams* p, int64_t N,
                   double* out /*[N,6] pose rot vel acc jerk nviol*/);
 
+/* TORM update step (feasible or end-pose stage): traj [N,T,D] in/out; Ainv scaled [(T-1),(T-1)]; alpha, lr [N] */
+int orc_torm_update(double* traj, int64_t N, int T, int D, const double* Ainv, int stage, int mode,
+                    const double* inc_smooth, const double* inc_coll, const double* inc_pose, const double* alpha,
+                    const double* lr, double sw, double ow, double limit, const int* cjoint, const double* jmin,
+                    const double* jmax);
+
 /* ---- PIRL path-wise IK env step */
 typedef struct {
     double ll[7], ul[7];

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "../../include/rlitg.h"
 
 namespace rlitg {
@@ -18,7 +20,19 @@ int launch_fk_jac(const T* q, int64_t B, int D, int flags, T* pos, T* rot, T* qu
 template <typename T>
 int launch_allfk(const T* q, int64_t B, int D, int flags, T* out, cudaStream_t st);
 
-struct Smooth;    // torm.cu
+// Smoothness operator of TormCost, built on the host in FP64 (torm.cu: smooth_build) and mirrored on the device.
+struct Smooth {
+    int T = 0;
+    double scale = 0;            // max coefficient of the unscaled inverse (the reference's `// 96.77624`)
+    double mcs = 1.0;            // max_cost_scale = max(1, scale)
+    std::vector<double> band;    // [(T+10)][13], scaled quad_cost_full_
+    std::vector<double> inv;     // [(T-1)][(T-1)], scaled quad_cost_inv_
+    std::vector<double> chol;    // [(T-1)][7] banded Cholesky factor of the unscaled free block
+    double* d_band64 = nullptr;
+    float* d_band32 = nullptr;
+    double* d_inv64 = nullptr;
+    double* d_chol = nullptr;
+};
 const double* smooth_inv_host(const Smooth* s);
 int smooth_T(const Smooth* s);
 struct Scene;     // scene.cu

@@ -546,16 +546,7 @@ torm_coll_smooth_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int
 #undef PROW
 
 // ---- smoothness operator (host, FP64): TormCost ctor + scaling -------------------------------------------
-struct Smooth {
-    int T = 0;
-    double scale = 0;               // max coefficient of the unscaled inverse
-    std::vector<double> band;       // [(T+10)][13], scaled
-    std::vector<double> inv;        // [(T-1)][(T-1)], scaled
-    double* d_band64 = nullptr;
-    float* d_band32 = nullptr;
-    double* d_inv64 = nullptr;      // device copies of the inverse, made on demand by the update step
-    float* d_inv32 = nullptr;
-};
+// (struct Smooth is declared in rlitg_internal.h: the update step in torm_update.cu shares it)
 
 static const double kRules[3][7] = {{-1.0 / 60, 3.0 / 20, -3.0 / 4, 0.0, 3.0 / 4, -3.0 / 20, 1.0 / 60},
                                     {1.0 / 90, -3.0 / 20, 3.0 / 2, -49.0 / 18, 3.0 / 2, -3.0 / 20, 1.0 / 90},
@@ -624,6 +615,8 @@ static int smooth_build(Smooth& sm, int T, double dt, const double* w3, double r
     for (auto& x : band) x *= mcs;
     for (auto& x : sm.inv) x /= mcs;
     sm.band.swap(band);
+    sm.chol.swap(L);  // Cholesky factor of the UNSCALED free block; A_scaled^-1 b = (L L^T)^-1 b / mcs
+    sm.mcs = mcs;
     sm.T = T;
     return RLITG_OK;
 }
@@ -726,6 +719,16 @@ RLITG_API int rlitg_smooth_create(int T, double dt, const double* w3, double rid
         rlitg_smooth_destroy(reinterpret_cast<RlitgSmooth*>(s));
         return rc;
     }
+    // for the update step: banded Cholesky factor (preconditioning solve) and the dense scaled inverse (rows are
+    // the columns handleJointLimits adds, torm/src/torm_optimizer.cpp:1256-1263)
+    const size_t nl = s->chol.size(), ni = s->inv.size();
+    if (cudaMalloc(&s->d_chol, nl * 8) != cudaSuccess || cudaMalloc(&s->d_inv64, ni * 8) != cudaSuccess ||
+        cudaMemcpy(s->d_chol, s->chol.data(), nl * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(s->d_inv64, s->inv.data(), ni * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+        rc = set_cuda_error("rlitg_smooth_create");
+        rlitg_smooth_destroy(reinterpret_cast<RlitgSmooth*>(s));
+        return rc;
+    }
     *out = reinterpret_cast<RlitgSmooth*>(s);
     return RLITG_OK;
 }
@@ -736,7 +739,7 @@ RLITG_API int rlitg_smooth_destroy(RlitgSmooth* h) {
     if (s->d_band64) cudaFree(s->d_band64);
     if (s->d_band32) cudaFree(s->d_band32);
     if (s->d_inv64) cudaFree(s->d_inv64);
-    if (s->d_inv32) cudaFree(s->d_inv32);
+    if (s->d_chol) cudaFree(s->d_chol);
     delete s;
     return RLITG_OK;
 }

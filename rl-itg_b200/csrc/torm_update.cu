@@ -1,0 +1,209 @@
+// TORM update step on the device: what localOptimizeTSGD does between two cost evaluations,
+//   calculateFeasibleIncrements   torm/src/torm_optimizer.cpp:1555-1609   max-abs normalisation, alpha blend,
+//                                                                         A^-1 preconditioning, learning rate
+//   calculateEndPoseIncrements    :1475-1482                              (weight already applied by kernel 3a)
+//   addIncrementsToTrajectory     :1611-1639                              joint_update_limit_ scaling
+//   handleJointLimits             :1189-1268                              <= 11 corrective A^-1 columns per joint
+// for N trajectories at once, so the [N,T,7] tensor never leaves the GPU between iterations.
+// updateGoalConfiguration / updateFullTrajectory (:1118-1123, :774-777) are implicit: padded rows are clamped reads.
+//
+// One CTA per trajectory.  The preconditioning A_free^-1 b is a banded Cholesky solve (A_free is SPD with half
+// bandwidth 6) instead of the reference's dense (T-1)^2 product: O(13 T) per joint, in FP64 (7 serial chains per
+// trajectory; the kernel is latency bound and tiny next to kernel 3).  The corrective columns of handleJointLimits
+// are rows of the dense scaled inverse kept on the device (symmetric, so a column read is contiguous).
+#include "rlitg_internal.h"
+
+namespace rlitg {
+
+struct UpdP {
+    int Tn, stage, mode;
+    double sw, ow, limit, mcs;
+    int cj[7];
+    double jmin[7], jmax[7];
+};
+
+constexpr int kUpdThreads = 64;
+
+__device__ __forceinline__ double block_max(double v, double* s_tmp) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_tmp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = s_tmp[0];
+    for (int w = 1; w < kUpdThreads / 32; w++) r = fmax(r, s_tmp[w]);
+    return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kUpdThreads)
+torm_update_kernel(UpdP P, T* __restrict__ traj, const T* __restrict__ inc_smooth, const T* __restrict__ inc_coll,
+                   const T* __restrict__ inc_pose, const T* __restrict__ alpha, const T* __restrict__ lr,
+                   const double* __restrict__ chol, const double* __restrict__ inv) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int Tn = P.Tn, F = Tn - 1, tid = threadIdx.x;
+    double* fin = reinterpret_cast<double*>(smem_raw);  // [F][7] right-hand side -> final increments
+    double* tr = fin + (size_t)F * 7;                   // [F][7] free rows of the trajectory
+    __shared__ double s_tmp[kUpdThreads / 32];
+    __shared__ double s_best[kUpdThreads];
+    __shared__ int s_idx[kUpdThreads];
+    const int64_t n = blockIdx.x;
+    T* trow = traj + n * (int64_t)Tn * 7 + 7;  // first free row
+    const size_t FD = (size_t)F * 7;
+    for (int k = tid; k < (int)FD; k += kUpdThreads) tr[k] = (double)trow[k];
+
+    if (P.stage == 0) {
+        const T* s = inc_smooth + n * FD;
+        const T* c = inc_coll + n * FD;
+        double ss = 1.0, sc = 1.0;
+        if (P.mode != 0) {
+            double ms = 0.0, mc = 0.0;
+            for (int k = tid; k < (int)FD; k += kUpdThreads) { ms = fmax(ms, fabs((double)s[k])); mc = fmax(mc, fabs((double)c[k])); }
+            ss = block_max(ms, s_tmp);
+            sc = block_max(mc, s_tmp);
+        }
+        const double a = alpha ? (double)alpha[n] : 0.5;
+        for (int k = tid; k < (int)FD; k += kUpdThreads) {
+            double sv = (double)s[k], cv = (double)c[k];
+            if (P.mode != 0) {
+                if (ss > 0) sv /= ss;
+                if (sc > 0) cv /= sc;
+                fin[k] = a * cv + (1 - a) * sv;
+            } else {
+                fin[k] = P.sw * sv + P.ow * cv;
+            }
+        }
+        __syncthreads();
+        // banded Cholesky solve per joint column: L y = b, L^T x = y ; L(i, j) at chol[i*7 + (j - i + 6)]
+        if (tid < 7) {
+            const int j = tid;
+            for (int i = 0; i < F; i++) {
+                double acc = fin[i * 7 + j];
+                const int lo = i - 6 < 0 ? 0 : i - 6;
+                for (int k = lo; k < i; k++) acc -= chol[i * 7 + (k - i + 6)] * fin[k * 7 + j];
+                fin[i * 7 + j] = acc / chol[i * 7 + 6];
+            }
+            for (int i = F - 1; i >= 0; i--) {
+                double acc = fin[i * 7 + j];
+                const int hi = i + 6 > F - 1 ? F - 1 : i + 6;
+                for (int k = i + 1; k <= hi; k++) acc -= chol[k * 7 + (i - k + 6)] * fin[k * 7 + j];
+                fin[i * 7 + j] = acc / chol[i * 7 + 6];
+            }
+        }
+        __syncthreads();
+        const double rate = (double)lr[n] / P.mcs;
+        for (int k = tid; k < (int)FD; k += kUpdThreads) fin[k] *= rate;
+    } else {
+        const T* p = inc_pose + n * FD;
+        for (int k = tid; k < (int)FD; k += kUpdThreads) fin[k] = (double)p[k];
+    }
+    __syncthreads();
+
+    // ---- addIncrementsToTrajectory :1611-1639
+    if (P.mode != 0) {
+        double m = 0.0;
+        for (int k = tid; k < (int)FD; k += kUpdThreads) m = fmax(m, fabs(fin[k]));
+        const double scale = block_max(m, s_tmp);
+        const bool clip = scale > P.limit && scale > 0;
+        for (int k = tid; k < (int)FD; k += kUpdThreads) tr[k] += clip ? fin[k] / scale * P.limit : fin[k];
+    } else {
+        for (int j = 0; j < 7; j++) {
+            double mx = -1e300, mn = 1e300;
+            for (int i = tid; i < F; i += kUpdThreads) { mx = fmax(mx, fin[i * 7 + j]); mn = fmin(mn, fin[i * 7 + j]); }
+            mx = block_max(mx, s_tmp);
+            mn = -block_max(-mn, s_tmp);
+            double scale = 1.0;
+            const double max_scale = P.limit / fabs(mx), min_scale = P.limit / fabs(mn);
+            if (max_scale < scale) scale = max_scale;
+            if (min_scale < scale) scale = min_scale;
+            for (int i = tid; i < F; i += kUpdThreads) tr[i * 7 + j] += scale * fin[i * 7 + j];
+        }
+    }
+    __syncthreads();
+
+    // ---- handleJointLimits :1189-1268 (continuous joints are skipped)
+    for (int j = 0; j < 7; j++) {
+        if (P.cj[j]) continue;
+        for (int count = 0; count <= 10; count++) {
+            double best = 1e-6, amount_best = 0.0;
+            int idx = -1;
+            for (int i = tid; i < F; i += kUpdThreads) {
+                const double v = tr[i * 7 + j];
+                double amount = 0.0;
+                if (v > P.jmax[j]) amount = P.jmax[j] - v;
+                else if (v < P.jmin[j]) amount = P.jmin[j] - v;
+                if (fabs(amount) > best) { best = fabs(amount); amount_best = amount; idx = i; }  // first maximum wins
+            }
+            s_best[tid] = idx >= 0 ? best : 0.0;
+            s_idx[tid] = idx;
+            __syncthreads();
+            // every thread resolves the winner the same way: largest violation, smallest row index on ties
+            double wb = 0.0;
+            int wi = -1;
+            for (int t = 0; t < kUpdThreads; t++) {
+                const int ti = s_idx[t];
+                if (ti >= 0 && (s_best[t] > wb || (s_best[t] == wb && ti < wi))) { wb = s_best[t]; wi = ti; }
+            }
+            __syncthreads();
+            if (wi < 0) break;
+            const double v = tr[wi * 7 + j];
+            const double viol = v > P.jmax[j] ? P.jmax[j] - v : P.jmin[j] - v;
+            (void)amount_best;
+            const double mult = viol / inv[(size_t)wi * F + wi];
+            __syncthreads();
+            for (int i = tid; i < F; i += kUpdThreads) tr[i * 7 + j] += mult * inv[(size_t)wi * F + i];
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    for (int k = tid; k < (int)FD; k += kUpdThreads) trow[k] = (T)tr[k];
+}
+
+template <typename T>
+static int launch_update(const RlitgTormUpdate* u, const RlitgTormParams* p, const Smooth* sm, T* traj, int64_t N,
+                         const T* inc_smooth, const T* inc_coll, const T* inc_pose, const T* alpha, const T* lr,
+                         cudaStream_t st) {
+    UpdP P;
+    P.Tn = p->T; P.stage = u->stage; P.mode = u->lr_schedule_mode;
+    P.sw = u->smoothness_update_weight; P.ow = u->obstacle_update_weight; P.limit = u->joint_update_limit;
+    P.mcs = sm->mcs;
+    for (int j = 0; j < 7; j++) { P.cj[j] = p->cjoint[j]; P.jmin[j] = u->joint_min[j]; P.jmax[j] = u->joint_max[j]; }
+    const size_t smem = sizeof(double) * 2 * (size_t)(p->T - 1) * 7;
+    if (smem > 200 * 1024) return set_error(RLITG_ERR_SHAPE, "T too large for the update step's shared-memory tile");
+    auto kern = torm_update_kernel<T>;
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return set_cuda_error("cudaFuncSetAttribute(torm_update_kernel)");
+        attr_smem = smem;
+    }
+    kern<<<(unsigned)N, kUpdThreads, smem, st>>>(P, traj, inc_smooth, inc_coll, inc_pose, alpha, lr, sm->d_chol, sm->d_inv64);
+    return check_launch("torm_update_kernel");
+}
+
+}  // namespace rlitg
+
+using namespace rlitg;
+
+extern "C" RLITG_API int rlitg_torm_update(void* traj, int64_t N, int dtype, const RlitgSmooth* smooth,
+                                           const RlitgTormParams* p, const RlitgTormUpdate* u, const void* inc_smooth,
+                                           const void* inc_coll, const void* inc_pose, const void* alpha,
+                                           const void* lr, void* stream) {
+    if (!p || !u || !smooth) return set_error(RLITG_ERR_NULL, "params / update / smooth is NULL");
+    if (p->D != 7) return set_error(RLITG_ERR_SHAPE, "TORM runs the 7-joint arm chain (D = 7)");
+    if (N < 0 || N > 0x7fffffff) return set_error(RLITG_ERR_SHAPE, "N out of range");
+    if (dtype != RLITG_F32 && dtype != RLITG_F64) return set_error(RLITG_ERR_DTYPE, "dtype must be RLITG_F32 or RLITG_F64");
+    if (u->stage != 0 && u->stage != 1) return set_error(RLITG_ERR_ARG, "stage must be 0 (feasible) or 1 (end-pose)");
+    const Smooth* sm = reinterpret_cast<const Smooth*>(smooth);
+    if (sm->T != p->T) return set_error(RLITG_ERR_SHAPE, "smooth handle was built for a different T");
+    if (N == 0) return RLITG_OK;
+    if (!traj) return set_error(RLITG_ERR_NULL, "traj is NULL");
+    if (u->stage == 0 && (!inc_smooth || !inc_coll || !lr)) return set_error(RLITG_ERR_NULL, "feasible stage needs inc_smooth, inc_coll and lr");
+    if (u->stage == 1 && !inc_pose) return set_error(RLITG_ERR_NULL, "end-pose stage needs inc_pose");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == RLITG_F32)
+        return launch_update<float>(u, p, sm, (float*)traj, N, (const float*)inc_smooth, (const float*)inc_coll,
+                                    (const float*)inc_pose, (const float*)alpha, (const float*)lr, st);
+    return launch_update<double>(u, p, sm, (double*)traj, N, (const double*)inc_smooth, (const double*)inc_coll,
+                                 (const double*)inc_pose, (const double*)alpha, (const double*)lr, st);
+}

@@ -220,3 +220,52 @@ class TormBatch:
 
     def getWeightedPoseCost(self, traj):
         return self.cost_grad(traj, STAGE_EVAL)["costs"][:, 6]
+
+
+# ------------------------------------------------------------------------------------------------ update step
+class RlitgTormUpdate(C.Structure):
+    _fields_ = [("stage", C.c_int32), ("lr_schedule_mode", C.c_int32), ("smoothness_update_weight", C.c_double),
+                ("obstacle_update_weight", C.c_double), ("joint_update_limit", C.c_double),
+                ("joint_min", C.c_double * 7), ("joint_max", C.c_double * 7)]
+
+
+lib.rlitg_torm_update.argtypes = [_vp, C.c_int64, C.c_int, _vp, C.POINTER(RlitgTormParams), C.POINTER(RlitgTormUpdate),
+                                  _vp, _vp, _vp, _vp, _vp, _vp]
+
+
+def _apply_increments(self, traj, feasible_stage, inc_smooth=None, inc_coll=None, inc_pose=None, alpha=None,
+                      learning_rate=None, lr_schedule_mode=1):
+    """calculateFeasibleIncrements | calculateEndPoseIncrements, then addIncrementsToTrajectory and
+    handleJointLimits (torm/src/torm_optimizer.cpp:1555-1639, 1189-1268), in place on traj [N,T,7].
+    alpha / learning_rate: python floats or [N] tensors (per-trajectory alpha_ / learning_rate_)."""
+    pr = self.parameters
+    N = traj.shape[0]
+    u = RlitgTormUpdate()
+    u.stage, u.lr_schedule_mode = (0 if feasible_stage else 1), int(lr_schedule_mode)
+    u.smoothness_update_weight = pr.smoothness_update_weight_ / self.T  # the mains pass 30 / T (SURVEY appendix C)
+    u.obstacle_update_weight = pr.obstacle_update_weight_
+    # TormOptimizer's constructor overwrites joint_update_limit_ when lr_schedule_mode_ == 0 (:104-106)
+    u.joint_update_limit = 0.1 if lr_schedule_mode == 0 else pr.joint_update_limit_
+    u.joint_min = (C.c_double * 7)(*fetch.LL)
+    u.joint_max = (C.c_double * 7)(*fetch.UL)
+
+    def vec(x, default):
+        if x is None:
+            x = default
+        if torch.is_tensor(x):
+            return x.to(self.device, traj.dtype).contiguous()
+        return torch.full((N,), float(x), device=self.device, dtype=traj.dtype)
+
+    a = vec(alpha, 0.5)
+    lr = vec(learning_rate, pr.learning_rate_)
+    p = lambda t: None if t is None else t.data_ptr()
+    code = _lib.F32 if traj.dtype == torch.float32 else _lib.F64
+    assert traj.is_contiguous()
+    with _lib.on_device(self.device):
+        check(lib.rlitg_torm_update(traj.data_ptr(), N, code, self.joint_costs_.handle, C.byref(self._cp), C.byref(u),
+                                    p(inc_smooth), p(inc_coll), p(inc_pose), a.data_ptr(), lr.data_ptr(),
+                                    torch.cuda.current_stream().cuda_stream))
+    return traj
+
+
+TormBatch.applyIncrements = _apply_increments
