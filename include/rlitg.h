@@ -262,6 +262,15 @@ RLITG_API int rlitg_torm_update(void* traj, int64_t N, int dtype, const RlitgSmo
                                 const void* inc_coll, const void* inc_pose, const void* alpha, const void* lr,
                                 void* stream);
 
+/* Candidate selection of the Greedy / Linear initialisers: replays the sequential rule of
+ * TormOptimizer::getNewTrajectory (torm/src/torm_optimizer.cpp:973-1003; same at :1066-1096) over C scored
+ * candidates: eCost = ([8] + rot_scale [9]) / (Tseg - 1) (ranged getEndPoseCost :1427-1446), candidates with
+ * eCost above the running best TOTAL cost are skipped (the reference's pruning quirk), total =
+ * pose_w eCost + col_w [5].  costs [C,10] from rlitg_torm_cost_grad run on the C interpolated segments
+ * ([C,Tseg,7], row 0 = segment start).  best_idx int32[1], best_cost [1] (nullable) on the device. */
+RLITG_API int rlitg_greedy_select(const void* costs, int C, int Tseg, int dtype, double rot_scale, double pose_w,
+                                  double col_w, int32_t* best_idx, void* best_cost, void* stream);
+
 /* Measurement aid: launches `ctas` x 256 threads each running 16 independent FFMA chains of `iters` steps
  * (2 * ctas * 256 * iters * 16 flops); bench.py times it with CUDA events to get the FP32 FMA-pipe peak that
  * the TORM kernel's roofline fraction is quoted against. */

@@ -207,3 +207,39 @@ extern "C" RLITG_API int rlitg_torm_update(void* traj, int64_t N, int dtype, con
     return launch_update<double>(u, p, sm, (double*)traj, N, (const double*)inc_smooth, (const double*)inc_coll,
                                  (const double*)inc_pose, (const double*)alpha, (const double*)lr, st);
 }
+
+// ---- candidate selection of the Greedy / Linear initialisers --------------------------------
+// TormOptimizer::getNewTrajectory torm/src/torm_optimizer.cpp:973-1003 (and :1066-1096) walks the candidates in
+// order with a running best TOTAL cost that it compares against each candidate's POSE-ONLY cost (SURVEY appendix B
+// item 9).  The rule is sequential, so one thread replays it over the scored batch; the scoring itself
+// (interpolated segments through rlitg_torm_cost_grad) is the parallel part.
+namespace rlitg {
+template <typename T>
+__global__ void greedy_select_kernel(const T* __restrict__ costs, int C, int Tseg, double rot_scale, double pose_w,
+                                     double col_w, int32_t* __restrict__ best_idx, T* __restrict__ best_cost) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double best = INFINITY;
+    int bi = -1;
+    for (int j = 0; j < C; j++) {
+        const T* c = costs + (size_t)j * RLITG_TORM_NCOST;
+        const double eCost = ((double)c[8] + rot_scale * (double)c[9]) / (double)(Tseg - 1);  // ranged getEndPoseCost
+        if (best < eCost) continue;
+        const double cost = pose_w * eCost + col_w * (double)c[5];
+        if (j == 0 || best > cost) { best = cost; bi = j; }
+    }
+    *best_idx = bi;
+    if (best_cost) *best_cost = (T)best;
+}
+}  // namespace rlitg
+
+extern "C" RLITG_API int rlitg_greedy_select(const void* costs, int C, int Tseg, int dtype, double rot_scale,
+                                             double pose_w, double col_w, int32_t* best_idx, void* best_cost,
+                                             void* stream) {
+    if (!costs || !best_idx) return set_error(RLITG_ERR_NULL, "costs / best_idx is NULL");
+    if (C < 1 || Tseg < 2) return set_error(RLITG_ERR_SHAPE, "C must be >= 1 and Tseg >= 2");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == RLITG_F32) greedy_select_kernel<float><<<1, 32, 0, st>>>((const float*)costs, C, Tseg, rot_scale, pose_w, col_w, best_idx, (float*)best_cost);
+    else if (dtype == RLITG_F64) greedy_select_kernel<double><<<1, 32, 0, st>>>((const double*)costs, C, Tseg, rot_scale, pose_w, col_w, best_idx, (double*)best_cost);
+    else return set_error(RLITG_ERR_DTYPE, "dtype must be RLITG_F32 or RLITG_F64");
+    return check_launch("greedy_select_kernel");
+}

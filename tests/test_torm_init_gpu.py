@@ -1,0 +1,94 @@
+"""GPU tests for the batched Greedy / Linear initialisers: the selection must equal a literal
+CPU replay of TormOptimizer::getNewTrajectory / getJointInterpolatedTrajectory built from oracle pieces."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def cpu_fill(st, gt, num, cj):
+    """fillInLinearInterpolation torm/src/torm_optimizer.cpp:784-807"""
+    out = np.empty((num + 1, 7)); out[0] = st
+    for i in range(7):
+        diff = gt[i] - st[i]
+        if cj[i] and abs(diff) > np.pi:
+            diff = 2 * np.pi - abs(diff) if diff < 0 else -2 * np.pi + abs(diff)
+        theta = diff / num
+        for t in range(1, num + 1):
+            out[t, i] = st[i] + t * theta
+    return out
+
+
+def cpu_greedy(start, cands, targets, pts, osc, clearance, pose_w=1.0, col_w=0.05):
+    from oracle import oracle as O
+    cj = [0, 0, 1, 0, 1, 0, 1]
+    T = targets.shape[0]
+    traj = np.empty((T, 7)); traj[0] = start
+    sp0, chosen = 0, []
+    for i, sp in enumerate(pts):
+        best, bi, bseg = np.inf, -1, None
+        for j, c in enumerate(cands[i]):
+            seg = cpu_fill(traj[sp0], c, sp - sp0, cj)
+            p = O.torm_params(seg.shape[0], clearance=clearance)
+            r = O.torm_cost_grad(seg[None], targets[sp0:sp + 1], osc, p, None, O.STAGE_POSE | O.STAGE_COLL)["costs"][0]
+            e = (r[8] + 0.17 * r[9]) / (seg.shape[0] - 1)
+            if best < e:
+                continue
+            cost = pose_w * e + col_w * r[5]
+            if j == 0 or best > cost:
+                best, bi, bseg = cost, j, seg
+        traj[sp0 + 1:sp + 1] = bseg[1:]
+        chosen.append(bi); sp0 = sp
+    return traj, chosen
+
+
+def test_greedy_and_linear_match_cpu_replay(cuda_device):
+    import torch
+    from oracle import oracle as O
+    from rlitg_b200 import fetch, scene as S, synth, torm as TM, torm_init as TI
+    T, Cn = 47, 12
+    rng = np.random.default_rng(5)
+    demo = synth.random_joint_paths(1, T, seed=3)[0]
+    targets = np.round(O.fk_quat(demo), 6)
+    occ, _ = synth.random_box_scene((64, 96, 64), (-0.3, -0.96, 0.0), 0.025, seed=2, n_clutter=3)
+    link, center, radius = fetch.default_spheres()
+    osc = O.Scene(O.build_field(occ, 0.025, 1.0), (-0.3, -0.96, 0.0), 0.025, link, center, radius)
+    gsc = S.Scene(cuda_device); gsc.set_occupancy(occ, (-0.3, -0.96, 0.0), 0.025, 1.0)
+    pts = TI.simplified_points(T)
+    assert pts == [10, 20, 30, 40, 46]
+    # candidates: the demonstration's own configuration plus perturbed / wrapped variants
+    cands = []
+    for sp in pts:
+        c = demo[sp] + rng.normal(0, 0.4, size=(Cn, 7)); c[3] = demo[sp]; c[5, 2] += 2 * np.pi - 0.3
+        cands.append(np.clip(c, fetch.LL - 3.2, fetch.UL + 3.2))
+    pr = TM.TormParameters(min_clearence_=0.3)
+    ti = TI.TrajectoryInitializer(targets, pr, gsc, cuda_device, torch.float64)
+    traj, chosen, best = ti.getNewTrajectory(demo[0], cands)
+    want, wchosen = cpu_greedy(demo[0], cands, targets, pts, osc, 0.3)
+    assert chosen.cpu().tolist() == wchosen
+    assert np.abs(traj.cpu().numpy() - want).max() < 1e-12
+    # FP32 build picks the same candidates on this problem
+    ti32 = TI.TrajectoryInitializer(targets, pr, gsc, cuda_device, torch.float32)
+    t32, c32, _ = ti32.getNewTrajectory(demo[0], cands)
+    assert c32.cpu().tolist() == wchosen and np.abs(t32.double().cpu().numpy() - want).max() < 5e-6
+    # Linear: 30 goal candidates for the last pose
+    goals = demo[-1] + rng.normal(0, 0.3, size=(30, 7)); goals[7] = demo[-1]
+    lt, li, lb = ti.getJointInterpolatedTrajectory(demo[0], goals)
+    wl, wi = cpu_greedy(demo[0], [goals], targets, [T - 1], osc, 0.3)
+    assert int(li.item()) == wi[0] and np.abs(lt.cpu().numpy() - wl).max() < 1e-12
+    gsc.close()
+
+
+def test_dls_ik_candidates(cuda_device):
+    """New work (not a parity target): candidates must reproduce the target pose through FK."""
+    import torch
+    from oracle import oracle as O
+    from rlitg_b200 import synth, torm_init as TI
+    q_true = synth.random_configs(1, seed=8)[0] * 0.6
+    target = O.fk_quat(q_true[None])[0]
+    q, ok = TI.dls_ik_candidates(target, 256, seed=1, device=cuda_device, dtype=torch.float64)
+    assert ok.float().mean().item() > 0.3
+    sol = q[ok].cpu().numpy()
+    tw = O.pose_diff(sol, np.tile(target, (sol.shape[0], 1)))
+    assert np.abs(tw[:, :3]).max() < 2e-4 and np.abs(tw[:, 3:]).max() < 2e-3
+    assert np.unique(np.round(sol, 1), axis=0).shape[0] > 3  # distinct IK branches, like random restarts give
