@@ -270,3 +270,19 @@ class PirlEnvFetch:
 
     def random_action(self):
         return np.random.uniform(self.act_ll, self.act_ul)
+
+
+def rollout_policy(env: PirlVecEnv, policy, start_conf=None, n_steps=None, deterministic=True):
+    """Batched PirlInterpolator::interpolate (torm/src/pirl_interpolator.cpp:102-140; SURVEY.md 8f-4): for every
+    environment, observation -> policy -> setAction (add, single +-2pi wrap, clamp to the limits; no rejection),
+    one waypoint per step.  `policy(obs [B,O] float32) -> action [B,7]` is any torch callable (the reference's is a
+    TorchScript MLP).  Returns the generated configurations [B, n_steps, 7]."""
+    obs = env.reset(start_conf, mode="test")
+    n_steps = int(env.max_timestep.max().item()) if n_steps is None else n_steps
+    out = torch.empty(env.B, n_steps, 7, device=env.device, dtype=env.dtype)
+    with torch.no_grad():
+        for k in range(n_steps):
+            act = policy(obs.float())
+            obs, _, _, _ = env.step(act)
+            out[:, k] = env.cur_conf
+    return out

@@ -171,3 +171,28 @@ def test_pinv_singular_configuration(cuda_device):
         got = P.pinv_step(torch.tensor(q, dtype=dt, device=cuda_device),
                           torch.tensor(tw, dtype=dt, device=cuda_device)).double().cpu().numpy()
         assert np.isfinite(got).all() and np.abs(got - want).max() < tol, (dtype, got, want)
+
+
+def test_policy_rollout_matches_cpu_loop(cuda_device):
+    """SURVEY 8f-4: batched PirlInterpolator::interpolate with a stand-in torch policy, FP64, vs a CPU loop built
+    from the oracle's env step in test mode."""
+    import torch
+    from oracle import oracle as O
+    from rlitg_b200 import pirl_env as P
+    B, T = 64, 25
+    c = build_case(B, T, 13, False, cuda_device)
+    torch.manual_seed(0)
+    W = (torch.randn(88, 7, dtype=torch.float64) * 0.02)
+    policy = lambda obs: torch.tanh(obs.double() @ W.to(obs.device)) * 0.26
+    env = P.PirlVecEnv(B, device=cuda_device, dtype=torch.float64)
+    mts = np.full(B, T - 1, dtype=np.int32)
+    env.set_problems(c["targets"], c["demos"], mts)
+    got = P.rollout_policy(env, policy, n_steps=T - 1).cpu().numpy()
+    ocfg = O.pirl_cfg(train_mode=False)
+    q = c["demos"][:, 0].copy(); ts = np.zeros(B, dtype=np.int32)
+    obs = O.pirl_obs(ocfg, q, ts, mts, c["targets"])
+    for k in range(T - 1):
+        act = (np.tanh(obs.astype(np.float32).astype(np.float64) @ W.numpy()) * 0.26).astype(np.float32)
+        r = O.pirl_env_step(ocfg, q, act, ts, mts, c["targets"], c["demos"])
+        q, ts, obs = r["q"], r["timestep"], r["obs"]
+        assert np.abs(got[:, k] - q).max() < 1e-6, k  # float32 observations feed the policy on both sides
