@@ -80,6 +80,28 @@ def run(dev, rank, world, max_over_ranks, barrier, steps=30, warmup=5):
     ms_full_cold = max_over_ranks(_time_loop(torch, lambda: tb.cost_grad(traj, full), min(steps, 10), 2, flush))
     ms_feas = max_over_ranks(_time_loop(torch, lambda: tb.cost_grad(traj, feas), steps, warmup))
     ms_pose = max_over_ranks(_time_loop(torch, lambda: tb.cost_grad(traj, pose), steps, warmup))
+    # CPU baseline for this workload: the FP64 oracle (restatement of the reference's serial loops) on all host
+    # threads, on a bounded sample of the same trajectories (rank 0, single-GPU run only)
+    cpu = None
+    if rank == 0 and world == 1:
+        try:
+            from oracle import oracle as O
+            O.set_num_threads(len(os.sched_getaffinity(0)))
+            n_s = 128
+            link, center, radius = fetch.default_spheres()
+            osc = O.Scene(O.build_field(occ, 0.02, 1.0), (-0.64, -1.28, -0.20), 0.02, link, center, radius)
+            op = O.torm_params(T, dt=0.1, clearance=0.3)
+            Aband, _, _ = O.smooth_setup(T, 0.1, (1.0, 0.0, 0.0), 0.0)
+            tj = traj[:n_s].double().cpu().numpy()
+            O.torm_cost_grad(tj[:8], targets, osc, op, Aband, full)
+            t0 = time.perf_counter(); reps = 0
+            while time.perf_counter() - t0 < 6.0:
+                O.torm_cost_grad(tj, targets, osc, op, Aband, full); reps += 1
+            dtc = time.perf_counter() - t0
+            cpu = {"value": reps * n_s * (T - 1) / dtc, "unit": "waypoints/s", "cores": O.num_threads(), "kind": "port",
+                   "sample": "%d x %d trajectories x %d waypoints, all stages, FP64 oracle (OpenMP), %.1f s" % (reps, n_s, T - 1, dtc)}
+        except Exception as e:  # noqa: BLE001
+            cpu = {"error": str(e)}
     flop_wp = 2060.0 + 430.0 * A  # SURVEY 8d per-waypoint figure
     wps = world * N * (T - 1)
     tf = flop_wp * N * (T - 1) / (ms_full * 1e-3) / 1e12
@@ -93,7 +115,7 @@ def run(dev, rank, world, max_over_ranks, barrier, steps=30, warmup=5):
         "roofline": {"bound": "fp32_fma", "achieved": tf, "peak": fma_peak, "unit": "TFLOP/s",
                      "frac": (tf / fma_peak) if fma_peak else None, "flop_per_waypoint": flop_wp,
                      "peak_source": "measured on this GPU by rlitg_fma_probe (FFMA chains, 16-way ILP)"},
-        "target_ms": 1.0}
+        "target_ms": 1.0, "cpu_baseline": cpu}
 
     # ---------------------------------------------------------------- PIRL env step
     for B in (16384, 65536):
@@ -126,11 +148,19 @@ def run(dev, rank, world, max_over_ranks, barrier, steps=30, warmup=5):
         ms = max_over_ranks(_time_loop(torch, step_only, steps, warmup))
         env.timestep.copy_(ts0)
         ms_cold = max_over_ranks(_time_loop(torch, step_only, min(steps, 10), 2, flush))
+        # launch-bound batch sizes: the same step captured in a CUDA graph (one replay = one step)
+        us_graph = None
+        try:
+            g, _ = env.capture_step_graph(act)
+            us_graph = 1e3 * max_over_ranks(_time_loop(torch, g.replay, steps, warmup))
+        except Exception:  # noqa: BLE001
+            us_graph = None
         bytes_env = 536.0
         out["pirl_env_step_%d" % B] = {
             "config": {"workload": "pirl_env_step", "envs_per_gpu": B, "obs": "Conf+LinkPoses t=1 z=0 (88 floats)",
                        "reward": "Task+NullSpaceImitation", "l2": "batch is L2 resident (8.8 MB at 16k envs); *_cold = L2 flushed"},
-            "us_per_step": ms * 1e3, "us_per_step_cold": ms_cold * 1e3, "env_steps_per_s": world * B / (ms * 1e-3),
+            "us_per_step": ms * 1e3, "us_per_step_cold": ms_cold * 1e3, "us_per_step_cuda_graph": us_graph,
+            "env_steps_per_s": world * B / (ms * 1e-3),
             "unit": "env-steps/s", "roofline": {"bound": "hbm", "achieved": bytes_env * B / (ms * 1e-3) / 1e9,
                                                "unit": "GB/s", "bytes_per_env": bytes_env}}
     sc.close()

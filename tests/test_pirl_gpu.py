@@ -196,3 +196,29 @@ def test_policy_rollout_matches_cpu_loop(cuda_device):
         r = O.pirl_env_step(ocfg, q, act, ts, mts, c["targets"], c["demos"])
         q, ts, obs = r["q"], r["timestep"], r["obs"]
         assert np.abs(got[:, k] - q).max() < 1e-6, k  # float32 observations feed the policy on both sides
+
+
+def test_step_cuda_graph_replay(cuda_device):
+    """The fused step is capturable (no allocation / sync inside): graph replays equal eager steps."""
+    import torch
+    from rlitg_b200 import pirl_env as P
+    B, T = 512, 30
+    c = build_case(B, T, 17, False, cuda_device)
+    mts = np.full(B, T - 1, dtype=np.int32)
+    envs = []
+    for _ in range(2):
+        e = P.PirlVecEnv(B, device=cuda_device, dtype=torch.float32)
+        e.set_problems(c["targets"], c["demos"], mts)
+        e.reset()
+        envs.append(e)
+    act = torch.zeros(B, 7, device=cuda_device)
+    g, out = envs[0].capture_step_graph(act)
+    envs[0].reset()  # capture ran the step twice (warm-up + capture): start both envs from the same state
+    gen = torch.Generator(device="cpu"); gen.manual_seed(0)
+    for k in range(5):
+        a = (torch.rand(B, 7, generator=gen) * 0.52 - 0.26).to(cuda_device)
+        act.copy_(a)
+        g.replay()
+        o2, r2, d2, _ = envs[1].step(a)
+        assert torch.equal(out[0], o2) and torch.equal(out[1], r2) and torch.equal(out[2], d2)
+        assert torch.equal(envs[0].timestep, envs[1].timestep)
