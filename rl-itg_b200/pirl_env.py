@@ -174,7 +174,7 @@ class PirlVecEnv:
             q0 = torch.where(need, wrapped, q0)
         else:
             q0 = torch.as_tensor(start_conf).to(self.device, self.dtype)
-        self.cur_conf = q0.contiguous()
+        self.cur_conf.copy_(q0.reshape(self.B, 7))  # in place: captured CUDA graphs keep pointing at this buffer
         self.timestep.zero_()
         self.counters.zero_()
         self._pre = None
