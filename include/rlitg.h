@@ -116,6 +116,12 @@ RLITG_API int rlitg_scene_set_field(RlitgScene* scene, const float* field, int n
 /* Read-back for parity tests: field_out float [nz][ny][nx][4]; bits_out uint32 [nz][ny][ceil(nx/32)]. */
 RLITG_API int rlitg_scene_get_field(const RlitgScene* scene, float* field_out);
 RLITG_API int rlitg_scene_get_bits(const RlitgScene* scene, uint32_t* bits_out);
+/* The occupancy dilated by each distinct sphere radius (bit = signed distance < radius), bit-packed like the
+ * occupancy: the volumes the binary collision test reads (one bit per sphere; staged in shared memory when they
+ * fit, e.g. for the pirl_gazebo grid).  ncls_out int32[1] (0 = not built: more than 8 distinct radii);
+ * radii_out float[ncls] and bits_out uint32[ncls][nz][ny][ceil(nx/32)] may be NULL. */
+RLITG_API int rlitg_scene_get_dilated(const RlitgScene* scene, int32_t* ncls_out, float* radii_out,
+                                      uint32_t* bits_out);
 
 /* cc_srv: `/collision_check` service (pirl_msgs/srv/collision.srv, pirl/src/collision_checker.cpp:39-61) and
  * TormIKSolver::collisionChecking (torm/src/torm_ik_solver.cpp:59-66).  out[b] = 1 when any sphere of

@@ -108,9 +108,7 @@ struct PirlVisit {
                 const V3<T> x = {off.x + f.p.x + f.c0.x * T(c.x) + f.c1.x * T(c.y) + f.c2.x * T(c.z),
                                  off.y + f.p.y + f.c0.y * T(c.x) + f.c1.y * T(c.y) + f.c2.y * T(c.z),
                                  off.z + f.p.z + f.c0.z * T(c.x) + f.c1.z * T(c.y) + f.c2.z * T(c.z)};
-                T d;
-                V3<T> g;
-                if (field_lookup(*sc, gm, x, d, g) && d - T(c.w) < T(0)) hit = true;
+                if (sphere_hits(*sc, gm, x, s, c.w, sc->dil)) hit = true;
             }
         }
     }

@@ -99,6 +99,10 @@ struct Scene {
     uint32_t* bits = nullptr;
     float4* spheres = nullptr;
     int* link_start = nullptr;
+    uint32_t* dil = nullptr;      // dilated bit volumes, one per distinct sphere radius
+    int* sph_class = nullptr;
+    int ncls = 0;
+    std::vector<float> h_radius;  // host copy of the sphere radii (float32, as stored on the device)
     int S = 0;
     int nx = 0, ny = 0, nz = 0, wx = 0;
     double origin[3] = {0, 0, 0};
@@ -107,17 +111,25 @@ struct Scene {
     void free_grid() {
         if (field) cudaFree(field);
         if (bits) cudaFree(bits);
+        free_dilated();
         field = nullptr; bits = nullptr;
         nx = ny = nz = wx = 0;
+    }
+    void free_dilated() {
+        if (dil) cudaFree(dil);
+        if (sph_class) cudaFree(sph_class);
+        dil = nullptr; sph_class = nullptr; ncls = 0;
     }
     void free_spheres() {
         if (spheres) cudaFree(spheres);
         if (link_start) cudaFree(link_start);
+        free_dilated();
         spheres = nullptr; link_start = nullptr; S = 0;
     }
     SceneDev dev() const {
         SceneDev d;
         d.field = field; d.bits = bits; d.spheres = spheres; d.link_start = link_start;
+        d.dil = dil; d.sph_class = sph_class; d.ncls = ncls;
         d.S = S; d.nx = nx; d.ny = ny; d.nz = nz; d.wx = wx;
         d.origin[0] = origin[0]; d.origin[1] = origin[1]; d.origin[2] = origin[2];
         d.res = res;
@@ -134,6 +146,60 @@ bool scene_ready(const Scene* s, bool need_grid, bool need_spheres) {
 SceneDev scene_dev(const Scene* s) { return s->dev(); }
 
 static inline unsigned blocks_for(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// occupancy dilated by a sphere radius, bit-packed like `bits`: bit = active cell with signed distance < radius.
+// One warp per 32-cell word (ballot).  These volumes turn the binary collision test into a single-bit lookup.
+__global__ void dilate_kernel(const float4* __restrict__ field, int nx, int ny, int nz, int wx, float radius,
+                              uint32_t* __restrict__ out) {
+    const int64_t nwords = (int64_t)wx * ny * nz;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= nwords) return;
+    const int w = (int)(warp % wx);
+    const int64_t row = warp / wx;
+    const int x = w * 32 + lane;
+    bool on = false;
+    if (x < nx) {
+        const float d = field[row * nx + x].x;
+        on = d < 1e29f && d < radius;
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) out[warp] = m;
+}
+
+constexpr int kMaxRadiusClasses = 8;
+
+// (re)builds the dilated bit volumes once both the sphere table and the grid are present
+static int rebuild_dilated(Scene* s) {
+    s->free_dilated();
+    if (!s->field || !s->spheres || s->S == 0) return RLITG_OK;
+    std::vector<float> cls;
+    std::vector<int> sc(s->S);
+    for (int i = 0; i < s->S; i++) {
+        int k = -1;
+        for (size_t c = 0; c < cls.size(); c++)
+            if (cls[c] == s->h_radius[i]) k = (int)c;
+        if (k < 0) { cls.push_back(s->h_radius[i]); k = (int)cls.size() - 1; }
+        sc[i] = k;
+    }
+    if ((int)cls.size() > kMaxRadiusClasses) return RLITG_OK;  // many distinct radii: keep the record-based test
+    const size_t words = (size_t)s->wx * s->ny * s->nz;
+    if (cudaMalloc(&s->dil, sizeof(uint32_t) * words * cls.size()) != cudaSuccess ||
+        cudaMalloc(&s->sph_class, sizeof(int) * s->S) != cudaSuccess ||
+        cudaMemcpy(s->sph_class, sc.data(), sizeof(int) * s->S, cudaMemcpyHostToDevice) != cudaSuccess) {
+        s->free_dilated();
+        return set_cuda_error("rebuild_dilated");
+    }
+    for (size_t c = 0; c < cls.size(); c++) {
+        dilate_kernel<<<blocks_for((int64_t)words * 32, 256), 256>>>(s->field, s->nx, s->ny, s->nz, s->wx, cls[c],
+                                                                     s->dil + c * words);
+        int rc = check_launch("dilate_kernel");
+        if (rc) return rc;
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) return set_cuda_error("rebuild_dilated");
+    s->ncls = (int)cls.size();
+    return RLITG_OK;
+}
 
 // ---- binary collision: any sphere with d(centre cell) - r < 0 ---------------------------------------------
 // B200 stand-in for cc_srv / TormIKSolver::collisionChecking (pirl/src/collision_checker.cpp:39-61,
@@ -154,9 +220,7 @@ struct CollideVisit {
                 const V3<T> x = {off.x + f.p.x + f.c0.x * T(c.x) + f.c1.x * T(c.y) + f.c2.x * T(c.z),
                                  off.y + f.p.y + f.c0.y * T(c.x) + f.c1.y * T(c.y) + f.c2.y * T(c.z),
                                  off.z + f.p.z + f.c0.z * T(c.x) + f.c1.z * T(c.y) + f.c2.z * T(c.z)};
-                T d;
-                V3<T> g;
-                if (field_lookup(sc, gm, x, d, g) && d - T(c.w) < T(0)) hit = true;
+                if (sphere_hits(sc, gm, x, s, c.w, sc.dil)) hit = true;
             }
         }
     }
@@ -182,10 +246,85 @@ __global__ void __launch_bounds__(128) sphere_collide_kernel(const T* __restrict
     out[b] = v.hit ? 1 : 0;
 }
 
+// Persistent variant for grids whose dilated bit volumes fit in shared memory (e.g. the pirl_gazebo 50 x 70 x 50
+// grid: 6 radius classes x 28 KB): each CTA stages the bit volumes once and then tests configurations from them,
+// so the only global traffic is q in and one byte out per configuration.
+template <typename T>
+struct CollideSmemVisit {
+    const SceneDev& sc;
+    const GridMap<T>& gm;
+    const float4* sph;
+    const int* link_start;
+    const int* cls;         // shared-memory copy of sph_class
+    const uint32_t* dil;    // shared-memory copy of the dilated volumes
+    size_t words;
+    V3<T> off;
+    bool hit = false;
+    template <int K>
+    RLITG_DEV void operator()(jidx<K>, const FrameC<T>& f) {
+        if constexpr (K < kNumLinks) {
+            for (int s = link_start[K]; s < link_start[K + 1]; s++) {
+                const float4 c = sph[s];
+                const V3<T> x = {off.x + f.p.x + f.c0.x * T(c.x) + f.c1.x * T(c.y) + f.c2.x * T(c.z),
+                                 off.y + f.p.y + f.c0.y * T(c.x) + f.c1.y * T(c.y) + f.c2.y * T(c.z),
+                                 off.z + f.p.z + f.c0.z * T(c.x) + f.c1.z * T(c.y) + f.c2.z * T(c.z)};
+                const int cx = gm.cell1(x.x, gm.ox), cy = gm.cell1(x.y, gm.oy), cz = gm.cell1(x.z, gm.oz);
+                if (cx < 0 || cy < 0 || cz < 0 || cx >= sc.nx || cy >= sc.ny || cz >= sc.nz) continue;
+                const uint32_t w = dil[(size_t)cls[s] * words + ((size_t)cz * sc.ny + cy) * sc.wx + (cx >> 5)];
+                if ((w >> (cx & 31)) & 1u) hit = true;
+            }
+        }
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) sphere_collide_smem_kernel(const T* __restrict__ q, int64_t B, SceneDev sc,
+                                                                  double ox, double oy, double oz,
+                                                                  uint8_t* __restrict__ out) {
+    extern __shared__ __align__(16) uint32_t s_dil[];
+    __shared__ float4 s_sph[kMaxSpheres];
+    __shared__ int s_start[kNumLinks + 1];
+    __shared__ int s_cls[kMaxSpheres];
+    const size_t words = (size_t)sc.wx * sc.ny * sc.nz;
+    const size_t total = words * sc.ncls;
+    for (size_t i = threadIdx.x; i < total; i += blockDim.x) s_dil[i] = sc.dil[i];
+    for (int i = threadIdx.x; i < sc.S; i += blockDim.x) { s_sph[i] = sc.spheres[i]; s_cls[i] = sc.sph_class[i]; }
+    if (threadIdx.x <= kNumLinks) s_start[threadIdx.x] = sc.link_start[threadIdx.x];
+    __syncthreads();
+    const GridMap<T> gm(sc);
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x) {
+        T qv[7];
+#pragma unroll
+        for (int j = 0; j < 7; j++) qv[j] = q[b * 7 + j];
+        CollideSmemVisit<T> v{sc, gm, s_sph, s_start, s_cls, s_dil, words, {T(ox), T(oy), T(oz)}};
+        walk_chain<T, 7>(qv, v);
+        out[b] = v.hit ? 1 : 0;
+    }
+}
+
 template <typename T>
 int launch_sphere_collide(const T* q, int64_t B, const Scene* s, const double* base_off, uint8_t* out,
                           cudaStream_t st) {
     if (B == 0) return RLITG_OK;
+    const size_t dil_bytes = sizeof(uint32_t) * (size_t)s->wx * s->ny * s->nz * s->ncls;
+    if (s->dil && dil_bytes <= 200 * 1024 && B >= 4096) {
+        auto kern = sphere_collide_smem_kernel<T>;
+        static size_t attr_smem = 0;
+        static int num_sms = 0;
+        if (dil_bytes > attr_smem) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dil_bytes) != cudaSuccess)
+                return set_cuda_error("cudaFuncSetAttribute(sphere_collide_smem_kernel)");
+            attr_smem = dil_bytes;
+        }
+        if (num_sms == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        }
+        const unsigned grid = (unsigned)std::min<int64_t>(num_sms, (B + 255) / 256);
+        kern<<<grid, 256, dil_bytes, st>>>(q, B, s->dev(), base_off[0], base_off[1], base_off[2], out);
+        return check_launch("sphere_collide_smem_kernel");
+    }
     sphere_collide_kernel<T><<<blocks_for(B, 128), 128, 0, st>>>(q, B, s->dev(), base_off[0], base_off[1],
                                                                  base_off[2], out);
     return check_launch("sphere_collide_kernel");
@@ -244,7 +383,9 @@ RLITG_API int rlitg_scene_set_spheres(RlitgScene* h, int S, const int32_t* link,
     CUDA_TRY(cudaMemcpy(s->link_start, start.data(), sizeof(int) * (kNumLinks + 1), cudaMemcpyHostToDevice), "H2D link_start");
     s->S = S;
     s->h_link.assign(link, link + S);
-    return RLITG_OK;
+    s->h_radius.resize(S);
+    for (int i = 0; i < S; i++) s->h_radius[i] = sp[i].w;
+    return rebuild_dilated(s);
 }
 
 static int scene_alloc_grid(Scene* s, int nx, int ny, int nz, const double* origin, double res) {
@@ -298,7 +439,8 @@ RLITG_API int rlitg_scene_set_occupancy(RlitgScene* h, const uint8_t* occ, int n
     cudaError_t e = cudaDeviceSynchronize();
     cudaFree(d_occ); cudaFree(a); cudaFree(b); cudaFree(dso); cudaFree(d);
     if (e != cudaSuccess) return set_cuda_error("scene_set_occupancy");
-    return rc;
+    if (rc) return rc;
+    return rebuild_dilated(s);
 }
 
 RLITG_API int rlitg_scene_set_field(RlitgScene* h, const float* field, int nx, int ny, int nz, const double* origin,
@@ -308,7 +450,7 @@ RLITG_API int rlitg_scene_set_field(RlitgScene* h, const float* field, int nx, i
     int rc = scene_alloc_grid(s, nx, ny, nz, origin, res);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpy(s->field, field, sizeof(float4) * (size_t)nx * ny * nz, cudaMemcpyHostToDevice), "H2D field");
-    return RLITG_OK;
+    return rebuild_dilated(s);
 }
 
 RLITG_API int rlitg_scene_get_field(const RlitgScene* h, float* field_out) {
@@ -322,6 +464,24 @@ RLITG_API int rlitg_scene_get_bits(const RlitgScene* h, uint32_t* bits_out) {
     const Scene* s = reinterpret_cast<const Scene*>(h);
     if (!s || !bits_out || !s->bits) return set_error(RLITG_ERR_NULL, "scene has no grid / output is NULL");
     CUDA_TRY(cudaMemcpy(bits_out, s->bits, sizeof(uint32_t) * (size_t)s->wx * s->ny * s->nz, cudaMemcpyDeviceToHost), "D2H bits");
+    return RLITG_OK;
+}
+
+RLITG_API int rlitg_scene_get_dilated(const RlitgScene* h, int32_t* ncls_out, float* radii_out, uint32_t* bits_out) {
+    const Scene* s = reinterpret_cast<const Scene*>(h);
+    if (!s || !ncls_out) return set_error(RLITG_ERR_NULL, "scene / ncls_out is NULL");
+    *ncls_out = s->ncls;
+    if (s->ncls == 0) return RLITG_OK;
+    if (radii_out) {  // class radii in first-appearance order of the sphere table
+        int k = 0;
+        for (int i = 0; i < s->S && k < s->ncls; i++) {
+            bool seen = false;
+            for (int j = 0; j < i; j++) seen = seen || (s->h_radius[j] == s->h_radius[i]);
+            if (!seen) radii_out[k++] = s->h_radius[i];
+        }
+    }
+    if (bits_out)
+        CUDA_TRY(cudaMemcpy(bits_out, s->dil, sizeof(uint32_t) * (size_t)s->wx * s->ny * s->nz * s->ncls, cudaMemcpyDeviceToHost), "D2H dilated bits");
     return RLITG_OK;
 }
 

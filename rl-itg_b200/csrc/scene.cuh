@@ -18,6 +18,9 @@ struct SceneDev {
     const uint32_t* bits;    // occupancy, bit-packed along x: word (z*ny + y)*wx + (x >> 5)
     const float4* spheres;   // [S] (cx, cy, cz, r) in the link frame, sorted by link
     const int* link_start;   // [kNumLinks + 1] sphere index ranges per link
+    const uint32_t* dil;     // [ncls][nz][ny][wx] occupancy dilated by each distinct sphere radius: bit = (d < r)
+    const int* sph_class;    // [S] radius class of each sphere (index into dil); nullptr when dil is not built
+    int ncls;
     int S;
     int nx, ny, nz, wx;
     double origin[3];
@@ -53,6 +56,23 @@ RLITG_DEV bool field_lookup(const SceneDev& s, const GridMap<T>& gm, V3<T> x, T&
     d = T(r.x);
     g = {T(r.y), T(r.z), T(r.w)};
     return true;
+}
+
+// Binary sphere test "signed distance at the centre cell < radius".  With the dilated bit volumes this is one
+// bit of a 4-byte word (32 cells along x share it) instead of a 16-byte record; the predicate is the same.
+template <typename T>
+RLITG_DEV bool sphere_hits(const SceneDev& s, const GridMap<T>& gm, V3<T> x, int sphere, float radius,
+                           const uint32_t* dil /* s.dil or a shared-memory copy */) {
+    if (dil != nullptr) {
+        const int cx = gm.cell1(x.x, gm.ox), cy = gm.cell1(x.y, gm.oy), cz = gm.cell1(x.z, gm.oz);
+        if (cx < 0 || cy < 0 || cz < 0 || cx >= s.nx || cy >= s.ny || cz >= s.nz) return false;
+        const size_t words = (size_t)s.wx * s.ny * s.nz;
+        const uint32_t w = dil[(size_t)s.sph_class[sphere] * words + ((size_t)cz * s.ny + cy) * s.wx + (cx >> 5)];
+        return (w >> (cx & 31)) & 1u;
+    }
+    T d;
+    V3<T> g;
+    return field_lookup(s, gm, x, d, g) && (float)d < radius;
 }
 
 }  // namespace rlitg

@@ -21,6 +21,7 @@ lib.rlitg_scene_set_occupancy.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_i
 lib.rlitg_scene_set_field.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double]
 lib.rlitg_scene_get_field.argtypes = [C.c_void_p, C.c_void_p]
 lib.rlitg_scene_get_bits.argtypes = [C.c_void_p, C.c_void_p]
+lib.rlitg_scene_get_dilated.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 lib.rlitg_sphere_grid_collide.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 
 # the pirl_gazebo grid geometry (cell centres): pirl_gazebo/script/save_pointcloud.py:22-27
@@ -94,6 +95,19 @@ class Scene:
         with _lib.on_device(self.device):
             check(lib.rlitg_scene_get_bits(self._h, out.ctypes.data))
         return out
+
+    def get_dilated(self):
+        """-> (radii float32 [ncls], bits uint32 [ncls, nz, ny, ceil(nx/32)]) or (None, None) when not built."""
+        n = C.c_int32(0)
+        with _lib.on_device(self.device):
+            check(lib.rlitg_scene_get_dilated(self._h, C.byref(n), None, None))
+            if n.value == 0:
+                return None, None
+            nz, ny, nx = self.shape
+            radii = np.empty(n.value, dtype=np.float32)
+            bits = np.empty((n.value, nz, ny, (nx + 31) // 32), dtype=np.uint32)
+            check(lib.rlitg_scene_get_dilated(self._h, C.byref(n), radii.ctypes.data, bits.ctypes.data))
+        return radii, bits
 
     def collide(self, q):
         """cc_srv for a batch: uint8 [B], 1 = some sphere penetrates an occupied region."""

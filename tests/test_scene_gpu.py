@@ -84,3 +84,39 @@ def test_scene_errors(cuda_device):
     with pytest.raises(RlitgError):
         sc.collide(torch.zeros(4, 7, device=cuda_device))  # no grid / spheres yet
     sc.close()
+
+
+def test_dilated_bit_volumes_and_smem_collide(cuda_device):
+    """North-star item: the occupancy is staged as bit-packed volumes (one per sphere radius) and the binary test
+    reads one bit per sphere -- from shared memory when the volumes fit (pirl_gazebo grid, 50 x 70 x 50 @ 0.02 m)."""
+    import torch
+    from oracle import oracle as O
+    from rlitg_b200 import fetch, scene as S, synth
+    g = S.PIRL_GAZEBO_GRID
+    rng = np.random.default_rng(3)
+    grid_xyz = np.zeros((50, 70, 50))
+    grid_xyz[20:40, 10:60, 0:18] = 1.0          # a table slab, [ix][iy][iz] like occ_N.npy
+    grid_xyz[25:30, 30:36, 18:30] = 1.0         # a box on it
+    sc = S.Scene(cuda_device)
+    sc.set_pirl_gazebo_occ(grid_xyz)
+    field = sc.get_field()
+    radii, bits = sc.get_dilated()
+    link, center, radius = fetch.default_spheres()
+    assert radii is not None and sorted(radii.tolist()) == sorted(set(np.float32(radius).tolist()))
+    nz, ny, nx = sc.shape
+    for k, r in enumerate(radii):
+        unpacked = ((bits[k][..., None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(nz, ny, -1)[..., :nx].astype(bool)
+        want = (field[..., 0] < 1e29) & (field[..., 0] < r)
+        assert np.array_equal(unpacked, want), k
+    occ = np.transpose(grid_xyz, (2, 1, 0)) != 0
+    osc = O.Scene(O.build_field(occ, g["res"], 1.0), g["origin"], g["res"], link, center, radius)
+    q = synth.random_configs(30000, seed=6)
+    want = O.sphere_collide(q, osc, fetch.BASE_OFFSET)
+    assert 0.02 < want.mean() < 0.98
+    for dtype, tol in ((torch.float64, 0), (torch.float32, 20)):
+        tq = torch.tensor(q, dtype=dtype, device=cuda_device)
+        big = sc.collide(tq).cpu().numpy()          # >= 4096 configurations: shared-memory resident volumes
+        small = torch.cat([sc.collide(tq[i:i + 1000]) for i in range(0, 30000, 1000)]).cpu().numpy()  # global path
+        assert np.array_equal(big, small)
+        assert int((big != want).sum()) <= tol
+    sc.close()
