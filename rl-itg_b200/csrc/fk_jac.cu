@@ -154,18 +154,21 @@ __global__ void __launch_bounds__(kTile) fk_jac_persist_kernel(const T* __restri
     T* stage0 = reinterpret_cast<T*>(smem_raw);
     const int tid = threadIdx.x;
     int64_t tile = blockIdx.x;
-    T qn[D];
-    auto load_q = [&](int64_t t) {
+    // joint vectors are prefetched two tiles ahead: under the kernel's write stream a read takes longer than one
+    // tile's worth of arithmetic (a one-tile prefetch still showed 20 % long-scoreboard stalls at its first use)
+    T qn[D], qn2[D];
+    auto load_q = [&](int64_t t, T (&dst)[D]) {
         const int64_t b = t * kTile + tid;
 #pragma unroll
-        for (int j = 0; j < D; j++) qn[j] = QSOA ? ld_stream(q + (int64_t)j * B + b) : ld_stream(q + b * D + j);
+        for (int j = 0; j < D; j++) dst[j] = QSOA ? ld_stream(q + (int64_t)j * B + b) : ld_stream(q + b * D + j);
     };
-    if (tile < ntiles) load_q(tile);
+    if (tile < ntiles) load_q(tile, qn);
+    if (tile + gridDim.x < ntiles) load_q(tile + gridDim.x, qn2);
     for (int it = 0; tile < ntiles; tile += gridDim.x, it++) {
         T qv[D];
 #pragma unroll
-        for (int j = 0; j < D; j++) qv[j] = qn[j];
-        if (tile + gridDim.x < ntiles) load_q(tile + gridDim.x);
+        for (int j = 0; j < D; j++) { qv[j] = qn[j]; qn[j] = qn2[j]; }
+        if (tile + 2 * (int64_t)gridDim.x < ntiles) load_q(tile + 2 * (int64_t)gridDim.x, qn2);
 
         FkJac<T, D> fj;
         walk_chain<T, D>(qv, fj);

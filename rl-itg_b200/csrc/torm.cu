@@ -222,8 +222,8 @@ RLITG_DEV void block_reduce(T (&red)[NR], T* s_red, T (&tot)[NR]) {
 // ---- kernel 3a: end-pose error / pinv step (A5) + trajectory evaluator (A8) -------------------------------
 // Writes costs[0..4], [6..9]; costs[5] (collision) is zeroed when the collision kernel does not run.
 constexpr int kNRedPose = 11;
-template <typename T, int MINB>
-__global__ void __launch_bounds__(kTormMaxThreads, MINB)
+template <typename T, int MAXREG>
+__global__ void __launch_bounds__(kTormMaxThreads) __maxnreg__(MAXREG)
 torm_pose_eval_kernel(TormP<T> P, const T* __restrict__ traj, const T* __restrict__ targets, int stage_mask,
                       int zero_coll_cost, T* __restrict__ inc_pose, T* __restrict__ costs) {
     const int CH = blockDim.x, tid = threadIdx.x, Tn = P.Tn;
@@ -653,10 +653,10 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
     if (!run_pose && !run_coll) return set_error(RLITG_ERR_ARG, "stage_mask selects no stage");
     if (run_pose) {
         const size_t smem = sizeof(T) * ((size_t)(CH + 12) * 7 + (size_t)(CH + 3) * 7 + 8 * kNRedPose);
-        // register budget of the pose kernel: 2 CTAs/SM (128 regs) or 3 (80 regs, some spills); RLITG_TORM_POSE_OCC
+        // register budget of the pose kernel: 2 CTAs/SM (128 regs) or 3 (96 regs at 224 threads); RLITG_TORM_POSE_OCC
         static const int occ = [] { const char* e = getenv("RLITG_TORM_POSE_OCC"); return e ? atoi(e) : 2; }();
-        auto kern = (sizeof(T) == 4 && occ == 3) ? torm_pose_eval_kernel<T, (sizeof(T) == 4 ? 3 : 1)>
-                                                 : torm_pose_eval_kernel<T, (sizeof(T) == 4 ? 2 : 1)>;
+        auto kern = (sizeof(T) == 4 && occ == 3) ? torm_pose_eval_kernel<T, (sizeof(T) == 4 ? 96 : 255)>
+                                                 : torm_pose_eval_kernel<T, (sizeof(T) == 4 ? 128 : 255)>;
         static size_t attr_smem = 0;
         if (smem > attr_smem) {
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
