@@ -269,3 +269,51 @@ def _apply_increments(self, traj, feasible_stage, inc_smooth=None, inc_coll=None
 
 
 TormBatch.applyIncrements = _apply_increments
+
+
+def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, check_collision=True):
+    """Lock-step two-stage gradient descent over the N trajectories of `traj` (in place): the loop body of
+    TormOptimizer::localOptimizeTSGD (torm/src/torm_optimizer.cpp:397-598) with lr_schedule_mode_ == 3 (fixed
+    learning rate, alpha_ = 0.5, stage 0 = feasible, stage 1 = end-pose, :471-473, :497-499), entirely on the device:
+    cost + increments (kernels 3a / 3b), update step, and the best-trajectory bookkeeping of :506-560 (a trajectory is
+    recorded when its evaluator cost improves and it is collision free and within the velocity limits).
+    The adaptive schedules (modes 1, 2) are scalar host control flow per trajectory and stay with the caller.
+    Returns (best_traj [N,T,7], best_cost [N]); best_cost stays +inf for trajectories never found feasible."""
+    pr = self.parameters
+    N = traj.shape[0]
+    best_cost = torch.full((N,), float("inf"), device=self.device, dtype=traj.dtype)
+    best_traj = traj.clone()
+    lr = pr.learning_rate_ if learning_rate is None else learning_rate
+    has_scene = self.scene is not None
+    zeros = None
+    for it in range(maxiter):
+        for stage in (0, 1):
+            feasible_stage = stage == 0
+            if feasible_stage:
+                mask = STAGE_SMOOTH | STAGE_EVAL | (STAGE_COLL if has_scene else 0)
+            else:
+                mask = STAGE_POSE_GRAD | STAGE_EVAL
+            r = self.cost_grad(traj, mask)
+            cur_cost = r["costs"][:, 6]
+            feas = torch.ones(N, dtype=torch.bool, device=self.device)
+            if pr.use_velocity_check_:
+                feas &= r["costs"][:, 7] == 0
+            if has_scene and check_collision and pr.use_collision_check_:
+                hit = self.scene.collide(traj.reshape(-1, 7)).reshape(N, self.T)
+                feas &= hit.sum(dim=1) == 0
+            better = feas & (cur_cost < best_cost)
+            best_cost = torch.where(better, cur_cost, best_cost)
+            best_traj = torch.where(better[:, None, None], traj, best_traj)
+            if feasible_stage:
+                inc_c = r["inc_coll"]
+                if inc_c is None:
+                    if zeros is None:
+                        zeros = torch.zeros_like(r["inc_smooth"])
+                    inc_c = zeros
+                self.applyIncrements(traj, True, r["inc_smooth"], inc_c, None, alpha, lr, lr_schedule_mode=3)
+            else:
+                self.applyIncrements(traj, False, inc_pose=r["inc_pose"], lr_schedule_mode=3)
+    return best_traj, best_cost
+
+
+TormBatch.localOptimizeTSGD = _local_optimize_tsgd

@@ -251,3 +251,37 @@ def test_tsgd_iterations_stay_on_device(cuda_device):
     # cost to ~0.84 of its start after 10 iterations (the CPU oracle gives the same curve)
     assert torch.isfinite(tt).all() and bool((c1 < c0).all()) and 0.7 < (c1 / c0).mean().item() < 0.92
     gsc.close()
+
+
+def test_lockstep_tsgd_on_reference_problem(cuda_device, init_traj):
+    """The reference's own `zig` problem: target path + Linear-initialiser trajectory (fixtures).  Lock-step TSGD on
+    the device follows the same trajectory as a CPU loop built from the oracle's cost / update pieces, and takes
+    the weighted pose cost from 0.3735 (SURVEY anchor) to below 1e-4."""
+    import torch
+    from oracle import oracle as O
+    from rlitg_b200 import torm as TM
+    path = init_traj["zig_path"]; T = path.shape[0]
+    start = np.stack([init_traj["zig_torm_jli_test"], init_traj["zig_pirl_bc_test"]])
+    pr = TM.TormParameters(min_clearence_=0.001)
+    tb = TM.TormBatch(path, pr, None, cuda_device, torch.float64)
+    tt = torch.tensor(start, dtype=torch.float64, device=cuda_device)
+    c0 = tb.getWeightedPoseCost(tt).cpu().numpy().copy()
+    assert abs(c0[0] - 0.373526) < 2e-6
+    iters = 12
+    best_traj, best_cost = tb.localOptimizeTSGD(tt, iters)
+    op = O.torm_params(T, dt=0.1, clearance=0.001)
+    Ab, _, Ainv = O.smooth_setup(T, 0.1, (1.0, 0.0, 0.0), 0.0, want_inverse=True)
+    tr = start.copy()
+    for it in range(iters):
+        r = O.torm_cost_grad(tr, path, None, op, Ab, O.STAGE_SMOOTH)
+        tr = O.torm_update(tr, Ainv, 0, 3, r["inc_smooth"], np.zeros_like(r["inc_smooth"]), None, 0.5, 0.01)
+        r = O.torm_cost_grad(tr, path, None, op, None, O.STAGE_POSE_GRAD)
+        tr = O.torm_update(tr, Ainv, 1, 3, None, None, r["inc_pose"], 0.5, 0.01)
+    assert np.abs(tt.cpu().numpy() - tr).max() < 1e-7
+    ev = O.traj_eval(tr, path, op)
+    assert (ev[:, 0] + 0.17 * ev[:, 1] < 0.06).all()
+    # float32 production build reaches the same basin
+    tb32 = TM.TormBatch(path, pr, None, cuda_device, torch.float32)
+    t32 = torch.tensor(start, dtype=torch.float32, device=cuda_device)
+    bt, bc = tb32.localOptimizeTSGD(t32, 25)
+    assert (tb32.getWeightedPoseCost(t32) < 1e-3).all() and torch.isfinite(bc).any()
