@@ -102,6 +102,11 @@ def run(dev, rank, world, max_over_ranks, barrier, steps=30, warmup=5):
                    "sample": "%d x %d trajectories x %d waypoints, all stages, FP64 oracle (OpenMP), %.1f s" % (reps, n_s, T - 1, dtc)}
         except Exception as e:  # noqa: BLE001
             cpu = {"error": str(e)}
+    # per-shard statistics over NCCL (the only cross-rank traffic of the path): off the timed region
+    from rlitg_b200 import dist as D
+    rcost = tb.cost_grad(traj, full)["costs"]
+    st = D.gather_stats(D.local_stats(cost=rcost[:, 6], offset=rank * N))
+    stats = {k: st[k] for k in ("count", "mean_cost", "min_cost", "argmin", "argmin_rank")}
     flop_wp = 2060.0 + 430.0 * A  # SURVEY 8d per-waypoint figure
     wps = world * N * (T - 1)
     tf = flop_wp * N * (T - 1) / (ms_full * 1e-3) / 1e12
@@ -115,7 +120,7 @@ def run(dev, rank, world, max_over_ranks, barrier, steps=30, warmup=5):
         "roofline": {"bound": "fp32_fma", "achieved": tf, "peak": fma_peak, "unit": "TFLOP/s",
                      "frac": (tf / fma_peak) if fma_peak else None, "flop_per_waypoint": flop_wp,
                      "peak_source": "measured on this GPU by rlitg_fma_probe (FFMA chains, 16-way ILP)"},
-        "target_ms": 1.0, "cpu_baseline": cpu}
+        "target_ms": 1.0, "cpu_baseline": cpu, "shard_statistics": stats}
 
     # ---------------------------------------------------------------- PIRL env step
     for B in (16384, 65536):
