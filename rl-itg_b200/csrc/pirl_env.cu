@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(kEnvTile, sizeof(T) == 4 ? 4 : 1) pirl_env_ker
         for (int i = 0; i < cfg.n_future; i++) {
             int t = ts + (i + 1);
             if (t > mts) t = mts;
+            t = min(max(t, 0), Tmax - 1);  // memory-safety guard: a caller stepping a finished episode stays in its path
             T t7[7];
 #pragma unroll
             for (int k = 0; k < 7; k++) t7[k] = tg[t * 7 + k];
@@ -232,10 +233,12 @@ __global__ void __launch_bounds__(kEnvTile, sizeof(T) == 4 ? 4 : 1) pirl_env_ker
         for (int k = 0; k < cfg.z_dim; k++) row[fo + k] = latent[b * cfg.z_dim + k];
 
         if constexpr (kStep) {
-            // ---- _compute_task_reward :495-513 (target index = timestep)
+            // ---- _compute_task_reward :495-513 (target index = timestep; clamped into the path as a memory-safety
+            // guard -- the reference raises IndexError when a finished episode is stepped)
+            const int tsc = min(max(ts, 0), Tmax - 1);
             T tp[7];
 #pragma unroll
-            for (int k = 0; k < 7; k++) tp[k] = tg[ts * 7 + k];
+            for (int k = 0; k < 7; k++) tp[k] = tg[tsc * 7 + k];
             const T dx = tp[0] - ee.p.x, dy = tp[1] - ee.p.y, dz = tp[2] - ee.p.z;
             const T d_err = sqrt_t(dx * dx + dy * dy + dz * dz);
             T ex, ey, ez, ew;
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(kEnvTile, sizeof(T) == 4 ? 4 : 1) pirl_env_ker
             // ---- imitation :515-526 and null-space imitation :528-539
             T imitate_rwd = T(0), imitate_err = T(0), null_rwd = T(0), null_obj = T(0);
             if (demos != nullptr) {
-                const T* dm = demos + ((int64_t)b * Tmax + ts) * 7;
+                const T* dm = demos + ((int64_t)b * Tmax + tsc) * 7;
                 T ce[7];
                 T l1 = T(0);
 #pragma unroll

@@ -222,3 +222,21 @@ def test_step_cuda_graph_replay(cuda_device):
         o2, r2, d2, _ = envs[1].step(a)
         assert torch.equal(out[0], o2) and torch.equal(out[1], r2) and torch.equal(out[2], d2)
         assert torch.equal(envs[0].timestep, envs[1].timestep)
+
+
+def test_stepping_finished_episodes_stays_in_bounds(cuda_device):
+    """The reference raises IndexError when a finished episode is stepped; the kernel clamps the path index instead
+    (memory-safety guard).  Run far past the end of every path on a batch whose last path ends the buffer."""
+    import torch
+    from rlitg_b200 import pirl_env as P
+    B, T = 4096, 14
+    c = build_case(B, T, 19, False, cuda_device)
+    env = P.PirlVecEnv(B, device=cuda_device, dtype=torch.float32)
+    env.set_problems(c["targets"], c["demos"], np.full(B, T - 1, dtype=np.int32))
+    env.reset()
+    act = torch.zeros(B, 7, device=cuda_device)
+    for _ in range(5 * T):
+        obs, rew, done, info = env.step(act)
+    torch.cuda.synchronize()
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+    assert int(env.timestep.min().item()) == 5 * T
