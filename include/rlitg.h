@@ -144,6 +144,10 @@ RLITG_API int rlitg_nullspace_norm(const void* err, const void* q, int64_t B, in
 RLITG_API int rlitg_pinv_step(const void* q, const void* twist, int64_t B, int D, int dtype, double eps, void* dq,
                               void* stream);
 
+/* TormOptimizer::checkSingularity (torm/src/torm_optimizer.cpp:748-765): out[b] = |sqrt(det(J J^T))| at q[b]
+ * (compare with singularity_lower_bound_).  q [B,D], out [B]. */
+RLITG_API int rlitg_manipulability(const void* q, int64_t B, int D, int dtype, void* out, void* stream);
+
 /* KDL::diff(FK(q[b]), target[b]) as used at torm/src/torm_optimizer.cpp:1413,1440 and
  * torm/src/utils/traj_evaluator.cpp:72,79: twist [B,6] = (p_t - p, R * rotvec(R^T R_t)).  target [B,7]. */
 RLITG_API int rlitg_pose_diff(const void* q, const void* target, int64_t B, int D, int dtype, void* twist,
@@ -248,6 +252,14 @@ RLITG_API int rlitg_torm_cost_grad(const void* traj, const void* targets, int64_
                                    const RlitgScene* scene, const RlitgSmooth* smooth, const RlitgTormParams* p,
                                    int stage_mask, const int32_t* stochastic_idx, void* inc_smooth, void* inc_coll,
                                    void* inc_pose, void* costs, float* active, void* stream);
+
+/* Host-buffer form of rlitg_torm_cost_grad: traj, targets, stochastic_idx and every output are HOST pointers (the
+ * reference's TormOptimizer holds Eigen matrices on the host); copies in / out through an internal device workspace
+ * and returns when the results are in the caller's buffers.  scene / smooth are the same device-resident handles. */
+RLITG_API int rlitg_torm_cost_grad_host(const void* traj, const void* targets, int64_t N, int dtype,
+                                        const RlitgScene* scene, const RlitgSmooth* smooth, const RlitgTormParams* p,
+                                        int stage_mask, const int32_t* stochastic_idx, void* inc_smooth,
+                                        void* inc_coll, void* inc_pose, void* costs);
 
 /* Update step of the two-stage gradient descent, for N trajectories in place:
  * calculateFeasibleIncrements (torm/src/torm_optimizer.cpp:1555-1609) or calculateEndPoseIncrements (:1475-1482),

@@ -64,6 +64,26 @@ __global__ void __launch_bounds__(128) nullspace_kernel(const T* __restrict__ er
     out[b] = nullspace_norm<T, 7>(J, e);
 }
 
+// sqrt(det(J J^T)) -- the "yosh" manipulability measure of TormOptimizer::checkSingularity
+// (torm/src/torm_optimizer.cpp:748-765).  With J^T = Q R (modified Gram-Schmidt), det(J J^T) = prod(R_kk)^2.
+template <typename T, int D>
+__global__ void __launch_bounds__(128) manipulability_kernel(const T* __restrict__ q, int64_t B, T* __restrict__ out) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    T qv[D];
+#pragma unroll
+    for (int j = 0; j < D; j++) qv[j] = q[b * D + j];
+    FkJac<T, D> fj;
+    walk_chain<T, D>(qv, fj);
+    T J[6 * D], R[36];
+    fill_jac<T, D>(fj, J);
+    mgs_rows<T, D>(J, R);
+    T prod = T(1);
+#pragma unroll
+    for (int k = 0; k < 6; k++) prod *= R[k * 6 + k];
+    out[b] = abs_t(prod);
+}
+
 static inline unsigned nblk(int64_t n) { return (unsigned)((n + 127) / 128); }
 
 template <typename T>
@@ -101,6 +121,22 @@ RLITG_API int rlitg_nullspace_norm(const void* err, const void* q, int64_t B, in
     if (dtype == RLITG_F32) nullspace_kernel<float><<<nblk(B), 128, 0, st>>>((const float*)err, (const float*)q, B, (float*)out);
     else nullspace_kernel<double><<<nblk(B), 128, 0, st>>>((const double*)err, (const double*)q, B, (double*)out);
     return check_launch("nullspace_kernel");
+}
+
+RLITG_API int rlitg_manipulability(const void* q, int64_t B, int D, int dtype, void* out, void* stream) {
+    int rc = check_args(B, D, dtype);
+    if (rc) return rc;
+    if (B == 0) return RLITG_OK;
+    if (!q || !out) return set_error(RLITG_ERR_NULL, "q / out is NULL");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == RLITG_F32) {
+        if (D == 7) manipulability_kernel<float, 7><<<nblk(B), 128, 0, st>>>((const float*)q, B, (float*)out);
+        else manipulability_kernel<float, 8><<<nblk(B), 128, 0, st>>>((const float*)q, B, (float*)out);
+    } else {
+        if (D == 7) manipulability_kernel<double, 7><<<nblk(B), 128, 0, st>>>((const double*)q, B, (double*)out);
+        else manipulability_kernel<double, 8><<<nblk(B), 128, 0, st>>>((const double*)q, B, (double*)out);
+    }
+    return check_launch("manipulability_kernel");
 }
 
 RLITG_API int rlitg_pinv_step(const void* q, const void* twist, int64_t B, int D, int dtype, double eps, void* dq,

@@ -11,6 +11,8 @@
 // bandwidth 6) instead of the reference's dense (T-1)^2 product: O(13 T) per joint, in FP64 (7 serial chains per
 // trajectory; the kernel is latency bound and tiny next to kernel 3).  The corrective columns of handleJointLimits
 // are rows of the dense scaled inverse kept on the device (symmetric, so a column read is contiguous).
+#include <mutex>
+
 #include "rlitg_internal.h"
 
 namespace rlitg {
@@ -242,4 +244,64 @@ extern "C" RLITG_API int rlitg_greedy_select(const void* costs, int C, int Tseg,
     else if (dtype == RLITG_F64) greedy_select_kernel<double><<<1, 32, 0, st>>>((const double*)costs, C, Tseg, rot_scale, pose_w, col_w, best_idx, (double*)best_cost);
     else return set_error(RLITG_ERR_DTYPE, "dtype must be RLITG_F32 or RLITG_F64");
     return check_launch("greedy_select_kernel");
+}
+
+// ---- host-buffer form of rlitg_torm_cost_grad (the reference's callers hold Eigen matrices on the host) --------
+namespace rlitg {
+struct HostWs {
+    std::mutex mu;
+    cudaStream_t st = nullptr;
+    void* buf = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (!st && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return set_cuda_error("cudaStreamCreate");
+        if (cap < bytes) {
+            if (buf) cudaFree(buf);
+            buf = nullptr; cap = 0;
+            if (cudaMalloc(&buf, bytes) != cudaSuccess) return set_cuda_error("cudaMalloc(torm host workspace)");
+            cap = bytes;
+        }
+        return RLITG_OK;
+    }
+};
+static HostWs g_torm_ws;
+}  // namespace rlitg
+
+extern "C" RLITG_API int rlitg_torm_cost_grad_host(const void* traj, const void* targets, int64_t N, int dtype,
+                                                   const RlitgScene* scene, const RlitgSmooth* smooth,
+                                                   const RlitgTormParams* p, int stage_mask,
+                                                   const int32_t* stochastic_idx, void* inc_smooth, void* inc_coll,
+                                                   void* inc_pose, void* costs) {
+    if (!p) return set_error(RLITG_ERR_NULL, "params is NULL");
+    if (dtype != RLITG_F32 && dtype != RLITG_F64) return set_error(RLITG_ERR_DTYPE, "dtype must be RLITG_F32 or RLITG_F64");
+    if (N < 0) return set_error(RLITG_ERR_SHAPE, "N out of range");
+    if (N == 0) return RLITG_OK;
+    if (!traj || !targets || !costs) return set_error(RLITG_ERR_NULL, "traj / targets / costs is NULL");
+    const size_t es = dtype == RLITG_F32 ? 4 : 8;
+    const size_t T = (size_t)p->T, F = T - 1;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_traj = al(es * N * T * 7), b_tg = al(es * T * 7), b_inc = al(es * N * F * 7), b_cost = al(es * N * RLITG_TORM_NCOST),
+                 b_st = al(4 * (size_t)N);
+    std::lock_guard<std::mutex> lk(g_torm_ws.mu);
+    int rc = g_torm_ws.ensure(b_traj + b_tg + 3 * b_inc + b_cost + b_st);
+    if (rc) return rc;
+    char* base = static_cast<char*>(g_torm_ws.buf);
+    char *d_traj = base, *d_tg = d_traj + b_traj, *d_is = d_tg + b_tg, *d_ic = d_is + b_inc, *d_ip = d_ic + b_inc,
+         *d_cost = d_ip + b_inc, *d_st = d_cost + b_cost;
+    cudaStream_t st = g_torm_ws.st;
+    if (cudaMemcpyAsync(d_traj, traj, es * N * T * 7, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(d_tg, targets, es * T * 7, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        (stochastic_idx && cudaMemcpyAsync(d_st, stochastic_idx, 4 * (size_t)N, cudaMemcpyHostToDevice, st) != cudaSuccess))
+        return set_cuda_error("H2D trajectories");
+    rc = rlitg_torm_cost_grad(d_traj, d_tg, N, dtype, scene, smooth, p, stage_mask,
+                              stochastic_idx ? reinterpret_cast<const int32_t*>(d_st) : nullptr,
+                              inc_smooth ? d_is : nullptr, inc_coll ? d_ic : nullptr, inc_pose ? d_ip : nullptr, d_cost,
+                              nullptr, st);
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpyAsync(costs, d_cost, es * N * RLITG_TORM_NCOST, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && inc_smooth && (stage_mask & RLITG_STAGE_SMOOTH)) e = cudaMemcpyAsync(inc_smooth, d_is, es * N * F * 7, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && inc_coll && (stage_mask & RLITG_STAGE_COLL)) e = cudaMemcpyAsync(inc_coll, d_ic, es * N * F * 7, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && inc_pose && (stage_mask & RLITG_STAGE_POSE_GRAD)) e = cudaMemcpyAsync(inc_pose, d_ip, es * N * F * 7, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return set_cuda_error("D2H increments");
+    return RLITG_OK;
 }

@@ -40,6 +40,7 @@ lib.rlitg_pirl_obs.argtypes = [C.POINTER(RlitgPirlCfg), _i64, _i, _vp, _vp, _vp,
 lib.rlitg_nullspace_norm.argtypes = [_vp, _vp, _i64, _i, _vp, _vp]
 lib.rlitg_pinv_step.argtypes = [_vp, _vp, _i64, _i, _i, C.c_double, _vp, _vp]
 lib.rlitg_pose_diff.argtypes = [_vp, _vp, _i64, _i, _i, _vp, _vp]
+lib.rlitg_manipulability.argtypes = [_vp, _i64, _i, _i, _vp, _vp]
 
 OBS_TYPES = {"onlyConf": 0, "Conf+LinkPoses": 1, "Conf+EE": 2, "onlyLinkPoses": 3}
 # (task, imitate, null-space) flags and (task, dist, rot, imit) success rewards: PirlEnv.py:130-161
@@ -96,6 +97,16 @@ def pinv_step(q, twist, eps=1e-5):
         check(lib.rlitg_pinv_step(q.data_ptr(), twist.data_ptr(), q.shape[0], q.shape[1], _code(q), float(eps),
                                   dq.data_ptr(), _stream()))
     return dq
+
+
+def manipulability(q):
+    """sqrt(det(J J^T)) per configuration: the measure TormOptimizer::checkSingularity compares with
+    singularity_lower_bound_ (torm/src/torm_optimizer.cpp:748-765)."""
+    q = q.contiguous()
+    out = torch.empty(q.shape[0], device=q.device, dtype=q.dtype)
+    with _lib.on_device(q.device):
+        check(lib.rlitg_manipulability(q.data_ptr(), q.shape[0], q.shape[1], _code(q), out.data_ptr(), _stream()))
+    return out
 
 
 def pose_diff(q, target):

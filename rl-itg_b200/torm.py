@@ -317,3 +317,33 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
 
 
 TormBatch.localOptimizeTSGD = _local_optimize_tsgd
+
+
+lib.rlitg_torm_cost_grad_host.argtypes = [_vp, _vp, C.c_int64, C.c_int, _vp, _vp, C.POINTER(RlitgTormParams), C.c_int, _vp,
+                                          _vp, _vp, _vp, _vp]
+
+
+def _cost_grad_host(self, traj, stage_mask, stochastic_idx=None):
+    """rlitg_torm_cost_grad_host: `traj` is a HOST numpy array [N,T,7] (float32 / float64 matching the batch dtype);
+    results come back as numpy arrays.  The end-to-end form for callers that keep trajectories on the host."""
+    npdt = np.float32 if self.dtype == torch.float32 else np.float64
+    traj = np.ascontiguousarray(traj, dtype=npdt)
+    N, T, _ = traj.shape
+    F = T - 1
+    targets = self.endPoses_desired_.cpu().numpy().astype(npdt)
+    out = {k: (np.empty((N, F, 7), dtype=npdt) if stage_mask & bit else None)
+           for k, bit in (("inc_smooth", STAGE_SMOOTH), ("inc_coll", STAGE_COLL), ("inc_pose", STAGE_POSE_GRAD))}
+    costs = np.empty((N, NCOST), dtype=npdt)
+    st = None if stochastic_idx is None else np.ascontiguousarray(stochastic_idx, dtype=np.int32)
+    p = lambda a: None if a is None else a.ctypes.data
+    with _lib.on_device(self.device):
+        check(lib.rlitg_torm_cost_grad_host(traj.ctypes.data, targets.ctypes.data, N,
+                                            _lib.F32 if npdt == np.float32 else _lib.F64,
+                                            None if self.scene is None else self.scene.handle, self.joint_costs_.handle,
+                                            C.byref(self._cp), int(stage_mask), p(st), p(out["inc_smooth"]),
+                                            p(out["inc_coll"]), p(out["inc_pose"]), costs.ctypes.data))
+    out["costs"] = costs
+    return out
+
+
+TormBatch.cost_grad_host = _cost_grad_host

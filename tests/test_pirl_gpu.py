@@ -240,3 +240,18 @@ def test_stepping_finished_episodes_stays_in_bounds(cuda_device):
     torch.cuda.synchronize()
     assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
     assert int(env.timestep.min().item()) == 5 * T
+
+
+@pytest.mark.parametrize("D", [7, 8])
+def test_manipulability_parity(cuda_device, D):
+    """checkSingularity's sqrt(det(J J^T)) (torm/src/torm_optimizer.cpp:758)"""
+    import torch
+    from oracle import oracle as O
+    from rlitg_b200 import pirl_env as P, synth
+    q = synth.random_configs(4000, seed=31, D=D)
+    q[0, -7:] = 0.0  # a singular configuration
+    want = O.manipulability(q)
+    for dtype, rel in ((torch.float64, 1e-9), (torch.float32, 2e-4)):
+        got = P.manipulability(torch.tensor(q, dtype=dtype, device=cuda_device)).double().cpu().numpy()
+        assert np.abs(got - want).max() <= rel * want.max() + (1e-12 if dtype == torch.float64 else 1e-6)
+    assert want[0] < 1e-6

@@ -285,3 +285,19 @@ def test_lockstep_tsgd_on_reference_problem(cuda_device, init_traj):
     t32 = torch.tensor(start, dtype=torch.float32, device=cuda_device)
     bt, bc = tb32.localOptimizeTSGD(t32, 25)
     assert (tb32.getWeightedPoseCost(t32) < 1e-3).all() and torch.isfinite(bc).any()
+
+
+def test_host_buffer_entry_point(cuda_device):
+    """rlitg_torm_cost_grad_host returns exactly what the device-pointer entry point computes."""
+    import torch
+    from rlitg_b200 import torm as TM
+    N, T = 9, 50
+    traj, targets, osc, gsc = make_problem(N, T, 31, cuda_device)
+    tb = TM.TormBatch(targets, TM.TormParameters(min_clearence_=0.3), gsc, cuda_device, torch.float32)
+    mask = TM.STAGE_POSE_GRAD | TM.STAGE_SMOOTH | TM.STAGE_COLL | TM.STAGE_EVAL
+    st = np.arange(N, dtype=np.int32) % (T - 1)
+    dev = tb.cost_grad(torch.tensor(traj, dtype=torch.float32, device=cuda_device), mask, st)
+    host = tb.cost_grad_host(traj.astype(np.float32), mask, st)
+    for k in ("costs", "inc_smooth", "inc_coll", "inc_pose"):
+        assert np.array_equal(host[k], dev[k].cpu().numpy()), k
+    gsc.close()
