@@ -651,21 +651,26 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
     const bool run_pose = (stage_mask & (RLITG_STAGE_POSE | RLITG_STAGE_POSE_GRAD | RLITG_STAGE_EVAL)) != 0;
     const bool run_coll = (stage_mask & (RLITG_STAGE_COLL | RLITG_STAGE_SMOOTH)) != 0;
     if (!run_pose && !run_coll) return set_error(RLITG_ERR_ARG, "stage_mask selects no stage");
-    if (run_pose) {
-        const size_t smem = sizeof(T) * ((size_t)(CH + 12) * 7 + (size_t)(CH + 3) * 7 + 8 * kNRedPose);
-        // register budget of the pose kernel: 2 CTAs/SM (128 regs) or 3 (96 regs at 224 threads); RLITG_TORM_POSE_OCC
-        static const int occ = [] { const char* e = getenv("RLITG_TORM_POSE_OCC"); return e ? atoi(e) : 2; }();
-        auto kern = (sizeof(T) == 4 && occ == 3) ? torm_pose_eval_kernel<T, (sizeof(T) == 4 ? 96 : 255)>
-                                                 : torm_pose_eval_kernel<T, (sizeof(T) == 4 ? 128 : 255)>;
-        static size_t attr_smem = 0;
-        if (smem > attr_smem) {
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-                return set_cuda_error("cudaFuncSetAttribute(torm_pose_eval_kernel)");
-            attr_smem = smem;
+    // When both kernels run they are forked onto two streams (joined again before returning to the caller's
+    // stream order): the pose kernel's CTAs fill the SMs that the collision kernel's last, partial wave leaves idle.
+    struct Fork { cudaStream_t side = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+    static Fork forks[64];
+    static const int concurrent = [] { const char* e = getenv("RLITG_TORM_CONCURRENT"); return e ? atoi(e) : 1; }();
+    cudaStream_t st_pose = st;
+    Fork* fk = nullptr;
+    if (run_pose && run_coll && concurrent) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        fk = &forks[dev & 63];
+        if (!fk->side) {
+            if (cudaStreamCreateWithFlags(&fk->side, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&fk->fork, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&fk->join, cudaEventDisableTiming) != cudaSuccess)
+                return set_cuda_error("torm fork stream / events");
         }
-        kern<<<(unsigned)N, CH, smem, st>>>(P, traj, targets, stage_mask, run_coll ? 0 : 1, inc_pose, costs);
-        int rc = check_launch("torm_pose_eval_kernel");
-        if (rc) return rc;
+        if (cudaEventRecord(fk->fork, st) != cudaSuccess || cudaStreamWaitEvent(fk->side, fk->fork, 0) != cudaSuccess)
+            return set_cuda_error("torm fork");
+        st_pose = fk->side;
     }
     if (run_coll) {
         SceneDev sd{};
@@ -691,7 +696,28 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
             band = reinterpret_cast<const T*>(sizeof(T) == 4 ? (const void*)smooth->d_band32 : (const void*)smooth->d_band64);
         kern<<<(unsigned)N, CH, smem, st>>>(P, traj, sd, S, band, stage_mask, run_pose ? 0 : 1, stoch, inc_smooth, inc_coll,
                                             costs, active);
-        return check_launch("torm_coll_smooth_kernel");
+        int rc = check_launch("torm_coll_smooth_kernel");
+        if (rc) return rc;
+    }
+    if (run_pose) {
+        const size_t smem = sizeof(T) * ((size_t)(CH + 12) * 7 + (size_t)(CH + 3) * 7 + 8 * kNRedPose);
+        // register budget of the pose kernel: 2 CTAs/SM (128 regs) or 3 (96 regs at 224 threads); RLITG_TORM_POSE_OCC
+        static const int occ = [] { const char* e = getenv("RLITG_TORM_POSE_OCC"); return e ? atoi(e) : 2; }();
+        auto kern = (sizeof(T) == 4 && occ == 3) ? torm_pose_eval_kernel<T, (sizeof(T) == 4 ? 96 : 255)>
+                                                 : torm_pose_eval_kernel<T, (sizeof(T) == 4 ? 128 : 255)>;
+        static size_t attr_smem = 0;
+        if (smem > attr_smem) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                return set_cuda_error("cudaFuncSetAttribute(torm_pose_eval_kernel)");
+            attr_smem = smem;
+        }
+        kern<<<(unsigned)N, CH, smem, st_pose>>>(P, traj, targets, stage_mask, run_coll ? 0 : 1, inc_pose, costs);
+        int rc = check_launch("torm_pose_eval_kernel");
+        if (rc) return rc;
+    }
+    if (fk) {
+        if (cudaEventRecord(fk->join, fk->side) != cudaSuccess || cudaStreamWaitEvent(st, fk->join, 0) != cudaSuccess)
+            return set_cuda_error("torm join");
     }
     return RLITG_OK;
 }
