@@ -301,3 +301,38 @@ def test_host_buffer_entry_point(cuda_device):
     for k in ("costs", "inc_smooth", "inc_coll", "inc_pose"):
         assert np.array_equal(host[k], dev[k].cpu().numpy()), k
     gsc.close()
+
+
+def test_tsgd_iteration_cuda_graph(cuda_device):
+    """cost + update of one feasible / end-pose iteration captured in a CUDA graph (the two TORM kernels fork onto a
+    side stream inside the call: legal under capture) replays to the same trajectory as eager execution."""
+    import torch
+    from rlitg_b200 import torm as TM
+    N, T = 32, 60
+    traj, targets, osc, gsc = make_problem(N, T, 41, cuda_device)
+    tb = TM.TormBatch(targets, TM.TormParameters(min_clearence_=0.3), gsc, cuda_device, torch.float32)
+    feas = TM.STAGE_POSE | TM.STAGE_SMOOTH | TM.STAGE_COLL | TM.STAGE_EVAL
+    pose = TM.STAGE_POSE_GRAD | TM.STAGE_EVAL
+    alpha = torch.full((N,), 0.5, device=cuda_device); lr = torch.full((N,), 0.01, device=cuda_device)
+
+    def iteration(t):
+        r = tb.cost_grad(t, feas)
+        tb.applyIncrements(t, True, r["inc_smooth"], r["inc_coll"], None, alpha, lr, lr_schedule_mode=3)
+        r = tb.cost_grad(t, pose)
+        tb.applyIncrements(t, False, inc_pose=r["inc_pose"], alpha=alpha, learning_rate=lr, lr_schedule_mode=3)
+
+    eager = torch.tensor(traj, dtype=torch.float32, device=cuda_device)
+    graphed = eager.clone()
+    warm = eager.clone()
+    iteration(warm)  # warm-up outside capture (kernel attributes, side stream, output buffers)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        iteration(graphed)
+    graphed.copy_(eager)
+    for _ in range(3):
+        iteration(eager)
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(eager, graphed)
+    gsc.close()
