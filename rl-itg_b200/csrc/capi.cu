@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -32,6 +33,34 @@ int check_launch(const char* kernel_name) {
     return RLITG_OK;
 }
 const char* last_error_cstr() { return g_err.c_str(); }
+
+int ensure_dynamic_smem(const void* func, size_t bytes, const char* name) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> granted;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return set_cuda_error("cudaGetDevice");
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& have = granted[std::make_pair(func, dev)];
+    if (bytes <= have) return RLITG_OK;
+    if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+        cudaError_t e = cudaGetLastError();
+        g_err = std::string("cudaFuncSetAttribute(") + name + "): " + cudaGetErrorString(e);
+        return RLITG_ERR_CUDA;
+    }
+    have = bytes;
+    return RLITG_OK;
+}
+
+int current_sm_count() {
+    static std::mutex mu;
+    static std::map<int, int> sms;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    int& n = sms[dev];
+    if (n == 0) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+}
 
 static int check_common(const void* q, int64_t B, int D, int dtype) {
     if (B < 0) return set_error(RLITG_ERR_SHAPE, "B must be >= 0");
@@ -68,12 +97,18 @@ struct HostPipe {
         return RLITG_OK;
     }
 };
-static HostPipe g_pipe;
+static HostPipe g_pipes[64];  // one workspace per device
+static HostPipe& host_pipe() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return g_pipes[dev & 63];
+}
 
 template <typename T>
 static int fk_jac_host_t(const T* q, int64_t B, int D, int flags, T* pos, T* rot, T* quat, T* J) {
     if (flags & (RLITG_Q_SOA | RLITG_OUT_SOA))
         return set_error(RLITG_ERR_ARG, "rlitg_fk_jac_host takes array-of-structs buffers ([B,D] in, [B,*] out)");
+    HostPipe& g_pipe = host_pipe();
     std::lock_guard<std::mutex> lk(g_pipe.mu);
     // chunk so that copies of one chunk overlap the kernel / copies of its neighbours
     const int64_t chunk = 1 << 17;
@@ -225,8 +260,8 @@ extern "C" RLITG_API int rlitg_write_probe(void* dst, const void* src, int64_t n
         return rlitg::set_error(RLITG_ERR_ARG, "bad write probe arguments");
     auto kern = rlitg::write_probe_kernel;
     const size_t smem = 2 * (size_t)tile_bytes;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return rlitg::set_cuda_error("cudaFuncSetAttribute(write_probe_kernel)");
+    int rc_attr = rlitg::ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "write_probe_kernel");
+    if (rc_attr) return rc_attr;
     kern<<<ctas, 128, smem, static_cast<cudaStream_t>(stream)>>>((char*)dst, (const float*)src, ntiles, tile_bytes,
                                                                  read_floats);
     return rlitg::check_launch("write_probe_kernel");

@@ -271,17 +271,10 @@ template <typename T, int D, bool QSOA, int NSTAGE>
 static int launch_fk_persist(const T* q, int64_t B, int64_t ntiles, T* pos, T* rot, T* quat, T* J, cudaStream_t st) {
     const size_t smem = sizeof(T) * NSTAGE * kTile * (6 * D + 9 + 4 + 3);
     auto kern = fk_jac_persist_kernel<T, D, QSOA, NSTAGE>;
-    static int ctas_per_sm = 0, num_sms = 0;
-    if (ctas_per_sm == 0) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return set_cuda_error("cudaFuncSetAttribute(fk_jac_persist_kernel)");
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kTile, smem) != cudaSuccess || ctas_per_sm < 1)
-            return set_cuda_error("cudaOccupancyMaxActiveBlocksPerMultiprocessor(fk_jac_persist_kernel)");
-    }
-    const int64_t grid = std::min<int64_t>(ntiles, (int64_t)num_sms * ctas_per_sm);
+    int rc0 = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "fk_jac_persist_kernel");
+    if (rc0) return rc0;
+    const int num_sms = current_sm_count();
+    const int64_t grid = ntiles;
     static const int dbg = [] { const char* e = getenv("RLITG_FK_DBG"); return e ? atoi(e) : 0; }();  // 1 = no stores
     // Two CTAs per SM measured best on B200 (1M configs: 45.9 us vs 48-49 us with 3-7 CTAs/SM; 8M: 6.14 TB/s):
     // the round-robin tile order keeps the set of tiles in flight -- the HBM write window -- narrow.
@@ -295,12 +288,8 @@ template <typename T, int D, bool QSOA, bool OSOA>
 static int launch_fk_jac_t(const T* q, int64_t B, T* pos, T* rot, T* quat, T* J, cudaStream_t st) {
     const size_t smem = sizeof(T) * kTile * (6 * D + 9 + 4 + 3 + D);
     auto kern = fk_jac_kernel<T, D, QSOA, OSOA>;
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return set_cuda_error("cudaFuncSetAttribute(fk_jac_kernel)");
-        attr_set = true;
-    }
+    int rc0 = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "fk_jac_kernel");
+    if (rc0) return rc0;
     // TMA bulk stores need 16-byte aligned global addresses; tile offsets keep the alignment of the base
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     const int allow_bulk = al16(pos) && al16(rot) && al16(quat) && al16(J);
@@ -344,12 +333,8 @@ template <typename T, int D, bool QSOA>
 static int launch_allfk_t(const T* q, int64_t B, T* out, cudaStream_t st) {
     const size_t smem = sizeof(T) * kTile * ((D + 1) * 7 + 1 + D);
     auto kern = allfk_kernel<T, D, QSOA>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return set_cuda_error("cudaFuncSetAttribute(allfk_kernel)");
-        attr_set = true;
-    }
+    int rc0 = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "allfk_kernel");
+    if (rc0) return rc0;
     const int64_t grid = (B + kTile - 1) / kTile;
     kern<<<(unsigned)grid, kTile, smem, st>>>(q, B, out);
     return check_launch("allfk_kernel");

@@ -347,11 +347,9 @@ static int launch_pirl(const RlitgPirlCfg* cfg, int64_t B, T* q, const float* ac
     const size_t smem = sizeof(T) * kEnvTile * (size_t)(c.O | 1);
     if (smem > 200 * 1024) return set_error(RLITG_ERR_SHAPE, "observation too long for the shared-memory tile");
     auto kern = pirl_env_kernel<T, kStep>;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return set_cuda_error("cudaFuncSetAttribute(pirl_env_kernel)");
-        attr_smem = smem;
+    {
+        int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "pirl_env_kernel");
+        if (rc_attr) return rc_attr;
     }
     SceneDev sd{};
     int has_scene = 0;

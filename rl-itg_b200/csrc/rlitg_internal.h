@@ -14,6 +14,10 @@ int set_error(int code, const char* msg);
 int set_cuda_error(const char* where);            // captures cudaGetLastError()
 int check_launch(const char* kernel_name);        // counts the launch, reports launch errors
 const char* last_error_cstr();
+// Thread-safe and per device: makes sure kernel `func` may be launched with `bytes` of dynamic shared memory on
+// the current device (cudaFuncSetAttribute is per device and must not race).  Returns RLITG_OK or an error code.
+int ensure_dynamic_smem(const void* func, size_t bytes, const char* name);
+int current_sm_count();
 
 template <typename T>
 int launch_fk_jac(const T* q, int64_t B, int D, int flags, T* pos, T* rot, T* quat, T* J, cudaStream_t st);

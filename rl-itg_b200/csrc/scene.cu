@@ -309,18 +309,9 @@ int launch_sphere_collide(const T* q, int64_t B, const Scene* s, const double* b
     const size_t dil_bytes = sizeof(uint32_t) * (size_t)s->wx * s->ny * s->nz * s->ncls;
     if (s->dil && dil_bytes <= 200 * 1024 && B >= 4096) {
         auto kern = sphere_collide_smem_kernel<T>;
-        static size_t attr_smem = 0;
-        static int num_sms = 0;
-        if (dil_bytes > attr_smem) {
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dil_bytes) != cudaSuccess)
-                return set_cuda_error("cudaFuncSetAttribute(sphere_collide_smem_kernel)");
-            attr_smem = dil_bytes;
-        }
-        if (num_sms == 0) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        }
+        int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), dil_bytes, "sphere_collide_smem_kernel");
+        if (rc_attr) return rc_attr;
+        const int num_sms = current_sm_count();
         const unsigned grid = (unsigned)std::min<int64_t>(num_sms, (B + 255) / 256);
         kern<<<grid, 256, dil_bytes, st>>>(q, B, s->dev(), base_off[0], base_off[1], base_off[2], out);
         return check_launch("sphere_collide_smem_kernel");

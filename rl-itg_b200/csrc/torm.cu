@@ -685,11 +685,9 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
         static const int cocc = [] { const char* e = getenv("RLITG_TORM_COLL_OCC"); return e ? atoi(e) : 2; }();
         auto kern = (sizeof(T) == 4 && cocc == 3) ? torm_coll_smooth_kernel<T, (sizeof(T) == 4 ? 96 : 255)>
                                                   : torm_coll_smooth_kernel<T, (sizeof(T) == 4 ? 128 : 255)>;
-        static size_t attr_smem = 0;
-        if (smem > attr_smem) {
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-                return set_cuda_error("cudaFuncSetAttribute(torm_coll_smooth_kernel)");
-            attr_smem = smem;
+        {
+            int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "torm_coll_smooth_kernel");
+            if (rc_attr) return rc_attr;
         }
         const T* band = nullptr;
         if (stage_mask & RLITG_STAGE_SMOOTH)
@@ -705,11 +703,9 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
         static const int occ = [] { const char* e = getenv("RLITG_TORM_POSE_OCC"); return e ? atoi(e) : 2; }();
         auto kern = (sizeof(T) == 4 && occ == 3) ? torm_pose_eval_kernel<T, (sizeof(T) == 4 ? 96 : 255)>
                                                  : torm_pose_eval_kernel<T, (sizeof(T) == 4 ? 128 : 255)>;
-        static size_t attr_smem = 0;
-        if (smem > attr_smem) {
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-                return set_cuda_error("cudaFuncSetAttribute(torm_pose_eval_kernel)");
-            attr_smem = smem;
+        {
+            int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "torm_pose_eval_kernel");
+            if (rc_attr) return rc_attr;
         }
         kern<<<(unsigned)N, CH, smem, st_pose>>>(P, traj, targets, stage_mask, run_coll ? 0 : 1, inc_pose, costs);
         int rc = check_launch("torm_pose_eval_kernel");

@@ -173,11 +173,9 @@ static int launch_update(const RlitgTormUpdate* u, const RlitgTormParams* p, con
     const size_t smem = sizeof(double) * 2 * (size_t)(p->T - 1) * 7;
     if (smem > 200 * 1024) return set_error(RLITG_ERR_SHAPE, "T too large for the update step's shared-memory tile");
     auto kern = torm_update_kernel<T>;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return set_cuda_error("cudaFuncSetAttribute(torm_update_kernel)");
-        attr_smem = smem;
+    {
+        int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "torm_update_kernel");
+        if (rc_attr) return rc_attr;
     }
     kern<<<(unsigned)N, kUpdThreads, smem, st>>>(P, traj, inc_smooth, inc_coll, inc_pose, alpha, lr, sm->d_chol, sm->d_inv64);
     return check_launch("torm_update_kernel");
@@ -264,7 +262,7 @@ struct HostWs {
         return RLITG_OK;
     }
 };
-static HostWs g_torm_ws;
+static HostWs g_torm_wss[64];  // one workspace per device
 }  // namespace rlitg
 
 extern "C" RLITG_API int rlitg_torm_cost_grad_host(const void* traj, const void* targets, int64_t N, int dtype,
@@ -282,6 +280,9 @@ extern "C" RLITG_API int rlitg_torm_cost_grad_host(const void* traj, const void*
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t b_traj = al(es * N * T * 7), b_tg = al(es * T * 7), b_inc = al(es * N * F * 7), b_cost = al(es * N * RLITG_TORM_NCOST),
                  b_st = al(4 * (size_t)N);
+    int ws_dev = 0;
+    cudaGetDevice(&ws_dev);
+    HostWs& g_torm_ws = g_torm_wss[ws_dev & 63];
     std::lock_guard<std::mutex> lk(g_torm_ws.mu);
     int rc = g_torm_ws.ensure(b_traj + b_tg + 3 * b_inc + b_cost + b_st);
     if (rc) return rc;

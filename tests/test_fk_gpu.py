@@ -135,3 +135,19 @@ def test_empty_batch(cuda_device):
     from rlitg_b200 import kinematics as K
     r = K.fk_jac(torch.empty(0, 7, device=cuda_device))
     assert r["pos"].shape == (0, 3) and r["jac"].shape == (0, 6, 7)
+
+
+def test_second_device_in_one_process():
+    """Kernel attributes and host workspaces are per device: the same process can drive two GPUs (skipped on 1 GPU)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from oracle import oracle as O
+    from rlitg_b200 import kinematics as K
+    q = random_configs(300000, 7, seed=2)
+    pos, R, J = O.fk_jac(q[:1000])
+    for dev in ("cuda:1", "cuda:0"):
+        r = K.fk_jac(torch.tensor(q, dtype=torch.float32, device=dev))
+        assert np.abs(r["jac"][:1000].cpu().numpy() - J).max() < 4e-6
+        a = K.allfk(torch.tensor(q[:5000], dtype=torch.float64, device=dev))
+        assert np.abs(a.cpu().numpy()[..., :3] - O.allfk(q[:5000])[..., :3]).max() < 1e-12
