@@ -155,8 +155,23 @@ __global__ void __launch_bounds__(kEnvTile, sizeof(T) == 4 ? 4 : 1) pirl_env_ker
         v.do_coll = false;
 
         bool collision_flag = false, joint_limit_flag = false;
+        // loads whose addresses are known once the timestep is: issued before the chain walk so that their latency
+        // overlaps the arithmetic instead of adding three dependent round trips at the end of the thread
+        T pf_tp[7], pf_dm[7];
+        int4 pf_cnt = make_int4(0, 0, 0, 0);
         if constexpr (kStep) {
             ts += 1;
+            {
+                const int tsp = min(max(ts, 0), Tmax - 1);
+#pragma unroll
+                for (int k = 0; k < 7; k++) pf_tp[k] = tg[tsp * 7 + k];
+                if (demos != nullptr) {
+                    const T* dmp = demos + ((int64_t)b * Tmax + tsp) * 7;
+#pragma unroll
+                    for (int k = 0; k < 7; k++) pf_dm[k] = dmp[k];
+                }
+                if (counters) pf_cnt = *reinterpret_cast<const int4*>(counters + b * 4);
+            }
             // _set_action :184-207
             T cl[7];
             bool no_out = true;
@@ -238,7 +253,8 @@ __global__ void __launch_bounds__(kEnvTile, sizeof(T) == 4 ? 4 : 1) pirl_env_ker
             const int tsc = min(max(ts, 0), Tmax - 1);
             T tp[7];
 #pragma unroll
-            for (int k = 0; k < 7; k++) tp[k] = tg[tsc * 7 + k];
+            for (int k = 0; k < 7; k++) tp[k] = pf_tp[k];
+            (void)tsc;
             const T dx = tp[0] - ee.p.x, dy = tp[1] - ee.p.y, dz = tp[2] - ee.p.z;
             const T d_err = sqrt_t(dx * dx + dy * dy + dz * dz);
             T ex, ey, ez, ew;
@@ -253,7 +269,7 @@ __global__ void __launch_bounds__(kEnvTile, sizeof(T) == 4 ? 4 : 1) pirl_env_ker
             // ---- imitation :515-526 and null-space imitation :528-539
             T imitate_rwd = T(0), imitate_err = T(0), null_rwd = T(0), null_obj = T(0);
             if (demos != nullptr) {
-                const T* dm = demos + ((int64_t)b * Tmax + tsc) * 7;
+                const T* dm = pf_dm;
                 T ce[7];
                 T l1 = T(0);
 #pragma unroll
@@ -302,7 +318,7 @@ __global__ void __launch_bounds__(kEnvTile, sizeof(T) == 4 ? 4 : 1) pirl_env_ker
             const uint32_t hi = (uint32_t)is_ds | ((uint32_t)is_rs << 8) | ((uint32_t)is_is << 16) | ((uint32_t)(is_ds * is_rs) << 24);
             *reinterpret_cast<uint2*>(flags + b * 8) = make_uint2(lo, hi);
             if (counters) {
-                int4 c = *reinterpret_cast<int4*>(counters + b * 4);
+                int4 c = pf_cnt;
                 c.x += is_ds * is_rs; c.y += is_ds; c.z += is_rs;
                 if (!cfg.refine_flag) c.w += is_is;
                 *reinterpret_cast<int4*>(counters + b * 4) = c;
