@@ -227,6 +227,60 @@ struct AllFkVisit {
     }
 };
 
+// persistent all-link FK (array-of-structs input or output, >= 1024 full tiles): same structure as
+// fk_jac_persist_kernel -- registers -> conflict-light 128-bit staging stores -> TMA bulk drain, q prefetched.
+template <typename T, int D>
+struct AllFkRegs {
+    T v[(D + 1) * 7];
+    template <int K>
+    RLITG_DEV void operator()(jidx<K>, const FrameC<T>& f) {
+        T x, y, z, w;
+        rot_to_quat_kdl(f.c0, f.c1, f.c2, x, y, z, w);
+        v[K * 7 + 0] = f.p.x; v[K * 7 + 1] = f.p.y; v[K * 7 + 2] = f.p.z;
+        v[K * 7 + 3] = x; v[K * 7 + 4] = y; v[K * 7 + 5] = z; v[K * 7 + 6] = w;
+    }
+};
+
+template <typename T, int D, bool QSOA, int NSTAGE>
+__global__ void __launch_bounds__(kTile) allfk_persist_kernel(const T* __restrict__ q, int64_t B, int64_t ntiles,
+                                                              T* __restrict__ out) {
+    constexpr int N = (D + 1) * 7;
+    constexpr int kStageElems = kTile * N;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* stage0 = reinterpret_cast<T*>(smem_raw);
+    const int tid = threadIdx.x;
+    int64_t tile = blockIdx.x;
+    T qn[D], qn2[D];
+    auto load_q = [&](int64_t t, T (&dst)[D]) {
+        const int64_t b = t * kTile + tid;
+#pragma unroll
+        for (int j = 0; j < D; j++) dst[j] = QSOA ? ld_stream(q + (int64_t)j * B + b) : ld_stream(q + b * D + j);
+    };
+    if (tile < ntiles) load_q(tile, qn);
+    if (tile + gridDim.x < ntiles) load_q(tile + gridDim.x, qn2);
+    for (int it = 0; tile < ntiles; tile += gridDim.x, it++) {
+        T qv[D];
+#pragma unroll
+        for (int j = 0; j < D; j++) { qv[j] = qn[j]; qn[j] = qn2[j]; }
+        if (tile + 2 * (int64_t)gridDim.x < ntiles) load_q(tile + 2 * (int64_t)gridDim.x, qn2);
+        AllFkRegs<T, D> r;
+        walk_chain<T, D>(qv, r);
+        T* sOut = stage0 + (it % NSTAGE) * kStageElems;
+        if (it >= NSTAGE) {
+            if (tid == 0) bulk_wait_read_pending<NSTAGE - 1>();
+            __syncthreads();
+        }
+        stage_row<T, N>(sOut, tid, r.v);
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            bulk_store(out + tile * kStageElems, sOut, (uint32_t)(kStageElems * sizeof(T)));
+            bulk_commit();
+        }
+    }
+    if (tid == 0) bulk_wait_read_all();
+}
+
 template <typename T, int D, bool QSOA>
 __global__ void __launch_bounds__(kTile) allfk_kernel(const T* __restrict__ q, int64_t B, T* __restrict__ out) {
     constexpr int N = (D + 1) * 7, NP = N + 1;  // padded row stride: odd -> conflict-free scalar stores
@@ -335,6 +389,27 @@ static int launch_allfk_t(const T* q, int64_t B, T* out, cudaStream_t st) {
     auto kern = allfk_kernel<T, D, QSOA>;
     int rc0 = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "allfk_kernel");
     if (rc0) return rc0;
+    const int64_t ntiles = B / kTile;
+    const bool al16 = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    if (al16 && ntiles >= 1024 && (!QSOA || ntiles * kTile == B)) {
+        constexpr int N = (D + 1) * 7;
+        // measured on B200 at 1M configs (RLITG_ALLFK_CTAS / RLITG_ALLFK_STAGES): 1 stage x 6 CTAs/SM 47.8 us, 1 x 4
+        // 51.8, 2 x 4 51.7, 1 x 2 82.5; the tile-per-CTA kernel 70 us.  Eight quaternion conversions per configuration
+        // make this kernel more arithmetic-heavy than fk_jac, so it wants more resident warps.
+        static const int amult = [] { const char* e = getenv("RLITG_ALLFK_CTAS"); return e ? atoi(e) : 6; }();
+        static const int astage = [] { const char* e = getenv("RLITG_ALLFK_STAGES"); return e ? atoi(e) : 1; }();
+        auto pk = astage == 1 ? allfk_persist_kernel<T, D, QSOA, 1> : allfk_persist_kernel<T, D, QSOA, 2>;
+        const size_t psmem = sizeof(T) * astage * kTile * N;
+        int rc1 = ensure_dynamic_smem(reinterpret_cast<const void*>(pk), psmem, "allfk_persist_kernel");
+        if (rc1) return rc1;
+        const int64_t g2 = std::min<int64_t>(ntiles, (int64_t)current_sm_count() * amult);
+        pk<<<(unsigned)g2, kTile, psmem, st>>>(q, B, ntiles, out);
+        rc1 = check_launch("allfk_persist_kernel");
+        const int64_t done = ntiles * kTile;
+        if (rc1 || done == B) return rc1;
+        kern<<<1, kTile, smem, st>>>(q + done * D, B - done, out + done * N);
+        return check_launch("allfk_kernel");
+    }
     const int64_t grid = (B + kTile - 1) / kTile;
     kern<<<(unsigned)grid, kTile, smem, st>>>(q, B, out);
     return check_launch("allfk_kernel");

@@ -47,7 +47,7 @@ def test_fk_jac_parity(cuda_device, D, dtype, rel, floor, q_soa, out_soa, B):
 
 @pytest.mark.parametrize("D", [7, 8])
 @pytest.mark.parametrize("dtype,tol", [("float32", 2e-6), ("float64", 1e-12)])
-@pytest.mark.parametrize("B", [1, 129, 2050])
+@pytest.mark.parametrize("B", [1, 129, 2050, 131072 + 77])  # the last one takes the persistent kernel + a tail
 def test_allfk_parity(cuda_device, D, dtype, tol, B):
     import torch
     from oracle import oracle as O
