@@ -120,7 +120,28 @@ def run(dev, rank, world, max_over_ranks, barrier, steps=30, warmup=5):
         "roofline": {"bound": "fp32_fma", "achieved": tf, "peak": fma_peak, "unit": "TFLOP/s",
                      "frac": (tf / fma_peak) if fma_peak else None, "flop_per_waypoint": flop_wp,
                      "peak_source": "measured on this GPU by rlitg_fma_probe (FFMA chains, 16-way ILP)"},
+        "hbm_note": "DRAM traffic is ~20 MB per iteration (profiles/r01_torm_final_full.json): ~2 % of HBM peak, so the FMA fraction is the relevant one",
         "target_ms": 1.0, "cpu_baseline": cpu, "shard_statistics": stats}
+
+    # ---------------------------------------------------------------- BASELINE config 1: the reference's own batch-1 CPU path
+    # one 100-pose path, one thread, per waypoint FK + Jacobian + pose error (comparable with the reference's recorded
+    # 0.003 ms per KDL FK call, pirl/script/module_topic_speed_test.py:72)
+    if rank == 0 and world == 1:
+        try:
+            from oracle import oracle as O
+            O.set_num_threads(1)
+            path = synth.random_ee_paths(1, 100, seed=0)[0]
+            qs = synth.random_configs(99, seed=0)
+            t0 = time.perf_counter(); reps = 0
+            while time.perf_counter() - t0 < 1.0:
+                O.fk_jac(qs); O.pose_diff(qs, path[1:]); reps += 1
+            dt1 = time.perf_counter() - t0
+            out["cpu_reference_batch1"] = {"us_per_waypoint": 1e6 * dt1 / (reps * 99), "cores": 1, "kind": "port",
+                                           "workload": "99 x (FK + Jacobian + pose error), one thread, FP64 oracle",
+                                           "reference_recorded": "0.003 ms per KDL FK call, 1.1 ms through the ROS service (authors' machine)"}
+            O.set_num_threads(len(os.sched_getaffinity(0)))
+        except Exception as e:  # noqa: BLE001
+            out["cpu_reference_batch1"] = {"error": str(e)}
 
     # ---------------------------------------------------------------- PIRL env step
     for B in (16384, 65536):
