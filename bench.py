@@ -226,6 +226,8 @@ def main():
             pass
 
     # ---- end to end: host buffers through rlitg_fk_jac_host (H2D q, kernel, D2H pos/rot/J)
+    from rlitg_b200.dist import bind_host_to_gpu
+    prev_affinity = None if os.environ.get("RLITG_BENCH_NO_NUMA") else bind_host_to_gpu(local)  # host buffers next to this rank's GPU (NUMA); undone after the e2e leg
     hq = q_host.pin_memory()
     hpos = torch.empty(B, 3).pin_memory(); hrot = torch.empty(B, 3, 3).pin_memory(); hjac = torch.empty(B, 6, D).pin_memory()
     e2e_steps = max(3, min(args.steps, 10))
@@ -239,7 +241,9 @@ def main():
     dt = max_over_ranks(time.perf_counter() - t0)
     e2e = {"value": world * B * e2e_steps / dt, "unit": "configs/s", "h2d_bytes_per_step": B * D * 4,
            "d2h_bytes_per_step": B * (3 + 9 + 6 * D) * 4, "steps": e2e_steps,
-           "api": "rlitg_fk_jac_host (pinned host buffers)"}
+           "api": "rlitg_fk_jac_host (pinned host buffers)", "numa_bound": prev_affinity is not None}
+    if prev_affinity is not None:
+        os.sched_setaffinity(0, prev_affinity)
 
     also = {}
     if not args.no_also:
