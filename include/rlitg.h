@@ -300,6 +300,24 @@ RLITG_API int rlitg_fma_probe(int ctas, int iters, float* out, void* stream);
 RLITG_API int rlitg_write_probe(void* dst, const void* src, int64_t ntiles, int tile_bytes, int read_floats,
                                 int ctas, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Device memory helpers for hosts built WITHOUT the CUDA toolkit.  The reference's C++ packages are plain catkin
+ * targets (torm/CMakeLists.txt:20-29, pirl/CMakeLists.txt:6-22: no CUDA language, no cudart); with these a
+ * maintainer links librlitg.so alone.  include/rlitg.hpp (the C++ mirror of TormIKSolver / TormOptimizer) uses
+ * nothing else.  Callers that already own device memory (torch, their own cudaMalloc) never need them: device
+ * pointers and streams of the primary context are interchangeable.
+ * ------------------------------------------------------------------------------------------------------- */
+RLITG_API int rlitg_device_count(int* count);
+RLITG_API int rlitg_set_device(int device);
+RLITG_API int rlitg_dev_alloc(void** out, uint64_t bytes);
+RLITG_API int rlitg_dev_free(void* ptr);
+RLITG_API int rlitg_dev_zero(void* ptr, uint64_t bytes, void* stream);
+/* stream-ordered copies; they return once the copy is queued unless the host buffer is pageable */
+RLITG_API int rlitg_copy_h2d(void* dst_dev, const void* src_host, uint64_t bytes, void* stream);
+RLITG_API int rlitg_copy_d2h(void* dst_host, const void* src_dev, uint64_t bytes, void* stream);
+RLITG_API int rlitg_copy_d2d(void* dst_dev, const void* src_dev, uint64_t bytes, void* stream);
+RLITG_API int rlitg_stream_sync(void* stream);
+
 #ifdef __cplusplus
 }
 #endif

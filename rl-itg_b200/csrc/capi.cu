@@ -266,3 +266,54 @@ extern "C" RLITG_API int rlitg_write_probe(void* dst, const void* src, int64_t n
                                                                  read_floats);
     return rlitg::check_launch("write_probe_kernel");
 }
+
+// ---- device memory helpers for hosts built without the CUDA toolkit (include/rlitg.hpp) ---------------------
+extern "C" {
+RLITG_API int rlitg_device_count(int* count) {
+    if (!count) return rlitg::set_error(RLITG_ERR_NULL, "count is NULL");
+    if (cudaGetDeviceCount(count) != cudaSuccess) return rlitg::set_cuda_error("cudaGetDeviceCount");
+    return RLITG_OK;
+}
+RLITG_API int rlitg_set_device(int device) {
+    if (cudaSetDevice(device) != cudaSuccess) return rlitg::set_cuda_error("cudaSetDevice");
+    return RLITG_OK;
+}
+RLITG_API int rlitg_dev_alloc(void** out, uint64_t bytes) {
+    if (!out) return rlitg::set_error(RLITG_ERR_NULL, "out is NULL");
+    *out = nullptr;
+    if (bytes == 0) return RLITG_OK;
+    if (cudaMalloc(out, (size_t)bytes) != cudaSuccess) return rlitg::set_cuda_error("cudaMalloc");
+    return RLITG_OK;
+}
+RLITG_API int rlitg_dev_free(void* ptr) {
+    if (ptr && cudaFree(ptr) != cudaSuccess) return rlitg::set_cuda_error("cudaFree");
+    return RLITG_OK;
+}
+RLITG_API int rlitg_dev_zero(void* ptr, uint64_t bytes, void* stream) {
+    if (bytes == 0) return RLITG_OK;
+    if (!ptr) return rlitg::set_error(RLITG_ERR_NULL, "ptr is NULL");
+    if (cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream) != cudaSuccess)
+        return rlitg::set_cuda_error("cudaMemsetAsync");
+    return RLITG_OK;
+}
+static int copy_any(void* dst, const void* src, uint64_t bytes, cudaMemcpyKind kind, void* stream) {
+    if (bytes == 0) return RLITG_OK;
+    if (!dst || !src) return rlitg::set_error(RLITG_ERR_NULL, "copy: NULL pointer");
+    if (cudaMemcpyAsync(dst, src, (size_t)bytes, kind, (cudaStream_t)stream) != cudaSuccess)
+        return rlitg::set_cuda_error("cudaMemcpyAsync");
+    return RLITG_OK;
+}
+RLITG_API int rlitg_copy_h2d(void* dst_dev, const void* src_host, uint64_t bytes, void* stream) {
+    return copy_any(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, stream);
+}
+RLITG_API int rlitg_copy_d2h(void* dst_host, const void* src_dev, uint64_t bytes, void* stream) {
+    return copy_any(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, stream);
+}
+RLITG_API int rlitg_copy_d2d(void* dst_dev, const void* src_dev, uint64_t bytes, void* stream) {
+    return copy_any(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, stream);
+}
+RLITG_API int rlitg_stream_sync(void* stream) {
+    if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return rlitg::set_cuda_error("cudaStreamSynchronize");
+    return RLITG_OK;
+}
+}  // extern "C"
