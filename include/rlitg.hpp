@@ -10,6 +10,7 @@
 //                               FP64 like KDL) + batched overloads on flat std::vector<double>
 //   rlitg::Scene                sphere table + occupancy grid handle (RAII)
 //   rlitg::TormCost             smoothness operator handle (RAII), getMaxQuadCostInvValue()
+//   rlitg::PirlVecEnv           B PIRL environments per step (PirlEnv_Fetch.reset / step), pirl_interpolate()
 //   rlitg::TormBatchOptimizer   N trajectories at once: getEndPoseCost, calculate*Increments, getCollisionCost,
 //                               calculateFeasibleIncrements / addIncrementsToTrajectory / handleJointLimits (fused in
 //                               the update call, as on the device), localOptimizeTSGD
@@ -461,6 +462,152 @@ class TormBatchOptimizer {
         alpha_, lr_;
     DeviceArray<uint8_t> hits_;
 };
+
+// ---- PIRL path-wise IK environment --------------------------------------------------------------------------
+// Constants of PirlEnv_Fetch.__init__ (pirl/script/envs/PirlEnv.py:118-174) and pirl/launch/pirl.yaml:9-14.
+inline RlitgPirlCfg make_pirl_cfg(const std::string& rewardType = "Task+NullSpaceImitation",
+                                  const std::string& obsType = "Conf+LinkPoses", int t = 1, int zDim = 0,
+                                  bool train_mode = true, bool refineFlag = false) {
+    RlitgPirlCfg c;
+    std::memset(&c, 0, sizeof(c));
+    const double ll[7] = {-1.6056, -1.221, -3.141592, -2.251, -3.141592, -2.16, -3.141592};
+    const double ul[7] = {1.6056, 1.518, 3.141592, 2.251, 3.141592, 2.16, 3.141592};
+    const int cj[7] = {0, 0, 1, 0, 1, 0, 1};
+    for (int j = 0; j < 7; j++) { c.ll[j] = ll[j]; c.ul[j] = ul[j]; c.cjoint[j] = cj[j]; }
+    c.n_future = t; c.z_dim = zDim;
+    if (obsType == "onlyConf") c.obs_type = 0;
+    else if (obsType == "Conf+LinkPoses") c.obs_type = 1;
+    else if (obsType == "Conf+EE") c.obs_type = 2;
+    else if (obsType == "onlyLinkPoses") c.obs_type = 3;
+    else throw Error(RLITG_ERR_ARG, "unknown obsType " + obsType);
+    c.train_mode = train_mode; c.refine_flag = refineFlag;
+    c.task_suc_r = 10.0; c.dist_suc_r = 1.0; c.rot_suc_r = 1.0; c.imit_suc_r = 0.0;
+    if (rewardType == "Task+NullSpaceImitation") { c.task_reward_flag = 1; c.null_reward_flag = 1; }
+    else if (rewardType == "Task+Imitation") { c.task_reward_flag = 1; c.imitate_reward_flag = 1; }
+    else if (rewardType == "Task") { c.task_reward_flag = 1; }
+    else if (rewardType == "Imitation") {
+        c.imitate_reward_flag = 1; c.task_suc_r = c.dist_suc_r = c.rot_suc_r = 0.0; c.imit_suc_r = 10.0;
+    } else throw Error(RLITG_ERR_ARG, "unknown rewardType " + rewardType);
+    c.thr_early_stop = 0.2; c.thr_dist = 0.04; c.thr_rot = 0.104; c.thr_imitate = 0.087; c.zero_task_dist = 0.04 * 2;
+    const double dp[4] = {2.0, -65.6, 30.0, 1.0}, rp[4] = {2.0, -5.0, 0.0, 0.0}, ip[4] = {1.0, -3.8, 0.05, 1.0},
+                 np_[4] = {1.0, -15, 0.5, 1.0};
+    for (int k = 0; k < 4; k++) { c.dist_p[k] = dp[k]; c.rot_p[k] = rp[k]; c.imit_p[k] = ip[k]; c.null_p[k] = np_[k]; }
+    c.w_col = 10.0; c.w_jlimit = 1.0; c.w_early_stop = 3.0;
+    return c;
+}
+
+// B environments stepped by one kernel: PirlEnv_Fetch.reset / step (PirlEnv.py:209-289, 352-392) with a leading
+// batch axis.  State lives on the device as float32; observations / rewards / flags come back to the host each step
+// (the policy of the C++ caller, PirlInterpolator's TorchScript module, runs on host tensors).
+class PirlVecEnv {
+  public:
+    struct Step {
+        std::vector<float> obs;      // [B,O]
+        std::vector<float> reward;   // [B]
+        std::vector<uint8_t> done;   // [B]
+        std::vector<uint8_t> flags;  // [B,8] is_col, is_jlimit, is_early_stop, is_timeout, is_dist_suc, is_rot_suc,
+                                     //       is_imitate_suc, is_task_suc
+    };
+    PirlVecEnv(int64_t B, const std::string& rewardType = "Task+NullSpaceImitation",
+               const std::string& obsType = "Conf+LinkPoses", int t = 1, int zDim = 0, bool refineFlag = false,
+               const Scene* scene = nullptr, std::array<double, 3> base_off = {-0.086875, 0.0, 0.37743})
+        : B_(B), rewardType_(rewardType), obsType_(obsType), t_(t), z_(zDim), refine_(refineFlag), scene_(scene),
+          base_off_(base_off), cfg_(make_pirl_cfg(rewardType, obsType, t, zDim, true, refineFlag)) {
+        O_ = rlitg_pirl_obs_dim(&cfg_);
+        q_.resize((size_t)B * 7); ts_.resize(B); mts_.resize(B); cnt_.resize((size_t)B * 4);
+        obs_.resize((size_t)B * O_); rew_.resize(B); done_.resize(B); flags_.resize((size_t)B * 8);
+        act_.resize((size_t)B * 7);
+        if (zDim > 0) { latent_.resize((size_t)B * zDim); latent_.zero(); }
+    }
+    int64_t numEnvs() const { return B_; }
+    int observationDim() const { return O_; }
+    // target_poses [B,Tmax,7] x y z qx qy qz qw; demo_configs [B,Tmax,7] (may be empty); max_timestep [B]
+    void setProblems(const std::vector<double>& target_poses, const std::vector<double>& demo_configs,
+                     const std::vector<int32_t>& max_timestep, int Tmax) {
+        if (target_poses.size() != (size_t)B_ * Tmax * 7 || max_timestep.size() != (size_t)B_ ||
+            (!demo_configs.empty() && demo_configs.size() != target_poses.size()))
+            throw Error(RLITG_ERR_SHAPE, "setProblems: sizes must be B*Tmax*7 / B");
+        Tmax_ = Tmax;
+        targets_.upload(std::vector<float>(target_poses.begin(), target_poses.end()));
+        demos_host_ = demo_configs;
+        if (!demo_configs.empty()) demos_.upload(std::vector<float>(demo_configs.begin(), demo_configs.end()));
+        mts_.upload(max_timestep);
+    }
+    // reset (:352-392): cur_conf = demo_configs[0] with continuous joints refined to (-pi, pi] (:577-590) unless
+    // start_conf [B,7] is given; counters and timestep cleared; returns the observation [B,O]
+    std::vector<float> reset(const std::vector<double>* start_conf = nullptr, bool train_mode = true) {
+        cfg_ = make_pirl_cfg(rewardType_, obsType_, t_, z_, train_mode, refine_);
+        std::vector<float> q0((size_t)B_ * 7);
+        const double pi = 3.14159265358979323846;
+        for (int64_t b = 0; b < B_; b++)
+            for (int j = 0; j < 7; j++) {
+                double v;
+                if (start_conf) v = (*start_conf)[b * 7 + j];
+                else {
+                    if (demos_host_.empty()) throw Error(RLITG_ERR_NULL, "reset needs start_conf or demo_configs");
+                    v = demos_host_[((size_t)b * Tmax_) * 7 + j];
+                    if (cfg_.cjoint[j] && std::fabs(v) > pi) {
+                        double buf = v - (double)(long long)(v / (2 * pi)) * 2 * pi;
+                        if (v > pi && buf > pi) buf -= 2 * pi;
+                        if (v < -pi && buf < -pi) buf += 2 * pi;
+                        v = buf;
+                    }
+                }
+                q0[b * 7 + j] = (float)v;
+            }
+        q_.upload(q0);
+        ts_.zero(); cnt_.zero();
+        check(rlitg_pirl_obs(&cfg_, B_, RLITG_F32, q_.data(), ts_.data(), mts_.data(), targets_.data(), Tmax_,
+                             z_ > 0 ? latent_.data() : nullptr, obs_.data(), nullptr));
+        return obs_.download();
+    }
+    Step step(const std::vector<float>& action /*[B,7]*/) {
+        if (action.size() != (size_t)B_ * 7) throw Error(RLITG_ERR_SHAPE, "action must hold B*7 values");
+        act_.upload(action);
+        check(rlitg_pirl_env_step(&cfg_, B_, RLITG_F32, q_.data(), act_.data(), ts_.data(), mts_.data(), targets_.data(),
+                                  demos_host_.empty() ? nullptr : demos_.data(), Tmax_, z_ > 0 ? latent_.data() : nullptr,
+                                  scene_ ? scene_->handle() : nullptr, base_off_.data(), obs_.data(), rew_.data(),
+                                  done_.data(), flags_.data(), cnt_.data(), nullptr, nullptr));
+        Step r;
+        r.obs = obs_.download(); r.reward = rew_.download(); r.done = done_.download(); r.flags = flags_.download();
+        return r;
+    }
+    std::vector<float> currentConfigurations() const { return q_.download(); }
+    std::vector<int32_t> successCounters() const { return cnt_.download(); }  // [B,4] task, dist, rot, imitate
+
+  private:
+    int64_t B_;
+    std::string rewardType_, obsType_;
+    int t_, z_;
+    bool refine_;
+    const Scene* scene_;
+    std::array<double, 3> base_off_;
+    RlitgPirlCfg cfg_;
+    int O_ = 0, Tmax_ = 0;
+    std::vector<double> demos_host_;
+    DeviceArray<float> q_, targets_, demos_, latent_, obs_, rew_, act_;
+    DeviceArray<int32_t> ts_, mts_, cnt_;
+    DeviceArray<uint8_t> done_, flags_;
+};
+
+// PirlInterpolator::interpolate (torm/src/pirl_interpolator.cpp:102-140) for B problems at once: observation ->
+// policy -> setAction (test mode: add, wrap, clamp, no rejection), one waypoint per step.
+// policy(obs [B*O], B, O) -> action [B*7].  Returns the generated configurations [B, n_steps, 7].
+template <class Policy>
+std::vector<float> pirl_interpolate(PirlVecEnv& env, Policy&& policy, int n_steps,
+                                    const std::vector<double>* start_conf = nullptr) {
+    const int64_t B = env.numEnvs();
+    std::vector<float> out((size_t)B * n_steps * 7);
+    std::vector<float> obs = env.reset(start_conf, /*train_mode=*/false);
+    for (int k = 0; k < n_steps; k++) {
+        const std::vector<float> act = policy(obs, B, env.observationDim());
+        PirlVecEnv::Step r = env.step(act);
+        obs = std::move(r.obs);
+        const std::vector<float> q = env.currentConfigurations();
+        for (int64_t b = 0; b < B; b++) std::memcpy(&out[((size_t)b * n_steps + k) * 7], &q[b * 7], 7 * sizeof(float));
+    }
+    return out;
+}
 
 }  // namespace rlitg
 #endif  // RLITG_HPP_

@@ -226,6 +226,96 @@ int main() {
     std::printf("objective %.5f -> %.5f over %d trajectories; kernels launched: %lld\n", before / N, after / N, N,
                 (long long)rlitg_launch_count());
 
+    // ---- PirlVecEnv: reset + three steps against the oracle (FP32 device state vs FP64 oracle)
+    {
+        const int Bp = 96, Tp = 12;
+        std::vector<double> demos((size_t)Bp * Tp * 7), tposes((size_t)Bp * Tp * 7);
+        for (int b = 0; b < Bp; b++) {
+            double cur[7];
+            for (int j = 0; j < 7; j++) cur[j] = kLL[j] * 0.5 + (kUL[j] - kLL[j]) * 0.5 * U(rng);
+            for (int i = 0; i < Tp; i++)
+                for (int j = 0; j < 7; j++) {
+                    cur[j] = std::fmin(kUL[j] - 0.05, std::fmax(kLL[j] + 0.05, cur[j] + 0.04 * G(rng)));
+                    demos[((size_t)b * Tp + i) * 7 + j] = (double)(float)cur[j];
+                }
+        }
+        orc_fk_quat(demos.data(), (int64_t)Bp * Tp, 7, tposes.data());
+        for (auto& v : tposes) v = (double)(float)(std::round(v * 1e6) / 1e6);
+        std::vector<int32_t> mts(Bp, Tp - 1);
+        PirlVecEnv env(Bp, "Task+NullSpaceImitation", "Conf+LinkPoses", 1, 0, false, &scene);
+        env.setProblems(tposes, demos, mts, Tp);
+        auto obs0 = env.reset();
+        EXPECT(env.observationDim() == 88 && obs0.size() == (size_t)Bp * 88, "obs dim %d", env.observationDim());
+
+        RlitgPirlCfg cc = make_pirl_cfg();
+        OrcPirlCfg oc2;
+        for (int j = 0; j < 7; j++) { oc2.ll[j] = cc.ll[j]; oc2.ul[j] = cc.ul[j]; oc2.cjoint[j] = cc.cjoint[j]; }
+        oc2.n_future = cc.n_future; oc2.z_dim = cc.z_dim; oc2.obs_type = cc.obs_type; oc2.train_mode = cc.train_mode;
+        oc2.refine_flag = cc.refine_flag; oc2.task_reward_flag = cc.task_reward_flag;
+        oc2.imitate_reward_flag = cc.imitate_reward_flag; oc2.null_reward_flag = cc.null_reward_flag;
+        oc2.task_suc_r = cc.task_suc_r; oc2.dist_suc_r = cc.dist_suc_r; oc2.rot_suc_r = cc.rot_suc_r; oc2.imit_suc_r = cc.imit_suc_r;
+        oc2.thr_early_stop = cc.thr_early_stop; oc2.thr_dist = cc.thr_dist; oc2.thr_rot = cc.thr_rot;
+        oc2.thr_imitate = cc.thr_imitate; oc2.zero_task_dist = cc.zero_task_dist;
+        for (int k = 0; k < 4; k++) { oc2.dist_p[k] = cc.dist_p[k]; oc2.rot_p[k] = cc.rot_p[k]; oc2.imit_p[k] = cc.imit_p[k]; oc2.null_p[k] = cc.null_p[k]; }
+        oc2.w_col = cc.w_col; oc2.w_jlimit = cc.w_jlimit; oc2.w_early_stop = cc.w_early_stop;
+
+        std::vector<double> oq((size_t)Bp * 7), oobs((size_t)Bp * 88), orew(Bp), oerr((size_t)Bp * 4);
+        for (int b = 0; b < Bp; b++)
+            for (int j = 0; j < 7; j++) oq[b * 7 + j] = demos[((size_t)b * Tp) * 7 + j];
+        std::vector<int32_t> ots(Bp, 0), ocnt((size_t)Bp * 4, 0);
+        std::vector<uint8_t> odone(Bp), oflags((size_t)Bp * 8);
+        orc_pirl_obs(&oc2, Bp, oq.data(), ots.data(), mts.data(), tposes.data(), Tp, nullptr, oobs.data());
+        double m = 0;
+        for (size_t i = 0; i < obs0.size(); i++) m = std::fmax(m, std::fabs(obs0[i] - oobs[i]));
+        EXPECT(m < 2e-5, "reset observation %g", m);
+        int flag_diff = 0, ncol = 0;
+        double mobs = 0, mrew = 0;
+        for (int k = 0; k < 3; k++) {
+            std::vector<float> act((size_t)Bp * 7);
+            for (int b = 0; b < Bp; b++)
+                for (int j = 0; j < 7; j++)
+                    act[b * 7 + j] = (float)(demos[((size_t)b * Tp + k + 1) * 7 + j] - oq[b * 7 + j] + 0.01 * G(rng));
+            auto r = env.step(act);
+            orc_pirl_env_step(&oc2, Bp, oq.data(), act.data(), ots.data(), mts.data(), tposes.data(), demos.data(), Tp,
+                              nullptr, &osc, base_off, oobs.data(), orew.data(), odone.data(), oflags.data(), ocnt.data(),
+                              oerr.data());
+            const auto qd = env.currentConfigurations();
+            for (int b = 0; b < Bp; b++) {
+                bool same = r.done[b] == odone[b];
+                for (int f = 0; f < 8; f++) same = same && r.flags[b * 8 + f] == oflags[b * 8 + f];
+                ncol += oflags[b * 8];
+                if (!same) { flag_diff++; continue; }
+                mrew = std::fmax(mrew, std::fabs(r.reward[b] - orew[b]));
+                for (int o = 0; o < 88; o++) mobs = std::fmax(mobs, std::fabs(r.obs[(size_t)b * 88 + o] - oobs[(size_t)b * 88 + o]));
+                for (int j = 0; j < 7; j++) oq[b * 7 + j] = qd[b * 7 + j];  // keep both sides on the same FP32 state
+            }
+        }
+        EXPECT(flag_diff <= 2, "flags differ in %d env-steps", flag_diff);
+        // reward carries 2 exp(-5 r) with r = 2 acos|w|: FP32 resolves r to ~5e-4 near 0 -> 1e-2
+        EXPECT(mobs < 5e-5 && mrew < 1e-2, "obs %g reward %g", mobs, mrew);
+        std::printf("pirl: 3 steps x %d envs, %d collisions, %d threshold ties\n", Bp, ncol, flag_diff);
+
+        // pirl_interpolate with a "follow the demonstration" policy reproduces the demo path
+        PirlVecEnv env2(Bp, "Task", "Conf+LinkPoses", 1, 0, false, nullptr);
+        env2.setProblems(tposes, demos, mts, Tp);
+        int step_k = 0;
+        auto policy = [&](const std::vector<float>& obs, int64_t nb, int od) {
+            std::vector<float> a((size_t)nb * 7);
+            for (int64_t b = 0; b < nb; b++)
+                for (int j = 0; j < 7; j++)  // obs[:7] is the current configuration (Conf+LinkPoses)
+                    a[b * 7 + j] = (float)demos[((size_t)b * Tp + step_k + 1) * 7 + j] - obs[(size_t)b * od + j];
+            step_k++;
+            return a;
+        };
+        auto gen = pirl_interpolate(env2, policy, Tp - 1);
+        m = 0;
+        for (int b = 0; b < Bp; b++)
+            for (int k = 0; k < Tp - 1; k++)
+                for (int j = 0; j < 7; j++)
+                    m = std::fmax(m, std::fabs(gen[((size_t)b * (Tp - 1) + k) * 7 + j] - demos[((size_t)b * Tp + k + 1) * 7 + j]));
+        EXPECT(m < 1e-5, "pirl_interpolate vs demonstration %g", m);
+    }
+
     // ---- error behaviour: C codes surface as exceptions
     bool threw = false;
     try {
