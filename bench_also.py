@@ -144,8 +144,7 @@ def run(dev, rank, world, max_over_ranks, barrier, steps=30, warmup=5):
             out["cpu_reference_batch1"] = {"error": str(e)}
 
     # ---------------------------------------------------------------- PIRL env step
-    for B in (16384, 65536):
-        Tp = 100
+    for B, Tp in ((16384, 100), (65536, 100), (1048576, 16)):  # 1M envs (16-pose paths): the HBM-bound size
         rng = np.random.default_rng(11 + rank)
         demos = synth.random_joint_paths(B, Tp, seed=5 + rank)
         dq = torch.tensor(demos.reshape(-1, 7) + rng.normal(0, 0.01, size=(B * Tp, 7)), dtype=torch.float32, device=dev)
@@ -184,10 +183,43 @@ def run(dev, rank, world, max_over_ranks, barrier, steps=30, warmup=5):
         bytes_env = 536.0
         out["pirl_env_step_%d" % B] = {
             "config": {"workload": "pirl_env_step", "envs_per_gpu": B, "obs": "Conf+LinkPoses t=1 z=0 (88 floats)",
-                       "reward": "Task+NullSpaceImitation", "l2": "batch is L2 resident (8.8 MB at 16k envs); *_cold = L2 flushed"},
+                       "path_poses": Tp, "reward": "Task+NullSpaceImitation",
+                       "l2": "batch is L2 resident (8.8 MB at 16k envs; 562 MB at 1M envs is not); *_cold = L2 flushed"},
             "us_per_step": ms * 1e3, "us_per_step_cold": ms_cold * 1e3, "us_per_step_cuda_graph": us_graph,
             "env_steps_per_s": world * B / (ms * 1e-3),
             "unit": "env-steps/s", "roofline": {"bound": "hbm", "achieved": bytes_env * B / (ms * 1e-3) / 1e9,
                                                "unit": "GB/s", "bytes_per_env": bytes_env}}
+        del env, demos, dq, pos, quat, targets_b
+
+    # ---------------------------------------------------------------- FK / Jacobian in the other layouts and sizes
+    fk = {}
+    for name, Bk, D, soa in (("soa_1M", 1 << 20, 7, True), ("aos_8M", 1 << 23, 7, False), ("aos_1M_D8_torso", 1 << 20, 8, False)):
+        g = torch.Generator(device="cpu"); g.manual_seed(3 + rank)
+        lo = torch.tensor(([0.0] if D == 8 else []) + list(fetch.LL), dtype=torch.float32)
+        hi = torch.tensor(([0.38615] if D == 8 else []) + list(fetch.UL), dtype=torch.float32)
+        qk = (lo + (hi - lo) * torch.rand(Bk, D, generator=g)).to(dev)
+        if soa:
+            qk = qk.t().contiguous()
+            outk = {"pos": torch.empty(3, Bk, device=dev), "rot": torch.empty(9, Bk, device=dev),
+                    "jac": torch.empty(6 * D, Bk, device=dev)}
+            fn = lambda: K.fk_jac(qk, q_soa=True, out_soa=True, out=outk)
+        else:
+            outk = {"pos": torch.empty(Bk, 3, device=dev), "rot": torch.empty(Bk, 3, 3, device=dev),
+                    "jac": torch.empty(Bk, 6, D, device=dev)}
+            fn = lambda: K.fk_jac(qk, out=outk)
+        barrier()
+        msk = max_over_ranks(_time_loop(torch, fn, steps, warmup))
+        bpc = 4 * (D + 12 + 6 * D)
+        fk[name] = {"configs_per_gpu": Bk, "D": D, "us_per_step": msk * 1e3, "configs_per_s": world * Bk / (msk * 1e-3),
+                    "gb_per_s": bpc * Bk / (msk * 1e-3) / 1e9, "bytes_per_config": bpc}
+        del qk, outk
+    qa = torch.tensor(synth.random_configs(1 << 20, seed=9 + rank), dtype=torch.float32, device=dev)
+    oa = torch.empty(1 << 20, 8, 7, device=dev)
+    barrier()
+    msk = max_over_ranks(_time_loop(torch, lambda: K.allfk(qa, out=oa), steps, warmup))
+    fk["allfk_1M"] = {"configs_per_gpu": 1 << 20, "D": 7, "us_per_step": msk * 1e3,
+                      "configs_per_s": world * (1 << 20) / (msk * 1e-3), "gb_per_s": 252 * (1 << 20) / (msk * 1e-3) / 1e9,
+                      "bytes_per_config": 252}
+    out["fk_other_layouts"] = fk
     sc.close()
     return out
