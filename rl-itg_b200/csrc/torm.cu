@@ -18,6 +18,7 @@
 // ten cost scalars are written.  Long paths (T > 256) are walked in 256-row chunks with recomputed halo rows.
 // FP32-FMA bound on paper, L2-gather latency bound in practice.
 #include <algorithm>
+#include <mutex>
 #include <cmath>
 #include <cstdlib>
 #include <vector>
@@ -653,8 +654,11 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
     if (!run_pose && !run_coll) return set_error(RLITG_ERR_ARG, "stage_mask selects no stage");
     // When both kernels run they are forked onto two streams (joined again before returning to the caller's
     // stream order): the pose kernel's CTAs fill the SMs that the collision kernel's last, partial wave leaves idle.
-    struct Fork { cudaStream_t side = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+    // The side stream and its two events are shared by every caller on a device, so the fork .. join sequence is
+    // serialised on the host (launches are asynchronous: the lock is held for microseconds).
+    struct Fork { std::mutex mu; cudaStream_t side = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
     static Fork forks[64];
+    std::unique_lock<std::mutex> fork_lock;
     static const int concurrent = [] { const char* e = getenv("RLITG_TORM_CONCURRENT"); return e ? atoi(e) : 1; }();
     cudaStream_t st_pose = st;
     Fork* fk = nullptr;
@@ -662,6 +666,7 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
         int dev = 0;
         cudaGetDevice(&dev);
         fk = &forks[dev & 63];
+        fork_lock = std::unique_lock<std::mutex>(fk->mu);
         if (!fk->side) {
             if (cudaStreamCreateWithFlags(&fk->side, cudaStreamNonBlocking) != cudaSuccess ||
                 cudaEventCreateWithFlags(&fk->fork, cudaEventDisableTiming) != cudaSuccess ||

@@ -336,3 +336,46 @@ def test_tsgd_iteration_cuda_graph(cuda_device):
     torch.cuda.synchronize()
     assert torch.equal(eager, graphed)
     gsc.close()
+
+
+def test_concurrent_host_threads_on_two_streams(cuda_device):
+    """Two host threads drive their own TormBatch on their own stream at the same time (ctypes releases the GIL):
+    the shared fork / join side stream of the launcher must not mix up their ordering.  Results = the serial ones."""
+    import threading
+    import torch
+    from rlitg_b200 import torm as TM
+    from oracle import oracle as O
+    mask = O.STAGE_POSE_GRAD | O.STAGE_SMOOTH | O.STAGE_COLL | O.STAGE_EVAL
+    jobs = []
+    for k in range(2):
+        traj, targets, _, gsc = make_problem(96, 120, 40 + k, cuda_device)
+        pr = TM.TormParameters(min_clearence_=0.3)
+        tb = TM.TormBatch(targets, pr, gsc, cuda_device, torch.float32)
+        t = torch.tensor(traj, dtype=torch.float32, device=cuda_device)
+        ref = {kk: (None if v is None else v.clone()) for kk, v in tb.cost_grad(t, mask).items()}
+        jobs.append((tb, t, ref))
+    torch.cuda.synchronize()
+    errors = []
+
+    def worker(tb, t, ref):
+        try:
+            s = torch.cuda.Stream(device=cuda_device)
+            with torch.cuda.stream(s):
+                for _ in range(200):
+                    # dirty the outputs on this stream, then recompute: a mis-ordered side stream shows up as zeros
+                    for name in ("costs", "inc_pose", "inc_coll", "inc_smooth"):
+                        tb._buf[name].zero_()
+                    got = tb.cost_grad(t, mask)
+                s.synchronize()
+                for name in ("costs", "inc_pose", "inc_coll", "inc_smooth"):
+                    if not torch.equal(got[name], ref[name]):
+                        errors.append((name, float((got[name] - ref[name]).abs().max())))
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=j) for j in jobs]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
