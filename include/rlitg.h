@@ -280,6 +280,14 @@ RLITG_API int rlitg_torm_update(void* traj, int64_t N, int dtype, const RlitgSmo
                                 const void* inc_coll, const void* inc_pose, const void* alpha, const void* lr,
                                 void* stream);
 
+/* Same, with the stage chosen per trajectory: stage_idx [N] int32 on the device, 0 = feasible, 1 = end-pose, negative =
+ * leave the trajectory untouched (u->stage is ignored).  lr_schedule_mode_ 1 lets each optimiser switch stages on its
+ * own feasibility history (torm/src/torm_optimizer.cpp:400-412), so a lock-step batch mixes both kinds of update. */
+RLITG_API int rlitg_torm_update_staged(void* traj, int64_t N, int dtype, const RlitgSmooth* smooth,
+                                       const RlitgTormParams* p, const RlitgTormUpdate* u, const int32_t* stage_idx,
+                                       const void* inc_smooth, const void* inc_coll, const void* inc_pose,
+                                       const void* alpha, const void* lr, void* stream);
+
 /* Candidate selection of the Greedy / Linear initialisers: replays the sequential rule of
  * TormOptimizer::getNewTrajectory (torm/src/torm_optimizer.cpp:973-1003; same at :1066-1096) over C scored
  * candidates: eCost = ([8] + rot_scale [9]) / (Tseg - 1) (ranged getEndPoseCost :1427-1446), candidates with

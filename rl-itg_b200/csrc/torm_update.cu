@@ -41,7 +41,8 @@ template <typename T>
 __global__ void __launch_bounds__(kUpdThreads)
 torm_update_kernel(UpdP P, T* __restrict__ traj, const T* __restrict__ inc_smooth, const T* __restrict__ inc_coll,
                    const T* __restrict__ inc_pose, const T* __restrict__ alpha, const T* __restrict__ lr,
-                   const double* __restrict__ chol, const double* __restrict__ inv) {
+                   const double* __restrict__ chol, const double* __restrict__ inv,
+                   const int32_t* __restrict__ stage_idx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Tn = P.Tn, F = Tn - 1, tid = threadIdx.x;
     double* fin = reinterpret_cast<double*>(smem_raw);  // [F][7] right-hand side -> final increments
@@ -50,11 +51,15 @@ torm_update_kernel(UpdP P, T* __restrict__ traj, const T* __restrict__ inc_smoot
     __shared__ double s_best[kUpdThreads];
     __shared__ int s_idx[kUpdThreads];
     const int64_t n = blockIdx.x;
+    // per-trajectory stage (lr_schedule_mode_ 1 lets every optimiser pick its own, torm_optimizer.cpp:400-412);
+    // a negative entry leaves the trajectory untouched
+    const int stage = stage_idx ? stage_idx[n] : P.stage;
+    if (stage < 0) return;
     T* trow = traj + n * (int64_t)Tn * 7 + 7;  // first free row
     const size_t FD = (size_t)F * 7;
     for (int k = tid; k < (int)FD; k += kUpdThreads) tr[k] = (double)trow[k];
 
-    if (P.stage == 0) {
+    if (stage == 0) {
         const T* s = inc_smooth + n * FD;
         const T* c = inc_coll + n * FD;
         double ss = 1.0, sc = 1.0;
@@ -164,7 +169,7 @@ torm_update_kernel(UpdP P, T* __restrict__ traj, const T* __restrict__ inc_smoot
 template <typename T>
 static int launch_update(const RlitgTormUpdate* u, const RlitgTormParams* p, const Smooth* sm, T* traj, int64_t N,
                          const T* inc_smooth, const T* inc_coll, const T* inc_pose, const T* alpha, const T* lr,
-                         cudaStream_t st) {
+                         const int32_t* stage_idx, cudaStream_t st) {
     UpdP P;
     P.Tn = p->T; P.stage = u->stage; P.mode = u->lr_schedule_mode;
     P.sw = u->smoothness_update_weight; P.ow = u->obstacle_update_weight; P.limit = u->joint_update_limit;
@@ -177,7 +182,8 @@ static int launch_update(const RlitgTormUpdate* u, const RlitgTormParams* p, con
         int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "torm_update_kernel");
         if (rc_attr) return rc_attr;
     }
-    kern<<<(unsigned)N, kUpdThreads, smem, st>>>(P, traj, inc_smooth, inc_coll, inc_pose, alpha, lr, sm->d_chol, sm->d_inv64);
+    kern<<<(unsigned)N, kUpdThreads, smem, st>>>(P, traj, inc_smooth, inc_coll, inc_pose, alpha, lr, sm->d_chol, sm->d_inv64,
+                                                 stage_idx);
     return check_launch("torm_update_kernel");
 }
 
@@ -185,27 +191,44 @@ static int launch_update(const RlitgTormUpdate* u, const RlitgTormParams* p, con
 
 using namespace rlitg;
 
-extern "C" RLITG_API int rlitg_torm_update(void* traj, int64_t N, int dtype, const RlitgSmooth* smooth,
-                                           const RlitgTormParams* p, const RlitgTormUpdate* u, const void* inc_smooth,
-                                           const void* inc_coll, const void* inc_pose, const void* alpha,
-                                           const void* lr, void* stream) {
+static int torm_update_impl(void* traj, int64_t N, int dtype, const RlitgSmooth* smooth, const RlitgTormParams* p,
+                            const RlitgTormUpdate* u, const int32_t* stage_idx, const void* inc_smooth,
+                            const void* inc_coll, const void* inc_pose, const void* alpha, const void* lr,
+                            void* stream) {
     if (!p || !u || !smooth) return set_error(RLITG_ERR_NULL, "params / update / smooth is NULL");
     if (p->D != 7) return set_error(RLITG_ERR_SHAPE, "TORM runs the 7-joint arm chain (D = 7)");
     if (N < 0 || N > 0x7fffffff) return set_error(RLITG_ERR_SHAPE, "N out of range");
     if (dtype != RLITG_F32 && dtype != RLITG_F64) return set_error(RLITG_ERR_DTYPE, "dtype must be RLITG_F32 or RLITG_F64");
-    if (u->stage != 0 && u->stage != 1) return set_error(RLITG_ERR_ARG, "stage must be 0 (feasible) or 1 (end-pose)");
+    if (!stage_idx && u->stage != 0 && u->stage != 1) return set_error(RLITG_ERR_ARG, "stage must be 0 (feasible) or 1 (end-pose)");
     const Smooth* sm = reinterpret_cast<const Smooth*>(smooth);
     if (sm->T != p->T) return set_error(RLITG_ERR_SHAPE, "smooth handle was built for a different T");
     if (N == 0) return RLITG_OK;
     if (!traj) return set_error(RLITG_ERR_NULL, "traj is NULL");
-    if (u->stage == 0 && (!inc_smooth || !inc_coll || !lr)) return set_error(RLITG_ERR_NULL, "feasible stage needs inc_smooth, inc_coll and lr");
-    if (u->stage == 1 && !inc_pose) return set_error(RLITG_ERR_NULL, "end-pose stage needs inc_pose");
+    const bool feas = stage_idx || u->stage == 0, endp = stage_idx || u->stage == 1;
+    if (feas && (!inc_smooth || !inc_coll || !lr)) return set_error(RLITG_ERR_NULL, "feasible stage needs inc_smooth, inc_coll and lr");
+    if (endp && !inc_pose) return set_error(RLITG_ERR_NULL, "end-pose stage needs inc_pose");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == RLITG_F32)
         return launch_update<float>(u, p, sm, (float*)traj, N, (const float*)inc_smooth, (const float*)inc_coll,
-                                    (const float*)inc_pose, (const float*)alpha, (const float*)lr, st);
+                                    (const float*)inc_pose, (const float*)alpha, (const float*)lr, stage_idx, st);
     return launch_update<double>(u, p, sm, (double*)traj, N, (const double*)inc_smooth, (const double*)inc_coll,
-                                 (const double*)inc_pose, (const double*)alpha, (const double*)lr, st);
+                                 (const double*)inc_pose, (const double*)alpha, (const double*)lr, stage_idx, st);
+}
+
+extern "C" RLITG_API int rlitg_torm_update(void* traj, int64_t N, int dtype, const RlitgSmooth* smooth,
+                                           const RlitgTormParams* p, const RlitgTormUpdate* u, const void* inc_smooth,
+                                           const void* inc_coll, const void* inc_pose, const void* alpha,
+                                           const void* lr, void* stream) {
+    return torm_update_impl(traj, N, dtype, smooth, p, u, nullptr, inc_smooth, inc_coll, inc_pose, alpha, lr, stream);
+}
+
+extern "C" RLITG_API int rlitg_torm_update_staged(void* traj, int64_t N, int dtype, const RlitgSmooth* smooth,
+                                                  const RlitgTormParams* p, const RlitgTormUpdate* u,
+                                                  const int32_t* stage_idx, const void* inc_smooth,
+                                                  const void* inc_coll, const void* inc_pose, const void* alpha,
+                                                  const void* lr, void* stream) {
+    if (!stage_idx) return set_error(RLITG_ERR_NULL, "stage_idx is NULL");
+    return torm_update_impl(traj, N, dtype, smooth, p, u, stage_idx, inc_smooth, inc_coll, inc_pose, alpha, lr, stream);
 }
 
 // ---- candidate selection of the Greedy / Linear initialisers --------------------------------

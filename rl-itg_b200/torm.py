@@ -233,11 +233,17 @@ lib.rlitg_torm_update.argtypes = [_vp, C.c_int64, C.c_int, _vp, C.POINTER(RlitgT
                                   _vp, _vp, _vp, _vp, _vp, _vp]
 
 
+lib.rlitg_torm_update_staged.argtypes = [_vp, C.c_int64, C.c_int, _vp, C.POINTER(RlitgTormParams),
+                                         C.POINTER(RlitgTormUpdate), _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+
+
 def _apply_increments(self, traj, feasible_stage, inc_smooth=None, inc_coll=None, inc_pose=None, alpha=None,
-                      learning_rate=None, lr_schedule_mode=1):
+                      learning_rate=None, lr_schedule_mode=1, stage_idx=None):
     """calculateFeasibleIncrements | calculateEndPoseIncrements, then addIncrementsToTrajectory and
     handleJointLimits (torm/src/torm_optimizer.cpp:1555-1639, 1189-1268), in place on traj [N,T,7].
-    alpha / learning_rate: python floats or [N] tensors (per-trajectory alpha_ / learning_rate_)."""
+    alpha / learning_rate: python floats or [N] tensors (per-trajectory alpha_ / learning_rate_).
+    stage_idx: optional int32 [N] device tensor choosing the stage per trajectory (0 feasible, 1 end-pose, < 0 skip);
+    `feasible_stage` is then ignored (rlitg_torm_update_staged)."""
     pr = self.parameters
     N = traj.shape[0]
     u = RlitgTormUpdate()
@@ -262,57 +268,121 @@ def _apply_increments(self, traj, feasible_stage, inc_smooth=None, inc_coll=None
     code = _lib.F32 if traj.dtype == torch.float32 else _lib.F64
     assert traj.is_contiguous()
     with _lib.on_device(self.device):
-        check(lib.rlitg_torm_update(traj.data_ptr(), N, code, self.joint_costs_.handle, C.byref(self._cp), C.byref(u),
-                                    p(inc_smooth), p(inc_coll), p(inc_pose), a.data_ptr(), lr.data_ptr(),
-                                    torch.cuda.current_stream().cuda_stream))
+        if stage_idx is None:
+            check(lib.rlitg_torm_update(traj.data_ptr(), N, code, self.joint_costs_.handle, C.byref(self._cp), C.byref(u),
+                                        p(inc_smooth), p(inc_coll), p(inc_pose), a.data_ptr(), lr.data_ptr(),
+                                        torch.cuda.current_stream().cuda_stream))
+        else:
+            assert stage_idx.dtype == torch.int32 and stage_idx.is_cuda and stage_idx.is_contiguous()
+            check(lib.rlitg_torm_update_staged(traj.data_ptr(), N, code, self.joint_costs_.handle, C.byref(self._cp),
+                                               C.byref(u), stage_idx.data_ptr(), p(inc_smooth), p(inc_coll), p(inc_pose),
+                                               a.data_ptr(), lr.data_ptr(), torch.cuda.current_stream().cuda_stream))
     return traj
 
 
 TormBatch.applyIncrements = _apply_increments
 
 
-def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, check_collision=True):
+def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, check_collision=True, lr_schedule_mode=3,
+                         return_state=False):
     """Lock-step two-stage gradient descent over the N trajectories of `traj` (in place): the loop body of
-    TormOptimizer::localOptimizeTSGD (torm/src/torm_optimizer.cpp:397-598) with lr_schedule_mode_ == 3 (fixed
-    learning rate, alpha_ = 0.5, stage 0 = feasible, stage 1 = end-pose, :471-473, :497-499), entirely on the device:
-    cost + increments (kernels 3a / 3b), update step, and the best-trajectory bookkeeping of :506-560 (a trajectory is
-    recorded when its evaluator cost improves and it is collision free and within the velocity limits).
-    The adaptive schedules (modes 1, 2) are scalar host control flow per trajectory and stay with the caller.
-    Returns (best_traj [N,T,7], best_cost [N]); best_cost stays +inf for trajectories never found feasible."""
+    TormOptimizer::localOptimizeTSGD (torm/src/torm_optimizer.cpp:397-598) entirely on the device -- cost +
+    increments (kernels 3a / 3b), feasibility checks, the alpha_ / learning_rate_ schedule, the best-trajectory
+    bookkeeping of :506-560 (a trajectory is recorded when its evaluator cost improves and it is collision free,
+    within the velocity limits and, with use_singularity_check_, away from singularities) and the update step.
+    Every trajectory carries its own optimiser state as [N] tensors:
+      lr_schedule_mode 0  fixed weights (smoothness_update_weight_ / obstacle_update_weight_), joint_update_limit 0.1
+                       1  adaptive: alpha_ +-0.1 steps on the feasibility pattern (:447-466), learning_rate_ halved /
+                          doubled inside [lr/100, lr*1000] (:471-492), and the stage of each trajectory chosen from its
+                          own history (:400-412) -- the batch then mixes feasible and end-pose updates
+                       2  alpha_ as in 1, cosine learning rate with period maxiter / 2 (:493-496)
+                       3  alpha_ = 0.5, fixed learning rate (:467-468, :497-498)
+    Returns (best_traj [N,T,7], best_cost [N]); best_cost stays +inf for trajectories never found feasible.
+    return_state=True appends a dict with the final alpha / lr / feasibility tensors."""
     pr = self.parameters
     N = traj.shape[0]
-    best_cost = torch.full((N,), float("inf"), device=self.device, dtype=traj.dtype)
+    dev, dt = self.device, traj.dtype
+    best_cost = torch.full((N,), float("inf"), device=dev, dtype=dt)
     best_traj = traj.clone()
-    lr = pr.learning_rate_ if learning_rate is None else learning_rate
+    lr0 = float(pr.learning_rate_ if learning_rate is None else learning_rate)
+    lr_max, lr_min = lr0 * 1000.0, lr0 / 100.0                      # constructor :99-101
+    lr = torch.full((N,), lr0, device=dev, dtype=dt)
+    al = torch.full((N,), float(alpha), device=dev, dtype=dt)
+    infea_col = torch.zeros(N, dtype=torch.bool, device=dev)         # :383
+    infea_vel = torch.zeros(N, dtype=torch.bool, device=dev)
     has_scene = self.scene is not None
     zeros = None
+    mode = int(lr_schedule_mode)
+    full_mask = STAGE_SMOOTH | STAGE_POSE_GRAD | STAGE_EVAL | (STAGE_COLL if has_scene else 0)
     for it in range(maxiter):
         for stage in (0, 1):
-            feasible_stage = stage == 0
-            if feasible_stage:
-                mask = STAGE_SMOOTH | STAGE_EVAL | (STAGE_COLL if has_scene else 0)
+            # ---- stage of each trajectory (:400-412)
+            if mode == 1:
+                if stage == 0:
+                    feas_stage = ~((lr < 1e-2) & ~infea_col & ~infea_vel)
+                else:
+                    feas_stage = (lr == lr_max) & infea_col
+                mask = full_mask
             else:
-                mask = STAGE_POSE_GRAD | STAGE_EVAL
+                feas_stage = None
+                if stage == 0:
+                    mask = STAGE_SMOOTH | STAGE_EVAL | (STAGE_COLL if has_scene else 0)
+                else:
+                    mask = STAGE_POSE_GRAD | STAGE_EVAL
             r = self.cost_grad(traj, mask)
             cur_cost = r["costs"][:, 6]
-            feas = torch.ones(N, dtype=torch.bool, device=self.device)
-            if pr.use_velocity_check_:
-                feas &= r["costs"][:, 7] == 0
+            # ---- feasibility (:436-446)
             if has_scene and check_collision and pr.use_collision_check_:
-                hit = self.scene.collide(traj.reshape(-1, 7)).reshape(N, self.T)
-                feas &= hit.sum(dim=1) == 0
+                infea_col = self.scene.collide(traj.reshape(-1, 7)).reshape(N, self.T).sum(dim=1) != 0
+            else:
+                infea_col = torch.zeros(N, dtype=torch.bool, device=dev)
+            if pr.use_velocity_check_:
+                infea_vel = r["costs"][:, 7] != 0
+            else:
+                infea_vel = torch.zeros(N, dtype=torch.bool, device=dev)
+            # ---- alpha_ (:447-469)
+            if mode in (1, 2):
+                only_col, only_vel = infea_col & ~infea_vel, ~infea_col & infea_vel
+                up = torch.where(al < 0.5, torch.full_like(al, 0.5), torch.clamp(al + 0.1, max=1.0))
+                down = torch.where(al > 0.5, torch.full_like(al, 0.5), torch.clamp(al - 0.1, min=0.0))
+                al = torch.where(only_col, up, torch.where(only_vel, down, torch.full_like(al, 0.5)))
+            elif mode == 3:
+                al = torch.full_like(al, 0.5)
+            # ---- learning_rate_ (:471-499)
+            if mode == 1:
+                ok = ~infea_col & ~infea_vel
+                shrink = torch.where(lr > lr0, torch.full_like(lr, lr0), torch.clamp(lr / 2.0, min=lr_min))
+                lr = torch.where(ok, shrink, torch.clamp(lr * 2.0, max=lr_max))
+            elif mode == 2:
+                period = max(maxiter // 2, 1)
+                ph = float(it % period) / period
+                lr = torch.full_like(lr, lr_min + 0.5 * (lr_max - lr_min) * (1.0 + np.cos(ph * np.pi)))
+            elif mode == 3:
+                lr = torch.full_like(lr, lr0)
+            # ---- best trajectory (:506-560)
+            feas = ~infea_col & ~infea_vel
+            if pr.use_singularity_check_:
+                from .pirl_env import manipulability
+                yosh = manipulability(traj[:, 1:].reshape(-1, 7)).reshape(N, self.T - 1)
+                feas &= ~(yosh.abs() < pr.singularity_lower_bound_).any(dim=1)
             better = feas & (cur_cost < best_cost)
             best_cost = torch.where(better, cur_cost, best_cost)
             best_traj = torch.where(better[:, None, None], traj, best_traj)
-            if feasible_stage:
-                inc_c = r["inc_coll"]
-                if inc_c is None:
-                    if zeros is None:
-                        zeros = torch.zeros_like(r["inc_smooth"])
-                    inc_c = zeros
-                self.applyIncrements(traj, True, r["inc_smooth"], inc_c, None, alpha, lr, lr_schedule_mode=3)
+            # ---- increments -> trajectory (:562-576)
+            inc_c = r["inc_coll"]
+            if inc_c is None and (mode == 1 or stage == 0):
+                if zeros is None:
+                    zeros = torch.zeros(N, self.T - 1, 7, device=dev, dtype=dt)
+                inc_c = zeros
+            if mode == 1:
+                self.applyIncrements(traj, True, r["inc_smooth"], inc_c, r["inc_pose"], al, lr, lr_schedule_mode=mode,
+                                     stage_idx=(~feas_stage).to(torch.int32))
+            elif stage == 0:
+                self.applyIncrements(traj, True, r["inc_smooth"], inc_c, None, al, lr, lr_schedule_mode=mode)
             else:
-                self.applyIncrements(traj, False, inc_pose=r["inc_pose"], lr_schedule_mode=3)
+                self.applyIncrements(traj, False, inc_pose=r["inc_pose"], alpha=al, learning_rate=lr, lr_schedule_mode=mode)
+    if return_state:
+        return best_traj, best_cost, dict(alpha=al, learning_rate=lr, infea_col=infea_col, infea_vel=infea_vel)
     return best_traj, best_cost
 
 

@@ -1,0 +1,115 @@
+"""TormBatch.localOptimizeTSGD for every lr_schedule_mode_ (0 fixed weights, 1 adaptive + per-trajectory stage, 2 cosine,
+3 fixed) against a literal scalar replay of TormOptimizer::localOptimizeTSGD (torm/src/torm_optimizer.cpp:381-598) run
+one trajectory at a time on the CPU oracle.  FP64 build; the replay and the batch must take the same decisions
+(stage, alpha_, learning_rate_, best-trajectory records) and end on the same trajectories to 1e-7."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def make_problem(N, T, seed, cuda_device, grid=(64, 96, 64), origin=(-0.3, -0.96, 0.0), res=0.025):
+    from oracle import oracle as O
+    from rlitg_b200 import fetch, scene as S, synth
+    traj = synth.linear_trajectories(N, T, seed=seed, noise=0.03)
+    targets = np.round(synth.random_ee_paths(1, T, seed=seed + 1)[0], 6)
+    occ, _ = synth.random_box_scene(grid, origin, res, seed=seed, n_clutter=3)
+    link, center, radius = fetch.default_spheres()
+    osc = O.Scene(O.build_field(occ, res, 1.0), origin, res, link, center, radius)
+    gsc = S.Scene(cuda_device)
+    gsc.set_occupancy(occ, origin, res, 1.0)
+    return traj, targets, osc, gsc
+
+
+def replay_one(traj, targets, osc, op, Aband, Ainv, pr, maxiter, mode, T):
+    """The reference loop for ONE trajectory with scalar state, on the oracle."""
+    from oracle import oracle as O
+    from rlitg_b200 import fetch
+    traj = traj.copy()
+    lr0 = pr.learning_rate_
+    lr, lr_max, lr_min = lr0, lr0 * 1000.0, lr0 / 100.0
+    alpha = 0.5
+    infea_col = infea_vel = False
+    best_cost, best_traj = np.inf, traj.copy()
+    log = []
+    limit = 0.1 if mode == 0 else pr.joint_update_limit_
+    for it in range(maxiter):
+        for stage in (0, 1):
+            if stage == 0:
+                feasible_stage = not (mode == 1 and lr < 1e-2 and not infea_col and not infea_vel)
+            else:
+                feasible_stage = (mode == 1 and lr == lr_max and infea_col)
+            mask = (O.STAGE_SMOOTH | O.STAGE_COLL | O.STAGE_EVAL) if feasible_stage else (O.STAGE_POSE_GRAD | O.STAGE_EVAL)
+            r = O.torm_cost_grad(traj[None], targets, osc, op, Aband, mask)
+            cur = r["costs"][0, 6]
+            infea_col = bool(O.sphere_collide(traj, osc, fetch.BASE_OFFSET).any())
+            infea_vel = bool(r["costs"][0, 7] != 0)
+            if mode in (1, 2):
+                if not infea_col and not infea_vel:
+                    alpha = 0.5
+                elif infea_col and not infea_vel:
+                    alpha = 0.5 if alpha < 0.5 else min(alpha + 0.1, 1.0)
+                elif not infea_col and infea_vel:
+                    alpha = 0.5 if alpha > 0.5 else max(alpha - 0.1, 0.0)
+                else:
+                    alpha = 0.5
+            elif mode == 3:
+                alpha = 0.5
+            if mode == 1:
+                if not infea_col and not infea_vel:
+                    lr = lr0 if lr > lr0 else max(lr / 2.0, lr_min)
+                else:
+                    lr = min(lr * 2.0, lr_max)
+            elif mode == 2:
+                period = maxiter // 2
+                ph = float(it % period) / period
+                lr = lr_min + 0.5 * (lr_max - lr_min) * (1 + np.cos(ph * np.pi))
+            elif mode == 3:
+                lr = lr0
+            if best_cost > cur and not infea_col and not infea_vel:
+                best_cost, best_traj = cur, traj.copy()
+            log.append((int(feasible_stage), alpha, lr, infea_col, infea_vel))
+            traj = O.torm_update(traj[None], Ainv, 0 if feasible_stage else 1, mode, r["inc_smooth"], r["inc_coll"],
+                                 r["inc_pose"], alpha, lr, sw=pr.smoothness_update_weight_ / T,
+                                 ow=pr.obstacle_update_weight_, limit=limit)[0]
+    return traj, best_traj, best_cost, log
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_lockstep_schedule_matches_scalar_replay(cuda_device, mode):
+    import torch
+    from oracle import oracle as O
+    from rlitg_b200 import torm as TM
+    N, T, maxiter = 6, 30, 6
+    traj, targets, osc, gsc = make_problem(N, T, 21, cuda_device)
+    rng = np.random.default_rng(2)
+    # a spread of situations: clean tracking starts, one far too fast (velocity violation), one through the table
+    base = O.fk_quat(traj[0])
+    targets = np.round(base, 6)
+    for n in range(N):
+        traj[n] = traj[0] + (rng.normal(0, 0.01 * (n + 1), size=(T, 7)) if n else 0.0)
+        traj[n, 0] = traj[0, 0]
+    traj[4, 1:, 0] += np.linspace(0, 1.4, T - 1) * np.where(np.arange(T - 1) % 2, 1, -1) * 0.2   # zig-zag: too fast
+    pr = TM.TormParameters(min_clearence_=0.3, learning_rate_=0.02)
+    op = O.torm_params(T, dt=pr.time_duration_, clearance=0.3)
+    Aband, _, Ainv = O.smooth_setup(T, pr.time_duration_, (1.0, 0.0, 0.0), 0.0, want_inverse=True)
+    tb = TM.TormBatch(targets, pr, gsc, cuda_device, torch.float64)
+    t = torch.tensor(traj, dtype=torch.float64, device=cuda_device)
+    best_traj, best_cost, state = tb.localOptimizeTSGD(t, maxiter, lr_schedule_mode=mode, return_state=True)
+    final = t.cpu().numpy()
+    seen_stage_mix = False
+    for n in range(N):
+        ftraj, btraj, bcost, log = replay_one(traj[n], targets, osc, op, Aband, Ainv, pr, maxiter, mode, T)
+        assert np.abs(final[n] - ftraj).max() < 1e-7, (mode, n, np.abs(final[n] - ftraj).max())
+        assert abs(float(state["alpha"][n]) - log[-1][1]) < 1e-12 and abs(float(state["learning_rate"][n]) - log[-1][2]) < 1e-12 * max(1, log[-1][2])
+        assert bool(state["infea_col"][n]) == log[-1][3] and bool(state["infea_vel"][n]) == log[-1][4]
+        if np.isfinite(bcost):
+            assert abs(float(best_cost[n]) - bcost) < 1e-9 * max(1.0, bcost)
+            assert np.abs(best_traj[n].cpu().numpy() - btraj).max() < 1e-7
+        else:
+            assert not np.isfinite(float(best_cost[n]))
+        stages = [l[0] for l in log]
+        seen_stage_mix |= stages[0::2] != [1] * maxiter or stages[1::2] != [0] * maxiter
+    if mode == 1:
+        assert seen_stage_mix, "mode 1 should make some trajectory leave the plain feasible / end-pose alternation"
+    gsc.close()
