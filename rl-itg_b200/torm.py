@@ -389,6 +389,45 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
 TormBatch.localOptimizeTSGD = _local_optimize_tsgd
 
 
+def _iterative_exploration(self, init_trajs, new_trajectories=None, max_epochs=1, lr_schedule_mode=0,
+                           return_threshold=-1.0, planning_time_limit=None, check_collision=True):
+    """TormOptimizer::iterativeExploration (torm/src/torm_optimizer.cpp:604-688) with the restarts as the batch axis:
+    every row of `init_trajs` [N,T,7] is one optimiser's initial trajectory (Greedy / Linear initialiser, PIRL roll-out,
+    ...).  Per epoch: localOptimizeTSGD(exploration_iter_) on all N (:634), stop when the wall clock passes
+    `planning_time_limit` (:635) or any best cost is below `return_threshold` (:644-647), else replace the working
+    trajectories by `new_trajectories(epoch) -> [N,T,7]` (the reference draws a new initial trajectory, :649-660) and go
+    on; every optimiser keeps its best trajectory across epochs (best_trajectory_backup_cost_).  With
+    new_trajectories=None this is `only_first`.  Returns dict(best_traj [N,T,7], best_cost [N], success [N] bool,
+    argmin int, epochs int)."""
+    import time as _time
+    pr = self.parameters
+    traj = init_trajs.clone()
+    N = traj.shape[0]
+    best_cost = torch.full((N,), float("inf"), device=self.device, dtype=traj.dtype)
+    best_traj = traj.clone()
+    t0 = _time.perf_counter()
+    epochs = 0
+    for eph in range(max_epochs):
+        bt, bc = self.localOptimizeTSGD(traj, pr.exploration_iter_, lr_schedule_mode=lr_schedule_mode,
+                                        check_collision=check_collision)
+        better = bc < best_cost
+        best_cost = torch.where(better, bc, best_cost)
+        best_traj = torch.where(better[:, None, None], bt, best_traj)
+        epochs = eph + 1
+        if planning_time_limit is not None and _time.perf_counter() - t0 > planning_time_limit:
+            break
+        if return_threshold != -1 and bool((best_cost < return_threshold).any()):
+            break
+        if new_trajectories is None or eph + 1 >= max_epochs:
+            break
+        traj = new_trajectories(eph + 1).to(self.device, traj.dtype).contiguous().clone()
+    return dict(best_traj=best_traj, best_cost=best_cost, success=torch.isfinite(best_cost),
+                argmin=int(torch.argmin(best_cost).item()), epochs=epochs)
+
+
+TormBatch.iterativeExploration = _iterative_exploration
+
+
 lib.rlitg_torm_cost_grad_host.argtypes = [_vp, _vp, C.c_int64, C.c_int, _vp, _vp, C.POINTER(RlitgTormParams), C.c_int, _vp,
                                           _vp, _vp, _vp, _vp]
 

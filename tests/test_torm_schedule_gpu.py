@@ -113,3 +113,32 @@ def test_lockstep_schedule_matches_scalar_replay(cuda_device, mode):
     if mode == 1:
         assert seen_stage_mix, "mode 1 should make some trajectory leave the plain feasible / end-pose alternation"
     gsc.close()
+
+
+def test_iterative_exploration_restarts_as_batch(cuda_device, init_traj):
+    """iterativeExploration with the restarts as the batch axis on the reference's `zig` problem: the per-optimiser best
+    over two epochs equals the better of two separate TSGD runs, the early-return threshold stops after one epoch."""
+    import torch
+    from rlitg_b200 import torm as TM
+    path = init_traj["zig_path"]
+    a, b = init_traj["zig_torm_jli_test"], init_traj["zig_pirl_bc_test"]
+    rng = np.random.default_rng(0)
+    first = np.stack([a, b, a + np.r_[np.zeros((1, 7)), rng.normal(0, 0.02, size=(a.shape[0] - 1, 7))]])
+    second = np.stack([b, a, b])
+    pr = TM.TormParameters(min_clearence_=0.001, exploration_iter_=8)
+    tb = TM.TormBatch(path, pr, None, cuda_device, torch.float64)
+    g = lambda x: torch.tensor(x, dtype=torch.float64, device=cuda_device)
+    out = tb.iterativeExploration(g(first), new_trajectories=lambda eph: g(second), max_epochs=2, lr_schedule_mode=3)
+    assert out["epochs"] == 2 and bool(out["success"].all())
+    _, c1 = tb.localOptimizeTSGD(g(first), 8, lr_schedule_mode=3)
+    _, c2 = tb.localOptimizeTSGD(g(second), 8, lr_schedule_mode=3)
+    want = torch.minimum(c1, c2)
+    assert torch.allclose(out["best_cost"], want, rtol=1e-12, atol=0)
+    assert out["argmin"] == int(torch.argmin(want))
+    got_cost = tb.getWeightedPoseCost(out["best_traj"])
+    assert torch.allclose(got_cost, out["best_cost"], rtol=1e-9)   # the recorded rows are the ones with that cost
+    early = tb.iterativeExploration(g(first), new_trajectories=lambda eph: g(second), max_epochs=5, lr_schedule_mode=3,
+                                    return_threshold=1.0)
+    assert early["epochs"] == 1
+    only_first = tb.iterativeExploration(g(first), max_epochs=5, lr_schedule_mode=3)
+    assert only_first["epochs"] == 1 and torch.allclose(only_first["best_cost"], c1, rtol=1e-12)
