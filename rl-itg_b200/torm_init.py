@@ -37,7 +37,7 @@ def simplified_points(T: int, gap: int = 10):
 def fill_in_linear_interpolation(start_conf, goal_confs, num: int, continuous=fetch.CONTINUOUS):
     """fillInLinearInterpolation (:784-807) for C goals at once: rows 1..num of [C, num+1, 7] (row 0 = start).
     Continuous joints take the short way round."""
-    st = start_conf.reshape(1, 7)
+    st = start_conf.reshape(-1, 7)  # one start for all goals, or one per goal
     diff = goal_confs - st
     cj = torch.as_tensor(np.asarray(continuous, dtype=bool), device=goal_confs.device).reshape(1, 7)
     two_pi = 2 * np.pi
@@ -45,7 +45,7 @@ def fill_in_linear_interpolation(start_conf, goal_confs, num: int, continuous=fe
     diff = torch.where(cj & (diff.abs() > np.pi), wrapped, diff)
     theta = diff / float(num)
     t = torch.arange(0, num + 1, device=goal_confs.device, dtype=goal_confs.dtype).reshape(1, num + 1, 1)
-    return st.reshape(1, 1, 7) + t * theta.reshape(-1, 1, 7)
+    return st.reshape(-1, 1, 7) + t * theta.reshape(-1, 1, 7)
 
 
 class SegmentScorer:
@@ -123,6 +123,38 @@ class TrajectoryInitializer:
         costs = self.scorer.score(segs, self.endPoses_desired_)
         idx, best = self.scorer.select(costs, self.T)
         return segs[idx.long()[0]].clone(), idx, best
+
+
+def set_pirl_trajectory(end_poses, start_confs, policy, obsType="Conf+LinkPoses", t=1, gap=10, batch=None,
+                        device="cuda:0", dtype=torch.float32):
+    """TormOptimizer::setPIRLTrajectory (torm/src/torm_optimizer.cpp:898-936) for B start configurations of one problem
+    at once (interpolation_mode_ 2, the RL-ITG initial trajectory): PirlInterpolator::interpolate
+    (torm/src/pirl_interpolator.cpp:102-140, multi_action = 1) rolls the policy out over the simplified points -- one
+    fused env step per point for all B -- the generated configurations become the rows at the simplified points
+    (:922), fillInLinearInterpolation (:784-807) fills the rows between them, and handleJointLimits (:934) is applied
+    when a TormBatch for the same problem is passed as `batch`.  `policy(obs [B,O] float32) -> action [B,7]`.
+    Returns trajectories [B,T,7] (row 0 = start configuration)."""
+    device = torch.device(device)
+    poses = torch.as_tensor(end_poses).to(device, dtype).contiguous()
+    T = int(poses.shape[0])
+    sp = simplified_points(T, gap)
+    st = torch.as_tensor(start_confs).to(device, dtype).reshape(-1, 7).contiguous()
+    B = st.shape[0]
+    # the env indexes its path from the start pose: row 0 = first target pose, rows 1.. = the simplified points
+    path = torch.cat([poses[:1], poses[torch.as_tensor(sp, device=device)]], dim=0)
+    env = pirl_env.PirlVecEnv(B, rewardType="Task", obsType=obsType, t=t, zDim=0, device=device, dtype=dtype)
+    env.set_problems(path.unsqueeze(0).expand(B, -1, -1).contiguous(), None, np.full(B, len(sp), dtype=np.int32))
+    gen = pirl_env.rollout_policy(env, policy, start_conf=st, n_steps=len(sp))   # [B, S, 7]
+    traj = torch.empty(B, T, 7, device=device, dtype=dtype)
+    traj[:, 0] = st
+    start_point = 0
+    for i, s_i in enumerate(sp):
+        seg = fill_in_linear_interpolation(traj[:, start_point], gen[:, i], s_i - start_point)
+        traj[:, start_point + 1:s_i + 1] = seg[:, 1:]   # the fill rewrites the goal row too: start + num * theta (:803-805)
+        start_point = s_i
+    if batch is not None:
+        batch.applyIncrements(traj, False, inc_pose=torch.zeros(B, T - 1, 7, device=device, dtype=dtype))
+    return traj
 
 
 def dls_ik_candidates(target_pose, n, seed=0, iters=60, step_limit=0.3, tol_pos=1e-4, tol_rot=1e-3, device="cuda:0",

@@ -92,3 +92,51 @@ def test_dls_ik_candidates(cuda_device):
     tw = O.pose_diff(sol, np.tile(target, (sol.shape[0], 1)))
     assert np.abs(tw[:, :3]).max() < 2e-4 and np.abs(tw[:, 3:]).max() < 2e-3
     assert np.unique(np.round(sol, 1), axis=0).shape[0] > 3  # distinct IK branches, like random restarts give
+
+
+def test_set_pirl_trajectory_matches_scalar_replay(cuda_device):
+    """setPIRLTrajectory (torm_optimizer.cpp:898-936) for B starts at once vs a CPU loop: oracle observation -> the same
+    policy -> setAction (test mode) per simplified point, then the literal fillInLinearInterpolation."""
+    import torch
+    from oracle import oracle as O
+    from rlitg_b200 import fetch, synth, torm_init as TI
+    T, gap, B = 47, 10, 5
+    poses = np.round(synth.random_ee_paths(1, T, seed=3)[0], 6)
+    rng = np.random.default_rng(1)
+    starts = synth.random_configs(B, seed=8) * 0.5
+    W = torch.tensor(rng.normal(0, 0.05, size=(88, 7)), dtype=torch.float64, device=cuda_device)
+
+    def policy(obs):   # any deterministic map: a fixed linear layer with tanh squashing to the action limits
+        return 0.26 * torch.tanh(obs.double() @ W)
+
+    got = TI.set_pirl_trajectory(poses, starts, policy, gap=gap, device=cuda_device, dtype=torch.float64).cpu().numpy()
+    sp = TI.simplified_points(T, gap)
+    path = np.concatenate([poses[:1], poses[sp]])[None]
+    cfg = O.pirl_cfg("Task", "Conf+LinkPoses", 1, 0, train_mode=False)
+    Wc = W.cpu().numpy()
+    for b in range(B):
+        q = starts[b:b + 1].copy()
+        ts = np.zeros(1, dtype=np.int32); mts = np.full(1, len(sp), dtype=np.int32)
+        obs = O.pirl_obs(cfg, q, ts, mts, path)
+        gen = []
+        for k in range(len(sp)):
+            # the policy sees float32 observations (torm/src/pirl_interpolator.cpp:182) and emits float32 actions
+            act = (0.26 * np.tanh(obs.astype(np.float32).astype(np.float64) @ Wc)).astype(np.float32)
+            r = O.pirl_env_step(cfg, q, act, ts, mts, path, None)
+            q, ts, obs = r["q"], r["timestep"], r["obs"]
+            gen.append(q[0].copy())
+        want = np.empty((T, 7)); want[0] = starts[b]
+        s0 = 0
+        for i, g in enumerate(sp):
+            want[g] = gen[i]
+            num = g - s0
+            for j in range(7):
+                diff = want[g, j] - want[s0, j]
+                if fetch.CONTINUOUS[j] and abs(diff) > np.pi:
+                    diff = 2 * np.pi - abs(diff) if diff < 0 else -2 * np.pi + abs(diff)
+                theta = diff / num
+                for tt, row in enumerate(range(s0 + 1, g + 1), start=1):
+                    want[row, j] = want[s0, j] + tt * theta
+            s0 = g
+        assert np.abs(got[b] - want).max() < 1e-9, (b, np.abs(got[b] - want).max())
+    assert np.abs(got[:, 1:] - got[:, :-1]).max() > 1e-3
