@@ -140,3 +140,15 @@ def test_set_pirl_trajectory_matches_scalar_replay(cuda_device):
             s0 = g
         assert np.abs(got[b] - want).max() < 1e-9, (b, np.abs(got[b] - want).max())
     assert np.abs(got[:, 1:] - got[:, :-1]).max() > 1e-3
+
+
+def test_example_plan_path_runs(cuda_device):
+    """examples/plan_path.py: reference-format path file -> batched IK -> Linear initialiser -> iterativeExploration."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "examples", "plan_path.py"), "--restarts", "32", "--iters", "25"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "best restart" in r.stdout
