@@ -123,6 +123,42 @@ def run(dev, rank, world, max_over_ranks, barrier, steps=30, warmup=5):
         "hbm_note": "DRAM traffic is ~20 MB per iteration (profiles/r01_torm_final_full.json): ~2 % of HBM peak, so the FMA fraction is the relevant one",
         "target_ms": 1.0, "cpu_baseline": cpu, "shard_statistics": stats}
 
+    # ---------------------------------------------------------------- one whole TSGD iteration (both stages + update steps)
+    try:
+        tw = traj.clone()
+        alpha_v = torch.full((N,), 0.5, device=dev); lr_v = torch.full((N,), 0.01, device=dev)
+
+        def kernels_only():
+            rr = tb.cost_grad(tw, feas)
+            tb.applyIncrements(tw, True, rr["inc_smooth"], rr["inc_coll"], None, alpha_v, lr_v, lr_schedule_mode=3)
+            rr = tb.cost_grad(tw, pose)
+            tb.applyIncrements(tw, False, inc_pose=rr["inc_pose"], alpha=alpha_v, learning_rate=lr_v, lr_schedule_mode=3)
+
+        kernels_only(); torch.cuda.synchronize()
+        barrier()
+        ms_iter = max_over_ranks(_time_loop(torch, kernels_only, steps, 2))
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            kernels_only()
+        ms_iter_graph = max_over_ranks(_time_loop(torch, g.replay, steps, 2))
+        tw.copy_(traj)
+        tb.localOptimizeTSGD(tw, 2, lr_schedule_mode=3)  # first call: lazily built dilated volumes, allocator warm-up
+        tw.copy_(traj)
+        n_it = 20
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        tb.localOptimizeTSGD(tw, n_it, lr_schedule_mode=3)
+        torch.cuda.synchronize()
+        ms_loop = max_over_ranks((time.perf_counter() - t0) * 1e3 / n_it)
+        out["torm_tsgd_iteration"] = {
+            "config": {"workload": "torm_tsgd_iteration_1024x200_grid128", "trajectories_per_gpu": N, "T": T,
+                       "contents": "feasible stage (cost + increments, update step) + end-pose stage (cost + increments, update step)"},
+            "ms_kernels_eager": ms_iter, "ms_kernels_cuda_graph": ms_iter_graph,
+            "ms_localOptimizeTSGD_per_iteration": ms_loop,
+            "note": "localOptimizeTSGD adds two sphere-grid feasibility checks and the best-trajectory bookkeeping per iteration (torch glue, wall clock)",
+            "trajectory_iterations_per_s": world * N / (min(ms_iter, ms_iter_graph) * 1e-3)}
+    except Exception as e:  # noqa: BLE001
+        out["torm_tsgd_iteration"] = {"error": repr(e)}
+
     # ---------------------------------------------------------------- BASELINE config 1: the reference's own batch-1 CPU path
     # one 100-pose path, one thread, per waypoint FK + Jacobian + pose error (comparable with the reference's recorded
     # 0.003 ms per KDL FK call, pirl/script/module_topic_speed_test.py:72)

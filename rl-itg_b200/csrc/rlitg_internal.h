@@ -31,7 +31,7 @@ struct Smooth {
     double mcs = 1.0;            // max_cost_scale = max(1, scale)
     std::vector<double> band;    // [(T+10)][13], scaled quad_cost_full_
     std::vector<double> inv;     // [(T-1)][(T-1)], scaled quad_cost_inv_
-    std::vector<double> chol;    // [(T-1)][7] banded Cholesky factor of the unscaled free block
+    std::vector<double> chol;    // [2][(T-1)][8] banded Cholesky factor of the unscaled free block: forward / backward substitution rows
     double* d_band64 = nullptr;
     float* d_band32 = nullptr;
     double* d_inv64 = nullptr;

@@ -616,7 +616,25 @@ static int smooth_build(Smooth& sm, int T, double dt, const double* w3, double r
     for (auto& x : band) x *= mcs;
     for (auto& x : sm.inv) x /= mcs;
     sm.band.swap(band);
-    sm.chol.swap(L);  // Cholesky factor of the UNSCALED free block; A_scaled^-1 b = (L L^T)^-1 b / mcs
+    // Device layout of the factor of the UNSCALED free block (A_scaled^-1 b = (L L^T)^-1 b / mcs) for the column-oriented
+    // substitution of torm_update_kernel: as soon as unknown i is known it is pushed into the six rows that use it, so
+    // the only dependent operation per step is one FMA.  Two tables of F rows of 8 doubles, coefficients pre-divided
+    // by the diagonal of the row they update (entries outside the matrix are 0):
+    //   forward  row i: L(i+k,i) / L(i+k,i+k), k = 1..6 | 1 / L(i+7,i+7) | 1 / L(i,i)
+    //   backward row i: L(i,i-k) / L(i-k,i-k), k = 1..6 | 1 / L(i-7,i-7) | 1 / L(i,i)
+    std::vector<double> Lt((size_t)2 * F * 8, 0.0);
+    for (int i = 0; i < F; i++) {
+        double* fw = &Lt[(size_t)i * 8];
+        double* bw = &Lt[((size_t)F + i) * 8];
+        for (int k = 1; k <= 6; k++) {
+            if (i + k < F) fw[k - 1] = Lr(i + k, i) / Lr(i + k, i + k);
+            if (i - k >= 0) bw[k - 1] = Lr(i, i - k) / Lr(i - k, i - k);
+        }
+        if (i + 7 < F) fw[6] = 1.0 / Lr(i + 7, i + 7);
+        if (i - 7 >= 0) bw[6] = 1.0 / Lr(i - 7, i - 7);
+        fw[7] = bw[7] = 1.0 / Lr(i, i);
+    }
+    sm.chol.swap(Lt);
     sm.mcs = mcs;
     sm.T = T;
     return RLITG_OK;

@@ -42,11 +42,16 @@ __global__ void __launch_bounds__(kUpdThreads)
 torm_update_kernel(UpdP P, T* __restrict__ traj, const T* __restrict__ inc_smooth, const T* __restrict__ inc_coll,
                    const T* __restrict__ inc_pose, const T* __restrict__ alpha, const T* __restrict__ lr,
                    const double* __restrict__ chol, const double* __restrict__ inv,
-                   const int32_t* __restrict__ stage_idx) {
+                   const int32_t* __restrict__ stage_idx, int tab_in_smem) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Tn = P.Tn, F = Tn - 1, tid = threadIdx.x;
     double* fin = reinterpret_cast<double*>(smem_raw);  // [F][7] right-hand side -> final increments
-    double* tr = fin + (size_t)F * 7;                   // [F][7] free rows of the trajectory
+    // second region, [F][8] doubles: during the solve it holds ONE substitution table at a time (tab_in_smem) -- every
+    // step reads one 64-byte row, and a first-touch L2 round trip per row (a 128-byte line = two rows) was most of the
+    // solve's latency -- and afterwards the free rows of the trajectory ([F][7]).  120 F bytes per CTA in all: 24 KB
+    // at T = 200, so that a whole 1,024-trajectory batch is resident in one wave.
+    double* tr = fin + (size_t)F * 7 + (F & 1);         // (F & 1): 7 F doubles is odd for odd F; keep 16-byte alignment
+    double4* s_tab = reinterpret_cast<double4*>(tr);
     __shared__ double s_tmp[kUpdThreads / 32];
     __shared__ double s_best[kUpdThreads];
     __shared__ int s_idx[kUpdThreads];
@@ -57,7 +62,9 @@ torm_update_kernel(UpdP P, T* __restrict__ traj, const T* __restrict__ inc_smoot
     if (stage < 0) return;
     T* trow = traj + n * (int64_t)Tn * 7 + 7;  // first free row
     const size_t FD = (size_t)F * 7;
-    for (int k = tid; k < (int)FD; k += kUpdThreads) tr[k] = (double)trow[k];
+    const double4* g_tab = reinterpret_cast<const double4*>(chol);  // [2][F] rows of 2 x double4
+    if (stage == 0 && tab_in_smem)
+        for (int k = tid; k < 2 * F; k += kUpdThreads) s_tab[k] = g_tab[k];  // forward table
 
     if (stage == 0) {
         const T* s = inc_smooth + n * FD;
@@ -81,29 +88,74 @@ torm_update_kernel(UpdP P, T* __restrict__ traj, const T* __restrict__ inc_smoot
             }
         }
         __syncthreads();
-        // banded Cholesky solve per joint column: L y = b, L^T x = y ; L(i, j) at chol[i*7 + (j - i + 6)]
+        // banded Cholesky solve per joint column: L y = b, then L^T x = y.  One thread per joint.  The recurrence is
+        // the critical path (an FP64 FMA has ~40 cycles of latency here), so the substitution is column oriented: six
+        // running rows live in registers, already divided by their diagonal; once unknown i is final it is pushed
+        // into all six with independent FMAs and the first of them IS unknown i+1 -- one dependent FMA per step.
+        // Coefficient rows (smooth_build) are fetched one step ahead.
         if (tid < 7) {
             const int j = tid;
+            const double4* tab = tab_in_smem ? s_tab : g_tab;  // one row = 2 x double4
+            auto rdiag = [&](const double4* t, int r) { return t[2 * r + 1].w; };
+            auto rhs_at = [&](int r) { return (r >= 0 && r < F) ? fin[r * 7 + j] : 0.0; };
+            // ---- forward: rows 0..5 start as b_r / L(r,r); a0 is the row being finalised
+            double a0 = rhs_at(0) * rdiag(tab, 0);
+            double a1 = F > 1 ? rhs_at(1) * rdiag(tab, 1) : 0.0, a2 = F > 2 ? rhs_at(2) * rdiag(tab, 2) : 0.0;
+            double a3 = F > 3 ? rhs_at(3) * rdiag(tab, 3) : 0.0, a4 = F > 4 ? rhs_at(4) * rdiag(tab, 4) : 0.0;
+            double a5 = F > 5 ? rhs_at(5) * rdiag(tab, 5) : 0.0, a6 = F > 6 ? rhs_at(6) * rdiag(tab, 6) : 0.0;
+            double4 ca = tab[0], cb = tab[1];
+            double nb_rhs = rhs_at(7);
             for (int i = 0; i < F; i++) {
-                double acc = fin[i * 7 + j];
-                const int lo = i - 6 < 0 ? 0 : i - 6;
-                for (int k = lo; k < i; k++) acc -= chol[i * 7 + (k - i + 6)] * fin[k * 7 + j];
-                fin[i * 7 + j] = acc / chol[i * 7 + 6];
-            }
-            for (int i = F - 1; i >= 0; i--) {
-                double acc = fin[i * 7 + j];
-                const int hi = i + 6 > F - 1 ? F - 1 : i + 6;
-                for (int k = i + 1; k <= hi; k++) acc -= chol[k * 7 + (i - k + 6)] * fin[k * 7 + j];
-                fin[i * 7 + j] = acc / chol[i * 7 + 6];
+                const int in = i + 1 < F ? i + 1 : i;
+                const double4 na = tab[2 * in], nb = tab[2 * in + 1];
+                const double nrhs = rhs_at(i + 8);
+                const double y = a0;
+                fin[i * 7 + j] = y;
+                a0 = a1 - ca.x * y; a1 = a2 - ca.y * y; a2 = a3 - ca.z * y; a3 = a4 - ca.w * y; a4 = a5 - cb.x * y;
+                a5 = a6 - cb.y * y;
+                a6 = nb_rhs * cb.z;  // row i+7 enters the window: b / L(i+7,i+7)
+                ca = na; cb = nb; nb_rhs = nrhs;
             }
         }
         __syncthreads();
+        if (tab_in_smem)
+            for (int k = tid; k < 2 * F; k += kUpdThreads) s_tab[k] = g_tab[2 * F + k];  // backward table
+        __syncthreads();
+        if (tid < 7) {
+            const int j = tid;
+            auto rdiag = [&](const double4* t, int r) { return t[2 * r + 1].w; };
+            auto rhs_at = [&](int r) { return (r >= 0 && r < F) ? fin[r * 7 + j] : 0.0; };
+            // ---- backward: rows F-1 .. F-6 start as y_r / L(r,r)
+            const double4* tbk = tab_in_smem ? s_tab : g_tab + 2 * (size_t)F;
+            double a0, a1, a2, a3, a4, a5, a6, nb_rhs;
+            double4 ca, cb;
+            const int e = F - 1;
+            a0 = rhs_at(e) * rdiag(tbk, e);
+            a1 = e - 1 >= 0 ? rhs_at(e - 1) * rdiag(tbk, e - 1) : 0.0; a2 = e - 2 >= 0 ? rhs_at(e - 2) * rdiag(tbk, e - 2) : 0.0;
+            a3 = e - 3 >= 0 ? rhs_at(e - 3) * rdiag(tbk, e - 3) : 0.0; a4 = e - 4 >= 0 ? rhs_at(e - 4) * rdiag(tbk, e - 4) : 0.0;
+            a5 = e - 5 >= 0 ? rhs_at(e - 5) * rdiag(tbk, e - 5) : 0.0; a6 = e - 6 >= 0 ? rhs_at(e - 6) * rdiag(tbk, e - 6) : 0.0;
+            ca = tbk[2 * e]; cb = tbk[2 * e + 1];
+            nb_rhs = rhs_at(e - 7);
+            for (int i = e; i >= 0; i--) {
+                const int in = i > 0 ? i - 1 : 0;
+                const double4 na = tbk[2 * in], nb = tbk[2 * in + 1];
+                const double nrhs = rhs_at(i - 8);
+                const double x = a0;
+                fin[i * 7 + j] = x;
+                a0 = a1 - ca.x * x; a1 = a2 - ca.y * x; a2 = a3 - ca.z * x; a3 = a4 - ca.w * x; a4 = a5 - cb.x * x;
+                a5 = a6 - cb.y * x;
+                a6 = nb_rhs * cb.z;  // row i-7 enters the window
+                ca = na; cb = nb; nb_rhs = nrhs;
+            }
+        }
+        __syncthreads();  // the table region is free again
         const double rate = (double)lr[n] / P.mcs;
         for (int k = tid; k < (int)FD; k += kUpdThreads) fin[k] *= rate;
     } else {
         const T* p = inc_pose + n * FD;
         for (int k = tid; k < (int)FD; k += kUpdThreads) fin[k] = (double)p[k];
     }
+    for (int k = tid; k < (int)FD; k += kUpdThreads) tr[k] = (double)trow[k];
     __syncthreads();
 
     // ---- addIncrementsToTrajectory :1611-1639
@@ -175,15 +227,19 @@ static int launch_update(const RlitgTormUpdate* u, const RlitgTormParams* p, con
     P.sw = u->smoothness_update_weight; P.ow = u->obstacle_update_weight; P.limit = u->joint_update_limit;
     P.mcs = sm->mcs;
     for (int j = 0; j < 7; j++) { P.cj[j] = p->cjoint[j]; P.jmin[j] = u->joint_min[j]; P.jmax[j] = u->joint_max[j]; }
-    const size_t smem = sizeof(double) * 2 * (size_t)(p->T - 1) * 7;
+    const size_t F = (size_t)(p->T - 1);
+    size_t smem = sizeof(double) * 2 * F * 7;
     if (smem > 200 * 1024) return set_error(RLITG_ERR_SHAPE, "T too large for the update step's shared-memory tile");
+    const size_t smem_tab = sizeof(double) * (F * 7 + (F & 1) + F * 8);
+    const int tab_in_smem = smem_tab <= 200 * 1024;  // longer paths read the tables through L1 / L2
+    smem = tab_in_smem ? smem_tab : smem + 8;
     auto kern = torm_update_kernel<T>;
     {
         int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "torm_update_kernel");
         if (rc_attr) return rc_attr;
     }
     kern<<<(unsigned)N, kUpdThreads, smem, st>>>(P, traj, inc_smooth, inc_coll, inc_pose, alpha, lr, sm->d_chol, sm->d_inv64,
-                                                 stage_idx);
+                                                 stage_idx, tab_in_smem);
     return check_launch("torm_update_kernel");
 }
 
