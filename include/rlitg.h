@@ -288,6 +288,29 @@ RLITG_API int rlitg_torm_update_staged(void* traj, int64_t N, int dtype, const R
                                        const void* inc_smooth, const void* inc_coll, const void* inc_pose,
                                        const void* alpha, const void* lr, void* stream);
 
+/* Optimiser state of TormOptimizer::localOptimizeTSGD between a cost evaluation and the update step, for N trajectories
+ * in lock step (one launch instead of the reference's scalar control flow, torm/src/torm_optimizer.cpp:400-560):
+ *   stage_idx [N] int32 out (nullable): lr_schedule_mode_ 1 stage choice (:400-412) from the state BEFORE this call,
+ *     0 = feasible, 1 = end-pose -- feed it to rlitg_torm_update_staged;
+ *   infea_col / infea_vel [N] uint8 in/out: isCurrentTrajectoryCollisionFree (:436-440, any of hits [N*T], the
+ *     per-waypoint flags of rlitg_sphere_grid_collide; NULL or use_collision_check = 0 -> feasible) and
+ *     checkJointVelocityLimit (:441-445, costs[:,7] != 0);
+ *   alpha, lr [N] in/out: alpha_ (:447-469) and learning_rate_ (:471-499); lr_iter (device scalar, nullable) is the
+ *     cosine-schedule value of this iteration for mode 2 (a device value so that a captured CUDA graph can be replayed);
+ *   best_cost [N], best_traj [N,T,7] in/out: best_trajectory_backup_cost_ / best_trajectory_ (:506-560), recorded when
+ *     costs[:,6] improves and the trajectory is feasible and not flagged in singular [N] uint8 (nullable). */
+typedef struct RlitgTormSchedule {
+    int32_t lr_schedule_mode;   /* 0..3 */
+    int32_t stage;              /* which half of the iteration this is: 0 (after :400-405) or 1 (:406-411) */
+    int32_t use_collision_check, use_velocity_check;
+    double learning_rate;       /* parameters_->learning_rate_ */
+    double learning_rate_min, learning_rate_max; /* / 100 and * 1000 (:99-101) */
+} RlitgTormSchedule;
+RLITG_API int rlitg_torm_bookkeep(const void* traj, void* best_traj, int64_t N, int T, int dtype, const void* costs,
+                                  const uint8_t* hits, const uint8_t* singular, void* alpha, void* lr,
+                                  uint8_t* infea_col, uint8_t* infea_vel, void* best_cost, int32_t* stage_idx,
+                                  const void* lr_iter, const RlitgTormSchedule* sch, void* stream);
+
 /* Candidate selection of the Greedy / Linear initialisers: replays the sequential rule of
  * TormOptimizer::getNewTrajectory (torm/src/torm_optimizer.cpp:973-1003; same at :1066-1096) over C scored
  * candidates: eCost = ([8] + rot_scale [9]) / (Tseg - 1) (ranged getEndPoseCost :1427-1446), candidates with

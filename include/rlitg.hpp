@@ -379,42 +379,52 @@ class TormBatchOptimizer {
     void setAlpha(float a) { alpha_.upload(std::vector<float>((size_t)N_, a)); }
     void setLearningRate(float lr) { lr_.upload(std::vector<float>((size_t)N_, lr)); }
 
-    // Loop body of TormOptimizer::localOptimizeTSGD (:397-598) with lr_schedule_mode_ == 3, in lock step over the N
-    // trajectories; best-trajectory bookkeeping of :506-560 (recorded when the evaluator cost improves and the
-    // trajectory is collision free and within the velocity limits).  Returns best cost per trajectory (+inf if never
-    // feasible); getBestTrajectories() holds the rows.
-    std::vector<double> localOptimizeTSGD(int maxiter) {
-        std::vector<double> best_cost((size_t)N_, std::numeric_limits<double>::infinity());
+    // TormOptimizer::localOptimizeTSGD (:397-598) in lock step over the N trajectories, entirely on the device: per
+    // half-iteration one cost call, the sphere-grid feasibility flags, rlitg_torm_bookkeep (stage choice of
+    // lr_schedule_mode_ 1, alpha_ / learning_rate_ schedule, best-trajectory record of :506-560) and the update step.
+    // Returns the best cost per trajectory (+inf if never feasible); getBestTrajectories() holds the rows.
+    std::vector<double> localOptimizeTSGD(int maxiter, int lr_schedule_mode = 3) {
+        const float inf = std::numeric_limits<float>::infinity();
+        best_cost_.upload(std::vector<float>((size_t)N_, inf));
         check(rlitg_copy_d2d(best_.data(), traj_.data(), traj_.size() * sizeof(float), nullptr));
+        alpha_.upload(std::vector<float>((size_t)N_, 0.5f));
+        lr_.upload(std::vector<float>((size_t)N_, (float)par_.learning_rate_));
+        infea_col_.resize((size_t)N_); infea_col_.zero();
+        infea_vel_.resize((size_t)N_); infea_vel_.zero();
+        stage_idx_.resize((size_t)N_);
+        lr_iter_.resize(1);
+        const bool check_col = scene_ && par_.use_collision_check_;
+        const double lr0 = par_.learning_rate_, lr_max = lr0 * 1000.0, lr_min = lr0 / 100.0;
+        const int full = RLITG_STAGE_SMOOTH | RLITG_STAGE_POSE_GRAD | RLITG_STAGE_EVAL | (scene_ ? RLITG_STAGE_COLL : 0);
         for (int it = 0; it < maxiter; it++) {
+            if (lr_schedule_mode == 2) {
+                const int period = maxiter / 2 > 0 ? maxiter / 2 : 1;
+                const double ph = (double)(it % period) / period;
+                const float v = (float)(lr_min + 0.5 * (lr_max - lr_min) * (1.0 + std::cos(ph * 3.14159265358979323846)));
+                lr_iter_.upload(&v, 1);
+            }
             for (int stage = 0; stage < 2; stage++) {
-                if (stage == 0)
-                    run(RLITG_STAGE_SMOOTH | RLITG_STAGE_EVAL | (scene_ ? RLITG_STAGE_COLL : 0));
-                else
-                    run(RLITG_STAGE_POSE_GRAD | RLITG_STAGE_EVAL);
-                const auto c = costs();
-                std::vector<uint8_t> hit;
-                if (scene_ && par_.use_collision_check_) {
+                if (lr_schedule_mode == 1) run(full);
+                else if (stage == 0) run(RLITG_STAGE_SMOOTH | RLITG_STAGE_EVAL | (scene_ ? RLITG_STAGE_COLL : 0));
+                else run(RLITG_STAGE_POSE_GRAD | RLITG_STAGE_EVAL);
+                if (check_col)
                     check(rlitg_sphere_grid_collide(traj_.data(), N_ * T_, RLITG_F32, scene_->handle(), cp_.base_off,
                                                     hits_.data(), nullptr));
-                    hit = hits_.download();
-                }
-                for (int64_t n = 0; n < N_; n++) {
-                    bool feasible = !(par_.use_velocity_check_ && c[n * RLITG_TORM_NCOST + 7] != 0.f);
-                    if (feasible && !hit.empty())
-                        for (int i = 0; i < T_ && feasible; i++) feasible = hit[(size_t)n * T_ + i] == 0;
-                    const double cur = c[n * RLITG_TORM_NCOST + 6];
-                    if (feasible && cur < best_cost[n]) {
-                        best_cost[n] = cur;
-                        const size_t off = (size_t)n * T_ * 7;
-                        check(rlitg_copy_d2d(best_.data() + off, traj_.data() + off, (size_t)T_ * 7 * sizeof(float), nullptr));
-                    }
-                }
-                update(stage, 3);
+                RlitgTormSchedule sch;
+                std::memset(&sch, 0, sizeof(sch));
+                sch.lr_schedule_mode = lr_schedule_mode; sch.stage = stage;
+                sch.use_collision_check = check_col; sch.use_velocity_check = par_.use_velocity_check_;
+                sch.learning_rate = lr0; sch.learning_rate_min = lr_min; sch.learning_rate_max = lr_max;
+                check(rlitg_torm_bookkeep(traj_.data(), best_.data(), N_, T_, RLITG_F32, costs_.data(),
+                                          check_col ? hits_.data() : nullptr, nullptr, alpha_.data(), lr_.data(),
+                                          infea_col_.data(), infea_vel_.data(), best_cost_.data(),
+                                          lr_schedule_mode == 1 ? stage_idx_.data() : nullptr,
+                                          lr_schedule_mode == 2 ? lr_iter_.data() : nullptr, &sch, nullptr));
+                update(stage, lr_schedule_mode, lr_schedule_mode == 1 ? stage_idx_.data() : nullptr);
             }
         }
-        check(rlitg_stream_sync(nullptr));
-        return best_cost;
+        const std::vector<float> bc = best_cost_.download();
+        return std::vector<double>(bc.begin(), bc.end());
     }
 
     std::vector<float> costs() const { return costs_.download(); }
@@ -438,7 +448,7 @@ class TormBatchOptimizer {
                                    smoothness_increments_.data(), collision_increments_.data(),
                                    endPose_increments_.data(), costs_.data(), nullptr, nullptr));
     }
-    void update(int stage, int lr_schedule_mode) {
+    void update(int stage, int lr_schedule_mode, const int32_t* stage_idx_dev = nullptr) {
         RlitgTormUpdate u;
         std::memset(&u, 0, sizeof(u));
         u.stage = stage;
@@ -447,9 +457,14 @@ class TormBatchOptimizer {
         u.obstacle_update_weight = par_.obstacle_update_weight_;
         u.joint_update_limit = lr_schedule_mode == 0 ? 0.1 : par_.joint_update_limit_;  // ctor override :104-106
         for (int k = 0; k < 7; k++) { u.joint_min[k] = par_.joint_min[k]; u.joint_max[k] = par_.joint_max[k]; }
-        check(rlitg_torm_update(traj_.data(), N_, RLITG_F32, joint_costs_.handle(), &cp_, &u,
-                                smoothness_increments_.data(), collision_increments_.data(),
-                                endPose_increments_.data(), alpha_.data(), lr_.data(), nullptr));
+        if (stage_idx_dev)
+            check(rlitg_torm_update_staged(traj_.data(), N_, RLITG_F32, joint_costs_.handle(), &cp_, &u, stage_idx_dev,
+                                           smoothness_increments_.data(), collision_increments_.data(),
+                                           endPose_increments_.data(), alpha_.data(), lr_.data(), nullptr));
+        else
+            check(rlitg_torm_update(traj_.data(), N_, RLITG_F32, joint_costs_.handle(), &cp_, &u,
+                                    smoothness_increments_.data(), collision_increments_.data(),
+                                    endPose_increments_.data(), alpha_.data(), lr_.data(), nullptr));
     }
 
     int64_t N_;
@@ -460,7 +475,9 @@ class TormBatchOptimizer {
     RlitgTormParams cp_;
     DeviceArray<float> targets_, traj_, best_, smoothness_increments_, collision_increments_, endPose_increments_, costs_,
         alpha_, lr_;
-    DeviceArray<uint8_t> hits_;
+    DeviceArray<float> best_cost_, lr_iter_;
+    DeviceArray<uint8_t> hits_, infea_col_, infea_vel_;
+    DeviceArray<int32_t> stage_idx_;
 };
 
 // ---- PIRL path-wise IK environment --------------------------------------------------------------------------

@@ -24,198 +24,229 @@ struct UpdP {
     double jmin[7], jmax[7];
 };
 
-constexpr int kUpdThreads = 64;
+constexpr int kUpdGroup = 64;  // threads that work on one trajectory
 
-__device__ __forceinline__ double block_max(double v, double* s_tmp) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) s_tmp[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double r = s_tmp[0];
-    for (int w = 1; w < kUpdThreads / 32; w++) r = fmax(r, s_tmp[w]);
-    return r;
+// barrier over the 64 threads of one trajectory's group (hardware barrier 1 + group; 0 is __syncthreads)
+__device__ __forceinline__ void group_sync(int g) {
+    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(kUpdGroup) : "memory");
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kUpdThreads)
-torm_update_kernel(UpdP P, T* __restrict__ traj, const T* __restrict__ inc_smooth, const T* __restrict__ inc_coll,
-                   const T* __restrict__ inc_pose, const T* __restrict__ alpha, const T* __restrict__ lr,
-                   const double* __restrict__ chol, const double* __restrict__ inv,
+__device__ __forceinline__ double group_max(double v, double* s_tmp, int g, int gt) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    group_sync(g);
+    if ((gt & 31) == 0) s_tmp[gt >> 5] = v;
+    group_sync(g);
+    return fmax(s_tmp[0], s_tmp[1]);
+}
+
+// PER trajectories per CTA, 64 threads each.  Everything but the banded solve is done by a trajectory's own group
+// with group barriers.  The solve is one thread per (trajectory, joint) and bound by the FP64 pipe's issue rate once
+// several CTAs share an SM (a warp-wide FP64 instruction costs the same for 7 active lanes as for 32), so the
+// 7 x PER solves of a CTA are packed into the lanes of warp 0: PER = 4 -> 28 lanes per FP64 instruction.
+template <typename T, int PER>
+__global__ void __launch_bounds__(kUpdGroup * PER)
+torm_update_kernel(UpdP P, T* __restrict__ traj, int64_t N, const T* __restrict__ inc_smooth,
+                   const T* __restrict__ inc_coll, const T* __restrict__ inc_pose, const T* __restrict__ alpha,
+                   const T* __restrict__ lr, const double* __restrict__ chol, const double* __restrict__ inv,
                    const int32_t* __restrict__ stage_idx, int tab_in_smem) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Tn = P.Tn, F = Tn - 1, tid = threadIdx.x;
-    double* fin = reinterpret_cast<double*>(smem_raw);  // [F][7] right-hand side -> final increments
-    // second region, [F][8] doubles: during the solve it holds ONE substitution table at a time (tab_in_smem) -- every
-    // step reads one 64-byte row, and a first-touch L2 round trip per row (a 128-byte line = two rows) was most of the
-    // solve's latency -- and afterwards the free rows of the trajectory ([F][7]).  120 F bytes per CTA in all: 24 KB
-    // at T = 200, so that a whole 1,024-trajectory batch is resident in one wave.
-    double* tr = fin + (size_t)F * 7 + (F & 1);         // (F & 1): 7 F doubles is odd for odd F; keep 16-byte alignment
-    double4* s_tab = reinterpret_cast<double4*>(tr);
-    __shared__ double s_tmp[kUpdThreads / 32];
-    __shared__ double s_best[kUpdThreads];
-    __shared__ int s_idx[kUpdThreads];
-    const int64_t n = blockIdx.x;
+    const int g = tid / kUpdGroup, gt = tid - g * kUpdGroup;
+    const size_t FD = (size_t)F * 7;
+    const size_t FDp = FD + (FD & 1);  // even number of doubles: every region stays 16-byte aligned
+    // shared memory: PER x { fin [F][7] right-hand side -> final increments, tr [F][7] free rows of the trajectory }
+    // then ONE substitution table [F][8] at a time (tab_in_smem): every step of the solve reads one 64-byte row, and a
+    // first-touch L2 round trip per row (a 128-byte line = two rows) was most of the solve's latency.
+    double* base = reinterpret_cast<double*>(smem_raw);
+    double* fin = base + (size_t)g * 2 * FDp;
+    double* tr = fin + FDp;
+    double4* s_tab = reinterpret_cast<double4*>(base + (size_t)PER * 2 * FDp);
+    __shared__ double s_tmp_all[PER][2];
+    __shared__ double s_best_all[PER][kUpdGroup];
+    __shared__ int s_idx_all[PER][kUpdGroup];
+    __shared__ int s_stage[PER];
+    double* s_tmp = s_tmp_all[g];
+    double* s_best = s_best_all[g];
+    int* s_idx = s_idx_all[g];
+
+    const int64_t n = (int64_t)blockIdx.x * PER + g;
     // per-trajectory stage (lr_schedule_mode_ 1 lets every optimiser pick its own, torm_optimizer.cpp:400-412);
     // a negative entry leaves the trajectory untouched
-    const int stage = stage_idx ? stage_idx[n] : P.stage;
-    if (stage < 0) return;
-    T* trow = traj + n * (int64_t)Tn * 7 + 7;  // first free row
-    const size_t FD = (size_t)F * 7;
+    const int stage = n < N ? (stage_idx ? stage_idx[n] : P.stage) : -1;
+    if (gt == 0) s_stage[g] = stage;
+    const bool active = stage >= 0;
+    T* trow = traj + (active ? n : 0) * (int64_t)Tn * 7 + 7;  // first free row
     const double4* g_tab = reinterpret_cast<const double4*>(chol);  // [2][F] rows of 2 x double4
-    if (stage == 0 && tab_in_smem)
-        for (int k = tid; k < 2 * F; k += kUpdThreads) s_tab[k] = g_tab[k];  // forward table
+    if (tab_in_smem)
+        for (int k = tid; k < 2 * F; k += kUpdGroup * PER) s_tab[k] = g_tab[k];  // forward table
+
+    if (active) {
+        for (int k = gt; k < (int)FD; k += kUpdGroup) tr[k] = (double)trow[k];
+        if (stage == 0) {
+            const T* s = inc_smooth + n * FD;
+            const T* c = inc_coll + n * FD;
+            double ss = 1.0, sc = 1.0;
+            if (P.mode != 0) {
+                double ms = 0.0, mc = 0.0;
+                for (int k = gt; k < (int)FD; k += kUpdGroup) { ms = fmax(ms, fabs((double)s[k])); mc = fmax(mc, fabs((double)c[k])); }
+                ss = group_max(ms, s_tmp, g, gt);
+                sc = group_max(mc, s_tmp, g, gt);
+            }
+            const double a = alpha ? (double)alpha[n] : 0.5;
+            for (int k = gt; k < (int)FD; k += kUpdGroup) {
+                double sv = (double)s[k], cv = (double)c[k];
+                if (P.mode != 0) {
+                    if (ss > 0) sv /= ss;
+                    if (sc > 0) cv /= sc;
+                    fin[k] = a * cv + (1 - a) * sv;
+                } else {
+                    fin[k] = P.sw * sv + P.ow * cv;
+                }
+            }
+        } else {
+            const T* p = inc_pose + n * FD;
+            for (int k = gt; k < (int)FD; k += kUpdGroup) fin[k] = (double)p[k];
+        }
+    }
+    __syncthreads();
+
+    // ---- banded Cholesky solve per (trajectory, joint) column: L y = b, then L^T x = y.  The recurrence is the
+    // critical path (an FP64 FMA has ~40 cycles of latency here), so the substitution is column oriented: six
+    // running rows live in registers, already divided by their diagonal; once unknown i is final it is pushed into
+    // all six with independent FMAs and the first of them IS unknown i+1 -- one dependent FMA per step, no division.
+    // Coefficient rows (smooth_build) are fetched one step ahead.
+    const int sg = tid / 7, sj = tid - sg * 7;  // solve lane -> (trajectory of this CTA, joint)
+    const bool solver = tid < 7 * PER && s_stage[sg < PER ? sg : 0] == 0;
+    double* sfin = base + (size_t)(sg < PER ? sg : 0) * 2 * FDp;
+    auto rdiag = [&](const double4* t, int r) { return t[2 * r + 1].w; };
+    auto rhs_at = [&](int r) { return (r >= 0 && r < F) ? sfin[r * 7 + sj] : 0.0; };
+    if (solver) {
+        const double4* tab = tab_in_smem ? s_tab : g_tab;  // one row = 2 x double4
+        // ---- forward: rows 0..6 start as b_r / L(r,r); a0 is the row being finalised
+        double a0 = rhs_at(0) * rdiag(tab, 0);
+        double a1 = F > 1 ? rhs_at(1) * rdiag(tab, 1) : 0.0, a2 = F > 2 ? rhs_at(2) * rdiag(tab, 2) : 0.0;
+        double a3 = F > 3 ? rhs_at(3) * rdiag(tab, 3) : 0.0, a4 = F > 4 ? rhs_at(4) * rdiag(tab, 4) : 0.0;
+        double a5 = F > 5 ? rhs_at(5) * rdiag(tab, 5) : 0.0, a6 = F > 6 ? rhs_at(6) * rdiag(tab, 6) : 0.0;
+        double4 ca = tab[0], cb = tab[1];
+        double nb_rhs = rhs_at(7);
+        for (int i = 0; i < F; i++) {
+            const int in = i + 1 < F ? i + 1 : i;
+            const double4 na = tab[2 * in], nb = tab[2 * in + 1];
+            const double nrhs = rhs_at(i + 8);
+            const double y = a0;
+            sfin[i * 7 + sj] = y;
+            a0 = a1 - ca.x * y; a1 = a2 - ca.y * y; a2 = a3 - ca.z * y; a3 = a4 - ca.w * y; a4 = a5 - cb.x * y;
+            a5 = a6 - cb.y * y;
+            a6 = nb_rhs * cb.z;  // row i+7 enters the window: b / L(i+7,i+7)
+            ca = na; cb = nb; nb_rhs = nrhs;
+        }
+    }
+    __syncthreads();
+    if (tab_in_smem)
+        for (int k = tid; k < 2 * F; k += kUpdGroup * PER) s_tab[k] = g_tab[2 * F + k];  // backward table
+    __syncthreads();
+    if (solver) {
+        // ---- backward: rows F-1 .. F-7 start as y_r / L(r,r)
+        const double4* tbk = tab_in_smem ? s_tab : g_tab + 2 * (size_t)F;
+        const int e = F - 1;
+        double a0 = rhs_at(e) * rdiag(tbk, e);
+        double a1 = e - 1 >= 0 ? rhs_at(e - 1) * rdiag(tbk, e - 1) : 0.0, a2 = e - 2 >= 0 ? rhs_at(e - 2) * rdiag(tbk, e - 2) : 0.0;
+        double a3 = e - 3 >= 0 ? rhs_at(e - 3) * rdiag(tbk, e - 3) : 0.0, a4 = e - 4 >= 0 ? rhs_at(e - 4) * rdiag(tbk, e - 4) : 0.0;
+        double a5 = e - 5 >= 0 ? rhs_at(e - 5) * rdiag(tbk, e - 5) : 0.0, a6 = e - 6 >= 0 ? rhs_at(e - 6) * rdiag(tbk, e - 6) : 0.0;
+        double4 ca = tbk[2 * e], cb = tbk[2 * e + 1];
+        double nb_rhs = rhs_at(e - 7);
+        for (int i = e; i >= 0; i--) {
+            const int in = i > 0 ? i - 1 : 0;
+            const double4 na = tbk[2 * in], nb = tbk[2 * in + 1];
+            const double nrhs = rhs_at(i - 8);
+            const double x = a0;
+            sfin[i * 7 + sj] = x;
+            a0 = a1 - ca.x * x; a1 = a2 - ca.y * x; a2 = a3 - ca.z * x; a3 = a4 - ca.w * x; a4 = a5 - cb.x * x;
+            a5 = a6 - cb.y * x;
+            a6 = nb_rhs * cb.z;  // row i-7 enters the window
+            ca = na; cb = nb; nb_rhs = nrhs;
+        }
+    }
+    __syncthreads();
+    if (!active) return;  // no CTA-wide barrier below this line
 
     if (stage == 0) {
-        const T* s = inc_smooth + n * FD;
-        const T* c = inc_coll + n * FD;
-        double ss = 1.0, sc = 1.0;
-        if (P.mode != 0) {
-            double ms = 0.0, mc = 0.0;
-            for (int k = tid; k < (int)FD; k += kUpdThreads) { ms = fmax(ms, fabs((double)s[k])); mc = fmax(mc, fabs((double)c[k])); }
-            ss = block_max(ms, s_tmp);
-            sc = block_max(mc, s_tmp);
-        }
-        const double a = alpha ? (double)alpha[n] : 0.5;
-        for (int k = tid; k < (int)FD; k += kUpdThreads) {
-            double sv = (double)s[k], cv = (double)c[k];
-            if (P.mode != 0) {
-                if (ss > 0) sv /= ss;
-                if (sc > 0) cv /= sc;
-                fin[k] = a * cv + (1 - a) * sv;
-            } else {
-                fin[k] = P.sw * sv + P.ow * cv;
-            }
-        }
-        __syncthreads();
-        // banded Cholesky solve per joint column: L y = b, then L^T x = y.  One thread per joint.  The recurrence is
-        // the critical path (an FP64 FMA has ~40 cycles of latency here), so the substitution is column oriented: six
-        // running rows live in registers, already divided by their diagonal; once unknown i is final it is pushed
-        // into all six with independent FMAs and the first of them IS unknown i+1 -- one dependent FMA per step.
-        // Coefficient rows (smooth_build) are fetched one step ahead.
-        if (tid < 7) {
-            const int j = tid;
-            const double4* tab = tab_in_smem ? s_tab : g_tab;  // one row = 2 x double4
-            auto rdiag = [&](const double4* t, int r) { return t[2 * r + 1].w; };
-            auto rhs_at = [&](int r) { return (r >= 0 && r < F) ? fin[r * 7 + j] : 0.0; };
-            // ---- forward: rows 0..5 start as b_r / L(r,r); a0 is the row being finalised
-            double a0 = rhs_at(0) * rdiag(tab, 0);
-            double a1 = F > 1 ? rhs_at(1) * rdiag(tab, 1) : 0.0, a2 = F > 2 ? rhs_at(2) * rdiag(tab, 2) : 0.0;
-            double a3 = F > 3 ? rhs_at(3) * rdiag(tab, 3) : 0.0, a4 = F > 4 ? rhs_at(4) * rdiag(tab, 4) : 0.0;
-            double a5 = F > 5 ? rhs_at(5) * rdiag(tab, 5) : 0.0, a6 = F > 6 ? rhs_at(6) * rdiag(tab, 6) : 0.0;
-            double4 ca = tab[0], cb = tab[1];
-            double nb_rhs = rhs_at(7);
-            for (int i = 0; i < F; i++) {
-                const int in = i + 1 < F ? i + 1 : i;
-                const double4 na = tab[2 * in], nb = tab[2 * in + 1];
-                const double nrhs = rhs_at(i + 8);
-                const double y = a0;
-                fin[i * 7 + j] = y;
-                a0 = a1 - ca.x * y; a1 = a2 - ca.y * y; a2 = a3 - ca.z * y; a3 = a4 - ca.w * y; a4 = a5 - cb.x * y;
-                a5 = a6 - cb.y * y;
-                a6 = nb_rhs * cb.z;  // row i+7 enters the window: b / L(i+7,i+7)
-                ca = na; cb = nb; nb_rhs = nrhs;
-            }
-        }
-        __syncthreads();
-        if (tab_in_smem)
-            for (int k = tid; k < 2 * F; k += kUpdThreads) s_tab[k] = g_tab[2 * F + k];  // backward table
-        __syncthreads();
-        if (tid < 7) {
-            const int j = tid;
-            auto rdiag = [&](const double4* t, int r) { return t[2 * r + 1].w; };
-            auto rhs_at = [&](int r) { return (r >= 0 && r < F) ? fin[r * 7 + j] : 0.0; };
-            // ---- backward: rows F-1 .. F-6 start as y_r / L(r,r)
-            const double4* tbk = tab_in_smem ? s_tab : g_tab + 2 * (size_t)F;
-            double a0, a1, a2, a3, a4, a5, a6, nb_rhs;
-            double4 ca, cb;
-            const int e = F - 1;
-            a0 = rhs_at(e) * rdiag(tbk, e);
-            a1 = e - 1 >= 0 ? rhs_at(e - 1) * rdiag(tbk, e - 1) : 0.0; a2 = e - 2 >= 0 ? rhs_at(e - 2) * rdiag(tbk, e - 2) : 0.0;
-            a3 = e - 3 >= 0 ? rhs_at(e - 3) * rdiag(tbk, e - 3) : 0.0; a4 = e - 4 >= 0 ? rhs_at(e - 4) * rdiag(tbk, e - 4) : 0.0;
-            a5 = e - 5 >= 0 ? rhs_at(e - 5) * rdiag(tbk, e - 5) : 0.0; a6 = e - 6 >= 0 ? rhs_at(e - 6) * rdiag(tbk, e - 6) : 0.0;
-            ca = tbk[2 * e]; cb = tbk[2 * e + 1];
-            nb_rhs = rhs_at(e - 7);
-            for (int i = e; i >= 0; i--) {
-                const int in = i > 0 ? i - 1 : 0;
-                const double4 na = tbk[2 * in], nb = tbk[2 * in + 1];
-                const double nrhs = rhs_at(i - 8);
-                const double x = a0;
-                fin[i * 7 + j] = x;
-                a0 = a1 - ca.x * x; a1 = a2 - ca.y * x; a2 = a3 - ca.z * x; a3 = a4 - ca.w * x; a4 = a5 - cb.x * x;
-                a5 = a6 - cb.y * x;
-                a6 = nb_rhs * cb.z;  // row i-7 enters the window
-                ca = na; cb = nb; nb_rhs = nrhs;
-            }
-        }
-        __syncthreads();  // the table region is free again
         const double rate = (double)lr[n] / P.mcs;
-        for (int k = tid; k < (int)FD; k += kUpdThreads) fin[k] *= rate;
-    } else {
-        const T* p = inc_pose + n * FD;
-        for (int k = tid; k < (int)FD; k += kUpdThreads) fin[k] = (double)p[k];
+        for (int k = gt; k < (int)FD; k += kUpdGroup) fin[k] *= rate;
+        group_sync(g);
     }
-    for (int k = tid; k < (int)FD; k += kUpdThreads) tr[k] = (double)trow[k];
-    __syncthreads();
 
     // ---- addIncrementsToTrajectory :1611-1639
     if (P.mode != 0) {
         double m = 0.0;
-        for (int k = tid; k < (int)FD; k += kUpdThreads) m = fmax(m, fabs(fin[k]));
-        const double scale = block_max(m, s_tmp);
+        for (int k = gt; k < (int)FD; k += kUpdGroup) m = fmax(m, fabs(fin[k]));
+        const double scale = group_max(m, s_tmp, g, gt);
         const bool clip = scale > P.limit && scale > 0;
-        for (int k = tid; k < (int)FD; k += kUpdThreads) tr[k] += clip ? fin[k] / scale * P.limit : fin[k];
+        for (int k = gt; k < (int)FD; k += kUpdGroup) tr[k] += clip ? fin[k] / scale * P.limit : fin[k];
     } else {
         for (int j = 0; j < 7; j++) {
             double mx = -1e300, mn = 1e300;
-            for (int i = tid; i < F; i += kUpdThreads) { mx = fmax(mx, fin[i * 7 + j]); mn = fmin(mn, fin[i * 7 + j]); }
-            mx = block_max(mx, s_tmp);
-            mn = -block_max(-mn, s_tmp);
+            for (int i = gt; i < F; i += kUpdGroup) { mx = fmax(mx, fin[i * 7 + j]); mn = fmin(mn, fin[i * 7 + j]); }
+            mx = group_max(mx, s_tmp, g, gt);
+            mn = -group_max(-mn, s_tmp, g, gt);
             double scale = 1.0;
             const double max_scale = P.limit / fabs(mx), min_scale = P.limit / fabs(mn);
             if (max_scale < scale) scale = max_scale;
             if (min_scale < scale) scale = min_scale;
-            for (int i = tid; i < F; i += kUpdThreads) tr[i * 7 + j] += scale * fin[i * 7 + j];
+            for (int i = gt; i < F; i += kUpdGroup) tr[i * 7 + j] += scale * fin[i * 7 + j];
         }
     }
-    __syncthreads();
+    group_sync(g);
 
     // ---- handleJointLimits :1189-1268 (continuous joints are skipped)
     for (int j = 0; j < 7; j++) {
         if (P.cj[j]) continue;
         for (int count = 0; count <= 10; count++) {
-            double best = 1e-6, amount_best = 0.0;
+            double best = 1e-6;
             int idx = -1;
-            for (int i = tid; i < F; i += kUpdThreads) {
+            for (int i = gt; i < F; i += kUpdGroup) {
                 const double v = tr[i * 7 + j];
                 double amount = 0.0;
                 if (v > P.jmax[j]) amount = P.jmax[j] - v;
                 else if (v < P.jmin[j]) amount = P.jmin[j] - v;
-                if (fabs(amount) > best) { best = fabs(amount); amount_best = amount; idx = i; }  // first maximum wins
+                if (fabs(amount) > best) { best = fabs(amount); idx = i; }  // first maximum wins
             }
-            s_best[tid] = idx >= 0 ? best : 0.0;
-            s_idx[tid] = idx;
-            __syncthreads();
+            s_best[gt] = idx >= 0 ? best : 0.0;
+            s_idx[gt] = idx;
+            group_sync(g);
             // every thread resolves the winner the same way: largest violation, smallest row index on ties
             double wb = 0.0;
             int wi = -1;
-            for (int t = 0; t < kUpdThreads; t++) {
+            for (int t = 0; t < kUpdGroup; t++) {
                 const int ti = s_idx[t];
                 if (ti >= 0 && (s_best[t] > wb || (s_best[t] == wb && ti < wi))) { wb = s_best[t]; wi = ti; }
             }
-            __syncthreads();
+            group_sync(g);
             if (wi < 0) break;
             const double v = tr[wi * 7 + j];
             const double viol = v > P.jmax[j] ? P.jmax[j] - v : P.jmin[j] - v;
-            (void)amount_best;
             const double mult = viol / inv[(size_t)wi * F + wi];
-            __syncthreads();
-            for (int i = tid; i < F; i += kUpdThreads) tr[i * 7 + j] += mult * inv[(size_t)wi * F + i];
-            __syncthreads();
+            group_sync(g);
+            for (int i = gt; i < F; i += kUpdGroup) tr[i * 7 + j] += mult * inv[(size_t)wi * F + i];
+            group_sync(g);
         }
     }
-    __syncthreads();
-    for (int k = tid; k < (int)FD; k += kUpdThreads) trow[k] = (T)tr[k];
+    group_sync(g);
+    for (int k = gt; k < (int)FD; k += kUpdGroup) trow[k] = (T)tr[k];
+}
+
+template <typename T, int PER>
+static int launch_update_per(const UpdP& P, const Smooth* sm, T* traj, int64_t N, const T* inc_smooth, const T* inc_coll,
+                             const T* inc_pose, const T* alpha, const T* lr, const int32_t* stage_idx, size_t smem,
+                             int tab_in_smem, cudaStream_t st) {
+    auto kern = torm_update_kernel<T, PER>;
+    int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "torm_update_kernel");
+    if (rc_attr) return rc_attr;
+    const unsigned grid = (unsigned)((N + PER - 1) / PER);
+    kern<<<grid, kUpdGroup * PER, smem, st>>>(P, traj, N, inc_smooth, inc_coll, inc_pose, alpha, lr, sm->d_chol,
+                                              sm->d_inv64, stage_idx, tab_in_smem);
+    return check_launch("torm_update_kernel");
 }
 
 template <typename T>
@@ -228,19 +259,17 @@ static int launch_update(const RlitgTormUpdate* u, const RlitgTormParams* p, con
     P.mcs = sm->mcs;
     for (int j = 0; j < 7; j++) { P.cj[j] = p->cjoint[j]; P.jmin[j] = u->joint_min[j]; P.jmax[j] = u->joint_max[j]; }
     const size_t F = (size_t)(p->T - 1);
-    size_t smem = sizeof(double) * 2 * F * 7;
-    if (smem > 200 * 1024) return set_error(RLITG_ERR_SHAPE, "T too large for the update step's shared-memory tile");
-    const size_t smem_tab = sizeof(double) * (F * 7 + (F & 1) + F * 8);
-    const int tab_in_smem = smem_tab <= 200 * 1024;  // longer paths read the tables through L1 / L2
-    smem = tab_in_smem ? smem_tab : smem + 8;
-    auto kern = torm_update_kernel<T>;
-    {
-        int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "torm_update_kernel");
-        if (rc_attr) return rc_attr;
-    }
-    kern<<<(unsigned)N, kUpdThreads, smem, st>>>(P, traj, inc_smooth, inc_coll, inc_pose, alpha, lr, sm->d_chol, sm->d_inv64,
-                                                 stage_idx, tab_in_smem);
-    return check_launch("torm_update_kernel");
+    const size_t FDp = F * 7 + ((F * 7) & 1);
+    auto bytes = [&](int per, bool tab) { return sizeof(double) * ((size_t)per * 2 * FDp + (tab ? F * 8 : 0)); };
+    // four trajectories per CTA (lane-packed solve) when some trajectory may take the feasible stage and two such CTAs
+    // fit an SM; otherwise one per CTA (measured faster for the solve-free end-pose update: 29 vs 35 us per 1,024).
+    // The substitution tables go to shared memory whenever they fit, longer paths read them through L1 / L2.
+    const bool may_solve = stage_idx != nullptr || u->stage == 0;
+    if (may_solve && N >= 4 && bytes(4, true) <= 110 * 1024)
+        return launch_update_per<T, 4>(P, sm, traj, N, inc_smooth, inc_coll, inc_pose, alpha, lr, stage_idx, bytes(4, true), 1, st);
+    const bool tab = may_solve && bytes(1, true) <= 200 * 1024;  // no solve, no table
+    if (bytes(1, tab) > 200 * 1024) return set_error(RLITG_ERR_SHAPE, "T too large for the update step's shared-memory tile");
+    return launch_update_per<T, 1>(P, sm, traj, N, inc_smooth, inc_coll, inc_pose, alpha, lr, stage_idx, bytes(1, tab), tab ? 1 : 0, st);
 }
 
 }  // namespace rlitg
@@ -285,6 +314,108 @@ extern "C" RLITG_API int rlitg_torm_update_staged(void* traj, int64_t N, int dty
                                                   const void* lr, void* stream) {
     if (!stage_idx) return set_error(RLITG_ERR_NULL, "stage_idx is NULL");
     return torm_update_impl(traj, N, dtype, smooth, p, u, stage_idx, inc_smooth, inc_coll, inc_pose, alpha, lr, stream);
+}
+
+// ---- per-trajectory optimiser state of localOptimizeTSGD (torm/src/torm_optimizer.cpp:400-560) --------------------
+// One CTA per trajectory replaces the scalar host control flow of the reference between the cost evaluation and the
+// update step: stage choice (lr_schedule_mode_ 1, :400-412, from the state BEFORE this sub-step), feasibility flags
+// (:436-446), alpha_ (:447-469), learning_rate_ (:471-499) and the best-trajectory record (:506-560).
+namespace rlitg {
+struct BookP {
+    int T, mode, stage, use_col, use_vel;
+    double lr0, lr_min, lr_max;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+torm_bookkeep_kernel(BookP P, const T* __restrict__ traj, T* __restrict__ best_traj, const T* __restrict__ costs,
+                     const uint8_t* __restrict__ hits, const uint8_t* __restrict__ singular, T* __restrict__ alpha,
+                     T* __restrict__ lr, uint8_t* __restrict__ infea_col, uint8_t* __restrict__ infea_vel,
+                     T* __restrict__ best_cost, int32_t* __restrict__ stage_idx, const T* __restrict__ lr_iter) {
+    const int64_t n = blockIdx.x;
+    const int tid = threadIdx.x;
+    __shared__ int s_hit;
+    __shared__ int s_better;
+    if (tid == 0) s_hit = 0;
+    __syncthreads();
+    if (P.use_col && hits) {
+        int h = 0;
+        for (int i = tid; i < P.T; i += blockDim.x) h |= hits[n * P.T + i];
+        if (h) s_hit = 1;  // benign race: every writer stores 1
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const T lr_old = lr[n];
+        const bool col_old = infea_col[n] != 0, vel_old = infea_vel[n] != 0;
+        if (stage_idx) {
+            bool feasible_stage;
+            if (P.stage == 0) feasible_stage = !(P.mode == 1 && lr_old < T(1e-2) && !col_old && !vel_old);
+            else feasible_stage = (P.mode == 1 && lr_old == T(P.lr_max) && col_old);
+            stage_idx[n] = feasible_stage ? 0 : 1;
+        }
+        const bool col = s_hit != 0;
+        const bool vel = P.use_vel && costs[n * RLITG_TORM_NCOST + 7] != T(0);
+        infea_col[n] = col; infea_vel[n] = vel;
+        T a = alpha[n];
+        if (P.mode == 1 || P.mode == 2) {
+            if (col && !vel) a = a < T(0.5) ? T(0.5) : (a + T(0.1) < T(1) ? a + T(0.1) : T(1));
+            else if (!col && vel) a = a > T(0.5) ? T(0.5) : (a - T(0.1) > T(0) ? a - T(0.1) : T(0));
+            else a = T(0.5);
+        } else if (P.mode == 3) {
+            a = T(0.5);
+        }
+        alpha[n] = a;
+        T l = lr_old;
+        if (P.mode == 1) {
+            if (!col && !vel) l = l > T(P.lr0) ? T(P.lr0) : (l / T(2) > T(P.lr_min) ? l / T(2) : T(P.lr_min));
+            else l = l * T(2) < T(P.lr_max) ? l * T(2) : T(P.lr_max);
+        } else if (P.mode == 2) {
+            l = lr_iter ? lr_iter[0] : T(P.lr0);
+        } else if (P.mode == 3) {
+            l = T(P.lr0);
+        }
+        lr[n] = l;
+        const T cur = costs[n * RLITG_TORM_NCOST + 6];
+        const bool ok = !col && !vel && !(singular && singular[n]);
+        const bool better = ok && cur < best_cost[n];
+        if (better) best_cost[n] = cur;
+        s_better = better;
+    }
+    __syncthreads();
+    if (s_better) {
+        const int64_t off = n * (int64_t)P.T * 7;
+        for (int k = tid; k < P.T * 7; k += blockDim.x) best_traj[off + k] = traj[off + k];
+    }
+}
+}  // namespace rlitg
+
+extern "C" RLITG_API int rlitg_torm_bookkeep(const void* traj, void* best_traj, int64_t N, int T, int dtype,
+                                             const void* costs, const uint8_t* hits, const uint8_t* singular,
+                                             void* alpha, void* lr, uint8_t* infea_col, uint8_t* infea_vel,
+                                             void* best_cost, int32_t* stage_idx, const void* lr_iter,
+                                             const RlitgTormSchedule* sch, void* stream) {
+    if (!sch) return set_error(RLITG_ERR_NULL, "schedule is NULL");
+    if (dtype != RLITG_F32 && dtype != RLITG_F64) return set_error(RLITG_ERR_DTYPE, "dtype must be RLITG_F32 or RLITG_F64");
+    if (N < 0 || N > 0x7fffffff || T < 2) return set_error(RLITG_ERR_SHAPE, "N / T out of range");
+    if (sch->stage != 0 && sch->stage != 1) return set_error(RLITG_ERR_ARG, "stage must be 0 or 1");
+    if (sch->lr_schedule_mode < 0 || sch->lr_schedule_mode > 3) return set_error(RLITG_ERR_ARG, "lr_schedule_mode must be 0..3");
+    if (N == 0) return RLITG_OK;
+    if (!traj || !best_traj || !costs || !alpha || !lr || !infea_col || !infea_vel || !best_cost)
+        return set_error(RLITG_ERR_NULL, "traj / best_traj / costs / alpha / lr / infea_* / best_cost is NULL");
+    BookP P;
+    P.T = T; P.mode = sch->lr_schedule_mode; P.stage = sch->stage;
+    P.use_col = sch->use_collision_check; P.use_vel = sch->use_velocity_check;
+    P.lr0 = sch->learning_rate; P.lr_min = sch->learning_rate_min; P.lr_max = sch->learning_rate_max;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == RLITG_F32)
+        torm_bookkeep_kernel<float><<<(unsigned)N, 128, 0, st>>>(P, (const float*)traj, (float*)best_traj, (const float*)costs,
+                                                                 hits, singular, (float*)alpha, (float*)lr, infea_col, infea_vel,
+                                                                 (float*)best_cost, stage_idx, (const float*)lr_iter);
+    else
+        torm_bookkeep_kernel<double><<<(unsigned)N, 128, 0, st>>>(P, (const double*)traj, (double*)best_traj, (const double*)costs,
+                                                                  hits, singular, (double*)alpha, (double*)lr, infea_col, infea_vel,
+                                                                  (double*)best_cost, stage_idx, (const double*)lr_iter);
+    return check_launch("torm_bookkeep_kernel");
 }
 
 // ---- candidate selection of the Greedy / Linear initialisers --------------------------------

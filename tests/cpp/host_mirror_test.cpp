@@ -226,6 +226,19 @@ int main() {
     std::printf("objective %.5f -> %.5f over %d trajectories; kernels launched: %lld\n", before / N, after / N, N,
                 (long long)rlitg_launch_count());
 
+    // every lr_schedule_mode_ runs on the device (the scene-bound optimiser: collisions feed the adaptive schedule)
+    for (int mode = 0; mode <= 3; mode++) {
+        opt.setTrajectories(traj);
+        auto bc = opt.localOptimizeTSGD(12, mode);
+        int nf = 0;
+        for (double v : bc) nf += std::isfinite(v);
+        auto after_t = opt.getTrajectories();
+        double moved = 0;
+        for (size_t i = 0; i < after_t.size(); i++) moved = std::fmax(moved, std::fabs(after_t[i] - traj[i]));
+        EXPECT(moved > 1e-3 && moved < 7.0, "mode %d: trajectories moved by %g", mode, moved);
+        std::printf("lr_schedule_mode %d: %d of %d trajectories recorded a feasible best\n", mode, nf, N);
+    }
+
     // ---- PirlVecEnv: reset + three steps against the oracle (FP32 device state vs FP64 oracle)
     {
         const int Bp = 96, Tp = 12;

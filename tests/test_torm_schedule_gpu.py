@@ -142,3 +142,29 @@ def test_iterative_exploration_restarts_as_batch(cuda_device, init_traj):
     assert early["epochs"] == 1
     only_first = tb.iterativeExploration(g(first), max_epochs=5, lr_schedule_mode=3)
     assert only_first["epochs"] == 1 and torch.allclose(only_first["best_cost"], c1, rtol=1e-12)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_graph_replay_equals_eager(cuda_device, mode, dtype):
+    """localOptimizeTSGD replays one captured iteration per step (no host synchronisation inside): bit-identical to the
+    eager loop, for every schedule mode, including the per-iteration cosine rate of mode 2."""
+    import torch
+    from rlitg_b200 import torm as TM
+    N, T, maxiter = 24, 40, 11
+    traj, targets, osc, gsc = make_problem(N, T, 33, cuda_device)
+    pr = TM.TormParameters(min_clearence_=0.3, learning_rate_=0.02)
+    tb = TM.TormBatch(targets, pr, gsc, cuda_device, getattr(torch, dtype))
+    a = torch.tensor(traj, dtype=getattr(torch, dtype), device=cuda_device)
+    b = a.clone()
+    bt_e, bc_e, st_e = tb.localOptimizeTSGD(a, maxiter, lr_schedule_mode=mode, return_state=True, use_cuda_graph=False)
+    bt_e, bc_e = bt_e.clone(), bc_e.clone()
+    st_e = {k: v.clone() for k, v in st_e.items()}
+    bt_g, bc_g, st_g = tb.localOptimizeTSGD(b, maxiter, lr_schedule_mode=mode, return_state=True, use_cuda_graph=True)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    assert torch.equal(bt_e, bt_g) and torch.equal(bc_e, bc_g)
+    for k in st_e:
+        assert torch.equal(st_e[k], st_g[k]), k
+    assert float((a - torch.tensor(traj, dtype=a.dtype, device=cuda_device)).abs().max()) > 1e-3
+    gsc.close()

@@ -56,18 +56,25 @@ def main():
         return 1e3 * ev_time(g.replay)
     print("update feasible (graph replay, GPU only) %.1f us" % graphed(lambda: tb.applyIncrements(tw.copy_(traj), True, inc_s, inc_c, None, al, lr, lr_schedule_mode=3)))
     print("update end-pose (graph replay, GPU only) %.1f us" % graphed(lambda: tb.applyIncrements(tw.copy_(traj), False, inc_pose=inc_p, alpha=al, learning_rate=lr, lr_schedule_mode=3)))
+    inside = traj * 0.5  # well inside the joint limits: handleJointLimits finds nothing to do
+    print("update end-pose, no limit hits (graph)   %.1f us" % graphed(lambda: tb.applyIncrements(tw.copy_(inside), False, inc_pose=inc_p * 0.01, alpha=al, learning_rate=lr, lr_schedule_mode=3)))
+    print("update feasible, no limit hits (graph)   %.1f us" % graphed(lambda: tb.applyIncrements(tw.copy_(inside), True, inc_s, inc_c, None, al, lr, lr_schedule_mode=3)))
     print("copy            (graph replay, GPU only) %.1f us" % graphed(lambda: tw.copy_(traj)))
     print("cost feasible   (graph replay, GPU only) %.1f us" % graphed(lambda: tb.cost_grad(tw, feas)))
     print("cost end-pose   (graph replay, GPU only) %.1f us" % graphed(lambda: tb.cost_grad(tw, pose)))
     print("copy only       %.1f us" % (1e3 * ev_time(lambda: tw.copy_(traj))))
     print("collide N*T     %.1f us" % (1e3 * ev_time(lambda: sc.collide(tw.reshape(-1, 7)))))
     for mode in (3, 1):
-        tw.copy_(traj)
-        tb.localOptimizeTSGD(tw, 2, lr_schedule_mode=mode)
-        torch.cuda.synchronize(); t0 = time.perf_counter()
-        tb.localOptimizeTSGD(tw, 20, lr_schedule_mode=mode)
-        torch.cuda.synchronize()
-        print("localOptimizeTSGD mode %d: %.3f ms per iteration (wall)" % (mode, (time.perf_counter() - t0) * 1e3 / 20))
+        for use_graph in (False, True):
+            tw.copy_(traj)
+            tb.localOptimizeTSGD(tw, 2, lr_schedule_mode=mode, use_cuda_graph=False)
+            for iters in (20, 100):
+                tw.copy_(traj)
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                tb.localOptimizeTSGD(tw, iters, lr_schedule_mode=mode, use_cuda_graph=use_graph)
+                torch.cuda.synchronize()
+                print("localOptimizeTSGD mode %d graph=%d, %3d iterations: %.3f ms per iteration (wall)" %
+                      (mode, use_graph, iters, (time.perf_counter() - t0) * 1e3 / iters))
 
 
 if __name__ == "__main__":
