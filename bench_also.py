@@ -154,7 +154,7 @@ def run(dev, rank, world, max_over_ranks, barrier, steps=30, warmup=5):
                        "contents": "feasible stage (cost + increments, update step) + end-pose stage (cost + increments, update step)"},
             "ms_kernels_eager": ms_iter, "ms_kernels_cuda_graph": ms_iter_graph,
             "ms_localOptimizeTSGD_per_iteration": ms_loop,
-            "note": "localOptimizeTSGD adds two sphere-grid feasibility checks and the best-trajectory bookkeeping per iteration (torch glue, wall clock)",
+            "note": "localOptimizeTSGD adds two sphere-grid feasibility checks and two rlitg_torm_bookkeep launches per iteration (wall clock, 20 iterations)",
             "trajectory_iterations_per_s": world * N / (min(ms_iter, ms_iter_graph) * 1e-3)}
     except Exception as e:  # noqa: BLE001
         out["torm_tsgd_iteration"] = {"error": repr(e)}

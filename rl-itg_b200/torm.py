@@ -254,19 +254,27 @@ def _apply_increments(self, traj, feasible_stage, inc_smooth=None, inc_coll=None
     `feasible_stage` is then ignored (rlitg_torm_update_staged)."""
     pr = self.parameters
     N = traj.shape[0]
-    u = RlitgTormUpdate()
-    u.stage, u.lr_schedule_mode = (0 if feasible_stage else 1), int(lr_schedule_mode)
-    u.smoothness_update_weight = pr.smoothness_update_weight_ / self.T  # the mains pass 30 / T (SURVEY appendix C)
-    u.obstacle_update_weight = pr.obstacle_update_weight_
-    # TormOptimizer's constructor overwrites joint_update_limit_ when lr_schedule_mode_ == 0 (:104-106)
-    u.joint_update_limit = 0.1 if lr_schedule_mode == 0 else pr.joint_update_limit_
-    u.joint_min = (C.c_double * 7)(*fetch.LL)
-    u.joint_max = (C.c_double * 7)(*fetch.UL)
+    ukey = (bool(feasible_stage), int(lr_schedule_mode))
+    u = self._upd_cache.get(ukey) if hasattr(self, "_upd_cache") else None
+    if u is None:  # the struct only depends on (stage, mode) and the parameters: built once (hot loop)
+        u = RlitgTormUpdate()
+        u.stage, u.lr_schedule_mode = (0 if feasible_stage else 1), int(lr_schedule_mode)
+        u.smoothness_update_weight = pr.smoothness_update_weight_ / self.T  # the mains pass 30 / T (SURVEY appendix C)
+        u.obstacle_update_weight = pr.obstacle_update_weight_
+        # TormOptimizer's constructor overwrites joint_update_limit_ when lr_schedule_mode_ == 0 (:104-106)
+        u.joint_update_limit = 0.1 if lr_schedule_mode == 0 else pr.joint_update_limit_
+        u.joint_min = (C.c_double * 7)(*fetch.LL)
+        u.joint_max = (C.c_double * 7)(*fetch.UL)
+        if not hasattr(self, "_upd_cache"):
+            self._upd_cache = {}
+        self._upd_cache[ukey] = u
 
     def vec(x, default):
         if x is None:
             x = default
         if torch.is_tensor(x):
+            if x.device == self.device and x.dtype == traj.dtype and x.is_contiguous():
+                return x
             return x.to(self.device, traj.dtype).contiguous()
         return torch.full((N,), float(x), device=self.device, dtype=traj.dtype)
 
