@@ -58,10 +58,13 @@ torm_update_kernel(UpdP P, T* __restrict__ traj, int64_t N, const T* __restrict_
     // shared memory: PER x { fin [F][7] right-hand side -> final increments, tr [F][7] free rows of the trajectory }
     // then ONE substitution table [F][8] at a time (tab_in_smem): every step of the solve reads one 64-byte row, and a
     // first-touch L2 round trip per row (a 128-byte line = two rows) was most of the solve's latency.
+    // fin carries 8 zero rows in front and behind, so that the solve's look-ahead reads need no bounds test
+    constexpr int kPad = 8 * 7;
+    const size_t stride = FDp + 2 * kPad + FDp;  // doubles per trajectory: padded fin, then tr
     double* base = reinterpret_cast<double*>(smem_raw);
-    double* fin = base + (size_t)g * 2 * FDp;
-    double* tr = fin + FDp;
-    double4* s_tab = reinterpret_cast<double4*>(base + (size_t)PER * 2 * FDp);
+    double* fin = base + (size_t)g * stride + kPad;
+    double* tr = fin + FDp + kPad;
+    double4* s_tab = reinterpret_cast<double4*>(base + (size_t)PER * stride);
     __shared__ double s_tmp_all[PER][2];
     __shared__ double s_best_all[PER][kUpdGroup];
     __shared__ int s_idx_all[PER][kUpdGroup];
@@ -81,6 +84,7 @@ torm_update_kernel(UpdP P, T* __restrict__ traj, int64_t N, const T* __restrict_
     if (tab_in_smem)
         for (int k = tid; k < 2 * F; k += kUpdGroup * PER) s_tab[k] = g_tab[k];  // forward table
 
+    if (gt < kPad) { fin[gt - kPad] = 0.0; fin[FD + gt] = 0.0; }
     if (active) {
         for (int k = gt; k < (int)FD; k += kUpdGroup) tr[k] = (double)trow[k];
         if (stage == 0) {
@@ -118,27 +122,26 @@ torm_update_kernel(UpdP P, T* __restrict__ traj, int64_t N, const T* __restrict_
     // Coefficient rows (smooth_build) are fetched one step ahead.
     const int sg = tid / 7, sj = tid - sg * 7;  // solve lane -> (trajectory of this CTA, joint)
     const bool solver = tid < 7 * PER && s_stage[sg < PER ? sg : 0] == 0;
-    double* sfin = base + (size_t)(sg < PER ? sg : 0) * 2 * FDp;
-    auto rdiag = [&](const double4* t, int r) { return t[2 * r + 1].w; };
-    auto rhs_at = [&](int r) { return (r >= 0 && r < F) ? sfin[r * 7 + sj] : 0.0; };
+    double* sfin = base + (size_t)(sg < PER ? sg : 0) * stride + kPad + sj;  // column sj of that trajectory, row stride 7
+    // (rows -8..-1 and F..F+7 of sfin are zero; table rows outside 0..F-1 are never needed: their products are with
+    //  those zeros, so the row index is simply clamped)
     if (solver) {
         const double4* tab = tab_in_smem ? s_tab : g_tab;  // one row = 2 x double4
         // ---- forward: rows 0..6 start as b_r / L(r,r); a0 is the row being finalised
-        double a0 = rhs_at(0) * rdiag(tab, 0);
-        double a1 = F > 1 ? rhs_at(1) * rdiag(tab, 1) : 0.0, a2 = F > 2 ? rhs_at(2) * rdiag(tab, 2) : 0.0;
-        double a3 = F > 3 ? rhs_at(3) * rdiag(tab, 3) : 0.0, a4 = F > 4 ? rhs_at(4) * rdiag(tab, 4) : 0.0;
-        double a5 = F > 5 ? rhs_at(5) * rdiag(tab, 5) : 0.0, a6 = F > 6 ? rhs_at(6) * rdiag(tab, 6) : 0.0;
+        double a[7];
+#pragma unroll
+        for (int r = 0; r < 7; r++) a[r] = sfin[r * 7] * tab[2 * min(r, F - 1) + 1].w;
         double4 ca = tab[0], cb = tab[1];
-        double nb_rhs = rhs_at(7);
+        double nb_rhs = sfin[7 * 7];
         for (int i = 0; i < F; i++) {
-            const int in = i + 1 < F ? i + 1 : i;
+            const int in = min(i + 1, F - 1);
             const double4 na = tab[2 * in], nb = tab[2 * in + 1];
-            const double nrhs = rhs_at(i + 8);
-            const double y = a0;
-            sfin[i * 7 + sj] = y;
-            a0 = a1 - ca.x * y; a1 = a2 - ca.y * y; a2 = a3 - ca.z * y; a3 = a4 - ca.w * y; a4 = a5 - cb.x * y;
-            a5 = a6 - cb.y * y;
-            a6 = nb_rhs * cb.z;  // row i+7 enters the window: b / L(i+7,i+7)
+            const double nrhs = sfin[(i + 8) * 7];
+            const double y = a[0];
+            sfin[i * 7] = y;
+            a[0] = a[1] - ca.x * y; a[1] = a[2] - ca.y * y; a[2] = a[3] - ca.z * y; a[3] = a[4] - ca.w * y;
+            a[4] = a[5] - cb.x * y; a[5] = a[6] - cb.y * y;
+            a[6] = nb_rhs * cb.z;  // row i+7 enters the window: b / L(i+7,i+7)
             ca = na; cb = nb; nb_rhs = nrhs;
         }
     }
@@ -150,21 +153,20 @@ torm_update_kernel(UpdP P, T* __restrict__ traj, int64_t N, const T* __restrict_
         // ---- backward: rows F-1 .. F-7 start as y_r / L(r,r)
         const double4* tbk = tab_in_smem ? s_tab : g_tab + 2 * (size_t)F;
         const int e = F - 1;
-        double a0 = rhs_at(e) * rdiag(tbk, e);
-        double a1 = e - 1 >= 0 ? rhs_at(e - 1) * rdiag(tbk, e - 1) : 0.0, a2 = e - 2 >= 0 ? rhs_at(e - 2) * rdiag(tbk, e - 2) : 0.0;
-        double a3 = e - 3 >= 0 ? rhs_at(e - 3) * rdiag(tbk, e - 3) : 0.0, a4 = e - 4 >= 0 ? rhs_at(e - 4) * rdiag(tbk, e - 4) : 0.0;
-        double a5 = e - 5 >= 0 ? rhs_at(e - 5) * rdiag(tbk, e - 5) : 0.0, a6 = e - 6 >= 0 ? rhs_at(e - 6) * rdiag(tbk, e - 6) : 0.0;
+        double a[7];
+#pragma unroll
+        for (int r = 0; r < 7; r++) a[r] = sfin[(e - r) * 7] * tbk[2 * max(e - r, 0) + 1].w;
         double4 ca = tbk[2 * e], cb = tbk[2 * e + 1];
-        double nb_rhs = rhs_at(e - 7);
+        double nb_rhs = sfin[(e - 7) * 7];
         for (int i = e; i >= 0; i--) {
-            const int in = i > 0 ? i - 1 : 0;
+            const int in = max(i - 1, 0);
             const double4 na = tbk[2 * in], nb = tbk[2 * in + 1];
-            const double nrhs = rhs_at(i - 8);
-            const double x = a0;
-            sfin[i * 7 + sj] = x;
-            a0 = a1 - ca.x * x; a1 = a2 - ca.y * x; a2 = a3 - ca.z * x; a3 = a4 - ca.w * x; a4 = a5 - cb.x * x;
-            a5 = a6 - cb.y * x;
-            a6 = nb_rhs * cb.z;  // row i-7 enters the window
+            const double nrhs = sfin[(i - 8) * 7];
+            const double x = a[0];
+            sfin[i * 7] = x;
+            a[0] = a[1] - ca.x * x; a[1] = a[2] - ca.y * x; a[2] = a[3] - ca.z * x; a[3] = a[4] - ca.w * x;
+            a[4] = a[5] - cb.x * x; a[5] = a[6] - cb.y * x;
+            a[6] = nb_rhs * cb.z;  // row i-7 enters the window
             ca = na; cb = nb; nb_rhs = nrhs;
         }
     }
@@ -260,7 +262,7 @@ static int launch_update(const RlitgTormUpdate* u, const RlitgTormParams* p, con
     for (int j = 0; j < 7; j++) { P.cj[j] = p->cjoint[j]; P.jmin[j] = u->joint_min[j]; P.jmax[j] = u->joint_max[j]; }
     const size_t F = (size_t)(p->T - 1);
     const size_t FDp = F * 7 + ((F * 7) & 1);
-    auto bytes = [&](int per, bool tab) { return sizeof(double) * ((size_t)per * 2 * FDp + (tab ? F * 8 : 0)); };
+    auto bytes = [&](int per, bool tab) { return sizeof(double) * ((size_t)per * (2 * FDp + 2 * 8 * 7) + (tab ? F * 8 : 0)); };
     // four trajectories per CTA (lane-packed solve) when some trajectory may take the feasible stage and two such CTAs
     // fit an SM; otherwise one per CTA (measured faster for the solve-free end-pose update: 29 vs 35 us per 1,024).
     // The substitution tables go to shared memory whenever they fit, longer paths read them through L1 / L2.
