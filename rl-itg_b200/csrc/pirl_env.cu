@@ -118,7 +118,7 @@ template <typename T, bool kStep>
 __global__ void __launch_bounds__(kEnvTile, sizeof(T) == 4 ? 4 : 1) pirl_env_kernel(
     PirlCfgT<T> cfg, int64_t B, T* __restrict__ q, const float* __restrict__ action, int32_t* __restrict__ timestep,
     const int32_t* __restrict__ max_timestep, const T* __restrict__ targets, const T* __restrict__ demos, int Tmax,
-    const T* __restrict__ latent, SceneDev sc, int has_scene, double ox, double oy, double oz, T* __restrict__ obs,
+    const T* __restrict__ latent, SceneDev sc, int has_scene, T ox, T oy, T oz, T* __restrict__ obs,
     T* __restrict__ reward, uint8_t* __restrict__ done, uint8_t* __restrict__ flags, int32_t* __restrict__ counters,
     T* __restrict__ errs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kEnvTile, sizeof(T) == 4 ? 4 : 1) pirl_env_ker
         v.link_off = (ot == 1) ? 7 : (ot == 3 ? 0 : -1);
         v.ee_off = (ot == 2) ? 7 : -1;
         v.sc = &sc; v.sph = s_sph; v.link_start = s_start;
-        v.off = {T(ox), T(oy), T(oz)};
+        v.off = {ox, oy, oz};
         v.hit = false;
         v.do_coll = false;
 
@@ -377,7 +377,7 @@ static int launch_pirl(const RlitgPirlCfg* cfg, int64_t B, T* q, const float* ac
     }
     const unsigned grid = (unsigned)((B + kEnvTile - 1) / kEnvTile);
     kern<<<grid, kEnvTile, smem, st>>>(c, B, q, action, timestep, max_timestep, targets, demos, Tmax, latent, sd,
-                                       has_scene, off[0], off[1], off[2], obs, reward, done, flags, counters, errs);
+                                       has_scene, (T)off[0], (T)off[1], (T)off[2], obs, reward, done, flags, counters, errs);
     return check_launch("pirl_env_kernel");
 }
 

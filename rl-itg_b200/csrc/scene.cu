@@ -133,6 +133,8 @@ struct Scene {
         d.S = S; d.nx = nx; d.ny = ny; d.nz = nz; d.wx = wx;
         d.origin[0] = origin[0]; d.origin[1] = origin[1]; d.origin[2] = origin[2];
         d.res = res;
+        d.origin_f[0] = (float)origin[0]; d.origin_f[1] = (float)origin[1]; d.origin_f[2] = (float)origin[2];
+        d.res_f = (float)res; d.inv_res_f = (float)(1.0 / res);
         return d;
     }
 };
@@ -228,7 +230,7 @@ struct CollideVisit {
 
 template <typename T>
 __global__ void __launch_bounds__(128) sphere_collide_kernel(const T* __restrict__ q, int64_t B, SceneDev sc,
-                                                             double ox, double oy, double oz,
+                                                             T ox, T oy, T oz,
                                                              uint8_t* __restrict__ out) {
     __shared__ float4 s_sph[kMaxSpheres];
     __shared__ int s_start[kNumLinks + 1];
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(128) sphere_collide_kernel(const T* __restrict
 #pragma unroll
     for (int j = 0; j < 7; j++) qv[j] = q[b * 7 + j];
     const GridMap<T> gm(sc);
-    CollideVisit<T> v{sc, gm, s_sph, s_start, {T(ox), T(oy), T(oz)}};
+    CollideVisit<T> v{sc, gm, s_sph, s_start, {ox, oy, oz}};
     walk_chain<T, 7>(qv, v);
     out[b] = v.hit ? 1 : 0;
 }
@@ -279,7 +281,7 @@ struct CollideSmemVisit {
 
 template <typename T>
 __global__ void __launch_bounds__(256) sphere_collide_smem_kernel(const T* __restrict__ q, int64_t B, SceneDev sc,
-                                                                  double ox, double oy, double oz,
+                                                                  T ox, T oy, T oz,
                                                                   uint8_t* __restrict__ out) {
     extern __shared__ __align__(16) uint32_t s_dil[];
     __shared__ float4 s_sph[kMaxSpheres];
@@ -296,7 +298,7 @@ __global__ void __launch_bounds__(256) sphere_collide_smem_kernel(const T* __res
         T qv[7];
 #pragma unroll
         for (int j = 0; j < 7; j++) qv[j] = q[b * 7 + j];
-        CollideSmemVisit<T> v{sc, gm, s_sph, s_start, s_cls, s_dil, words, {T(ox), T(oy), T(oz)}};
+        CollideSmemVisit<T> v{sc, gm, s_sph, s_start, s_cls, s_dil, words, {ox, oy, oz}};
         walk_chain<T, 7>(qv, v);
         out[b] = v.hit ? 1 : 0;
     }
@@ -313,11 +315,11 @@ int launch_sphere_collide(const T* q, int64_t B, const Scene* s, const double* b
         if (rc_attr) return rc_attr;
         const int num_sms = current_sm_count();
         const unsigned grid = (unsigned)std::min<int64_t>(num_sms, (B + 255) / 256);
-        kern<<<grid, 256, dil_bytes, st>>>(q, B, s->dev(), base_off[0], base_off[1], base_off[2], out);
+        kern<<<grid, 256, dil_bytes, st>>>(q, B, s->dev(), (T)base_off[0], (T)base_off[1], (T)base_off[2], out);
         return check_launch("sphere_collide_smem_kernel");
     }
-    sphere_collide_kernel<T><<<blocks_for(B, 128), 128, 0, st>>>(q, B, s->dev(), base_off[0], base_off[1],
-                                                                 base_off[2], out);
+    sphere_collide_kernel<T><<<blocks_for(B, 128), 128, 0, st>>>(q, B, s->dev(), (T)base_off[0], (T)base_off[1],
+                                                                 (T)base_off[2], out);
     return check_launch("sphere_collide_kernel");
 }
 template int launch_sphere_collide<float>(const float*, int64_t, const Scene*, const double*, uint8_t*, cudaStream_t);

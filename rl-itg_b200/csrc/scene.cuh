@@ -25,15 +25,23 @@ struct SceneDev {
     int nx, ny, nz, wx;
     double origin[3];
     double res;
+    // float copies made on the host: plain FP64 issues at 1/16 of the FP32 rate on this part, and converting these (plus
+    // the 1 / res division) in every thread of an FP32 kernel cost ~500 FP64-pipe cycles per warp
+    float origin_f[3];
+    float res_f, inv_res_f;
 };
 
 template <typename T>
 struct GridMap {  // world -> cell
     T ox, oy, oz, res, inv_res;
     int nx, ny, nz;
-    RLITG_DEV explicit GridMap(const SceneDev& s)
-        : ox(T(s.origin[0])), oy(T(s.origin[1])), oz(T(s.origin[2])), res(T(s.res)), inv_res(T(1.0 / s.res)),
-          nx(s.nx), ny(s.ny), nz(s.nz) {}
+    RLITG_DEV explicit GridMap(const SceneDev& s) : nx(s.nx), ny(s.ny), nz(s.nz) {
+        if constexpr (sizeof(T) == 8) {
+            ox = s.origin[0]; oy = s.origin[1]; oz = s.origin[2]; res = s.res; inv_res = 1.0 / s.res;
+        } else {
+            ox = s.origin_f[0]; oy = s.origin_f[1]; oz = s.origin_f[2]; res = s.res_f; inv_res = s.inv_res_f;
+        }
+    }
     RLITG_DEV int cell1(T x, T o) const {
         if constexpr (sizeof(T) == 8) return (int)floor((x - o) / res + T(0.5));  // literal (oracle) form
         else return (int)floorf(fmaf(x - o, inv_res, 0.5f));
