@@ -218,6 +218,32 @@ class TormBatch:
         return {"cost_pose": c[:, 0], "cost_rot": c[:, 1], "cost_vel": c[:, 2], "cost_acc": c[:, 3],
                 "cost_jerk": c[:, 4], "weighted": c[:, 6], "n_vel_violation": c[:, 7]}
 
+    # ---- binary feasibility, one flag per trajectory --------------------------------------------
+    def isCurrentTrajectoryCollisionFree(self, traj):
+        """torm/src/torm_optimizer.cpp:695-717 over all T rows: True = no waypoint collides (sphere-vs-grid stand-in for
+        the FCL test; True for every trajectory when use_collision_check_ is off or there is no scene)."""
+        N = traj.shape[0]
+        if self.scene is None or not self.parameters.use_collision_check_:
+            return torch.ones(N, dtype=torch.bool, device=self.device)
+        return self.scene.collide(traj.reshape(-1, 7)).reshape(N, self.T).sum(dim=1) == 0
+
+    def checkJointVelocityLimit(self, traj):
+        """:720-745: True = every consecutive pair of rows stays within vel_limit * time_duration_ (continuous joints by
+        shortest angular distance); always True when use_velocity_check_ is off."""
+        if not self.parameters.use_velocity_check_:
+            return torch.ones(traj.shape[0], dtype=torch.bool, device=self.device)
+        return self.cost_grad(traj, STAGE_EVAL)["costs"][:, 7] == 0
+
+    def checkSingularity(self, traj):
+        """:748-765: True = sqrt(det(J J^T)) >= singularity_lower_bound_ on every free row; always True when
+        use_singularity_check_ is off."""
+        N = traj.shape[0]
+        if not self.parameters.use_singularity_check_:
+            return torch.ones(N, dtype=torch.bool, device=self.device)
+        from .pirl_env import manipulability
+        yosh = manipulability(traj[:, 1:].reshape(-1, 7).contiguous()).reshape(N, self.T - 1)
+        return ~(yosh.abs() < self.parameters.singularity_lower_bound_).any(dim=1)
+
     def getWeightedPoseCost(self, traj):
         return self.cost_grad(traj, STAGE_EVAL)["costs"][:, 6]
 

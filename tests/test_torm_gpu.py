@@ -379,3 +379,32 @@ def test_concurrent_host_threads_on_two_streams(cuda_device):
     for th in threads:
         th.join()
     assert not errors, errors
+
+
+def test_binary_feasibility_members(cuda_device):
+    """isCurrentTrajectoryCollisionFree / checkJointVelocityLimit / checkSingularity (torm_optimizer.cpp:695-765) per
+    trajectory against the oracle pieces."""
+    import torch
+    from oracle import oracle as O
+    from rlitg_b200 import fetch, torm as TM
+    N, T = 24, 40
+    traj, targets, osc, gsc = make_problem(N, T, 9, cuda_device)
+    traj[3, 10, 1] += 0.5          # one jump: velocity violation
+    traj[5, 1:, 3] = 0.0           # elbow straight: wrist on the shoulder axis region -> small manipulability
+    pr = TM.TormParameters(min_clearence_=0.3, use_singularity_check_=True, singularity_lower_bound_=0.02)
+    tb = TM.TormBatch(targets, pr, gsc, cuda_device, torch.float64)
+    t = torch.tensor(traj, dtype=torch.float64, device=cuda_device)
+    free = tb.isCurrentTrajectoryCollisionFree(t).cpu().numpy()
+    want_free = ~O.sphere_collide(traj.reshape(-1, 7), osc, fetch.BASE_OFFSET).reshape(N, T).any(axis=1)
+    assert np.array_equal(free, want_free) and 0 < want_free.sum() < N
+    vel_ok = tb.checkJointVelocityLimit(t).cpu().numpy()
+    d = traj[:, 1:] - traj[:, :-1]
+    cj = fetch.CONTINUOUS.astype(bool)
+    d[:, :, cj] = (d[:, :, cj] + np.pi) % (2 * np.pi) - np.pi
+    want_vel = ~(np.abs(d) / pr.time_duration_ > np.asarray(fetch.VEL_LIMIT)).any(axis=(1, 2))
+    assert np.array_equal(vel_ok, want_vel) and not want_vel[3]
+    sing_ok = tb.checkSingularity(t).cpu().numpy()
+    yosh = O.manipulability(traj[:, 1:].reshape(-1, 7)).reshape(N, T - 1)
+    want_sing = ~(np.abs(yosh) < 0.02).any(axis=1)
+    assert np.array_equal(sing_ok, want_sing)
+    gsc.close()
