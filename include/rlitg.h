@@ -253,6 +253,17 @@ RLITG_API int rlitg_torm_cost_grad(const void* traj, const void* targets, int64_
                                    int stage_mask, const int32_t* stochastic_idx, void* inc_smooth, void* inc_coll,
                                    void* inc_pose, void* costs, float* active, void* stream);
 
+/* Same with the optimiser stage given per trajectory (traj_stage [N] int32 on the device, 0 = feasible, 1 = end-pose; from
+ * rlitg_torm_stage_decide): trajectories in the end-pose stage skip the collision / smoothness kernel (their costs[5] is
+ * 0 and their inc_smooth / inc_coll rows are left untouched), trajectories in the feasible stage skip the end-pose
+ * increments (inc_pose rows untouched).  The evaluator and end-pose cost sums are computed for all.  For
+ * lr_schedule_mode_ 1, where every optimiser picks its stage itself (torm/src/torm_optimizer.cpp:400-412). */
+RLITG_API int rlitg_torm_cost_grad_staged(const void* traj, const void* targets, int64_t N, int dtype,
+                                          const RlitgScene* scene, const RlitgSmooth* smooth, const RlitgTormParams* p,
+                                          int stage_mask, const int32_t* traj_stage, const int32_t* stochastic_idx,
+                                          void* inc_smooth, void* inc_coll, void* inc_pose, void* costs, float* active,
+                                          void* stream);
+
 /* Host-buffer form of rlitg_torm_cost_grad: traj, targets, stochastic_idx and every output are HOST pointers (the
  * reference's TormOptimizer holds Eigen matrices on the host); copies in / out through an internal device workspace
  * and returns when the results are in the caller's buffers.  scene / smooth are the same device-resident handles. */
@@ -306,6 +317,12 @@ typedef struct RlitgTormSchedule {
     double learning_rate;       /* parameters_->learning_rate_ */
     double learning_rate_min, learning_rate_max; /* / 100 and * 1000 (:99-101) */
 } RlitgTormSchedule;
+/* The stage choice alone (:400-412), to be made BEFORE the cost evaluation of the half-iteration sch->stage so that
+ * rlitg_torm_cost_grad_staged can skip the work the other stage would need; pass stage_idx = NULL to
+ * rlitg_torm_bookkeep then. */
+RLITG_API int rlitg_torm_stage_decide(int64_t N, int dtype, const void* lr, const uint8_t* infea_col,
+                                      const uint8_t* infea_vel, const RlitgTormSchedule* sch, int32_t* stage_idx,
+                                      void* stream);
 RLITG_API int rlitg_torm_bookkeep(const void* traj, void* best_traj, int64_t N, int T, int dtype, const void* costs,
                                   const uint8_t* hits, const uint8_t* singular, void* alpha, void* lr,
                                   uint8_t* infea_col, uint8_t* infea_vel, void* best_cost, int32_t* stage_idx,

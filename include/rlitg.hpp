@@ -404,21 +404,26 @@ class TormBatchOptimizer {
                 lr_iter_.upload(&v, 1);
             }
             for (int stage = 0; stage < 2; stage++) {
-                if (lr_schedule_mode == 1) run(full);
-                else if (stage == 0) run(RLITG_STAGE_SMOOTH | RLITG_STAGE_EVAL | (scene_ ? RLITG_STAGE_COLL : 0));
-                else run(RLITG_STAGE_POSE_GRAD | RLITG_STAGE_EVAL);
-                if (check_col)
-                    check(rlitg_sphere_grid_collide(traj_.data(), N_ * T_, RLITG_F32, scene_->handle(), cp_.base_off,
-                                                    hits_.data(), nullptr));
                 RlitgTormSchedule sch;
                 std::memset(&sch, 0, sizeof(sch));
                 sch.lr_schedule_mode = lr_schedule_mode; sch.stage = stage;
                 sch.use_collision_check = check_col; sch.use_velocity_check = par_.use_velocity_check_;
                 sch.learning_rate = lr0; sch.learning_rate_min = lr_min; sch.learning_rate_max = lr_max;
+                if (lr_schedule_mode == 1) {  // every optimiser picks its stage; the cost kernels skip the other one's work
+                    check(rlitg_torm_stage_decide(N_, RLITG_F32, lr_.data(), infea_col_.data(), infea_vel_.data(), &sch,
+                                                  stage_idx_.data(), nullptr));
+                    run(full, nullptr, stage_idx_.data());
+                } else if (stage == 0) {
+                    run(RLITG_STAGE_SMOOTH | RLITG_STAGE_EVAL | (scene_ ? RLITG_STAGE_COLL : 0));
+                } else {
+                    run(RLITG_STAGE_POSE_GRAD | RLITG_STAGE_EVAL);
+                }
+                if (check_col)
+                    check(rlitg_sphere_grid_collide(traj_.data(), N_ * T_, RLITG_F32, scene_->handle(), cp_.base_off,
+                                                    hits_.data(), nullptr));
                 check(rlitg_torm_bookkeep(traj_.data(), best_.data(), N_, T_, RLITG_F32, costs_.data(),
                                           check_col ? hits_.data() : nullptr, nullptr, alpha_.data(), lr_.data(),
-                                          infea_col_.data(), infea_vel_.data(), best_cost_.data(),
-                                          lr_schedule_mode == 1 ? stage_idx_.data() : nullptr,
+                                          infea_col_.data(), infea_vel_.data(), best_cost_.data(), nullptr,
                                           lr_schedule_mode == 2 ? lr_iter_.data() : nullptr, &sch, nullptr));
                 update(stage, lr_schedule_mode, lr_schedule_mode == 1 ? stage_idx_.data() : nullptr);
             }
@@ -441,10 +446,10 @@ class TormBatchOptimizer {
         for (int64_t n = 0; n < N_; n++) out[n] = c[n * RLITG_TORM_NCOST + k];
         return out;
     }
-    void run(int stage_mask, const int32_t* stochastic_idx_dev = nullptr) {
+    void run(int stage_mask, const int32_t* stochastic_idx_dev = nullptr, const int32_t* traj_stage_dev = nullptr) {
         if ((stage_mask & RLITG_STAGE_COLL) && !scene_) throw Error(RLITG_ERR_NULL, "collision stage needs a scene");
-        check(rlitg_torm_cost_grad(traj_.data(), targets_.data(), N_, RLITG_F32, scene_ ? scene_->handle() : nullptr,
-                                   joint_costs_.handle(), &cp_, stage_mask, stochastic_idx_dev,
+        check(rlitg_torm_cost_grad_staged(traj_.data(), targets_.data(), N_, RLITG_F32, scene_ ? scene_->handle() : nullptr,
+                                   joint_costs_.handle(), &cp_, stage_mask, traj_stage_dev, stochastic_idx_dev,
                                    smoothness_increments_.data(), collision_increments_.data(),
                                    endPose_increments_.data(), costs_.data(), nullptr, nullptr));
     }

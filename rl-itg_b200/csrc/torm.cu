@@ -226,15 +226,18 @@ constexpr int kNRedPose = 11;
 template <typename T, int MAXREG>
 __global__ void __launch_bounds__(kTormMaxThreads) __maxnreg__(MAXREG)
 torm_pose_eval_kernel(TormP<T> P, const T* __restrict__ traj, const T* __restrict__ targets, int stage_mask,
-                      int zero_coll_cost, T* __restrict__ inc_pose, T* __restrict__ costs) {
+                      int zero_coll_cost, T* __restrict__ inc_pose, T* __restrict__ costs,
+                      const int32_t* __restrict__ traj_stage) {
     const int CH = blockDim.x, tid = threadIdx.x, Tn = P.Tn;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* s_traj = reinterpret_cast<T*>(smem_raw);  // [(CH + 12)][7]  rows c0-6 .. c0+CH+5, clamped
     T* s_v = s_traj + (CH + 12) * 7;             // [(CH + 3)][7]   first differences of continuous joints
     T* s_red = s_v + (CH + 3) * 7;               // [8][kNRedPose]
-    const bool do_pgrad = (stage_mask & RLITG_STAGE_POSE_GRAD) != 0;
-    const bool do_eval = (stage_mask & RLITG_STAGE_EVAL) != 0;
     const int64_t n = blockIdx.x;
+    // traj_stage (nullable): per-trajectory stage of the optimiser; the end-pose increments are only computed for
+    // trajectories in the end-pose stage (1), the collision / smoothness kernel only runs for those in stage 0
+    const bool do_pgrad = (stage_mask & RLITG_STAGE_POSE_GRAD) != 0 && (!traj_stage || traj_stage[n] == 1);
+    const bool do_eval = (stage_mask & RLITG_STAGE_EVAL) != 0;
     const T* tr = traj + n * (int64_t)Tn * 7;
     T* o_pose = inc_pose ? inc_pose + n * (int64_t)(Tn - 1) * 7 : nullptr;
 
@@ -359,7 +362,7 @@ __global__ void __launch_bounds__(kTormMaxThreads) __maxnreg__(MAXREG)
 torm_coll_smooth_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S, const T* __restrict__ Aband,
                         int stage_mask, int zero_pose_costs, const int32_t* __restrict__ stoch,
                         T* __restrict__ inc_smooth, T* __restrict__ inc_coll, T* __restrict__ costs,
-                        float* __restrict__ active) {
+                        float* __restrict__ active, const int32_t* __restrict__ traj_stage) {
     const int CH = blockDim.x, tid = threadIdx.x, Tn = P.Tn;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* s_traj = reinterpret_cast<T*>(smem_raw);  // [(CH + 12)][7]
@@ -382,6 +385,18 @@ torm_coll_smooth_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int
         if (tid <= kNumLinks) s_start[tid] = sc.link_start[tid];
     }
     const int64_t n = blockIdx.x;
+    if (traj_stage && traj_stage[n] != 0) {  // this trajectory takes the end-pose stage: nothing to do here
+        if (tid == 0) {
+            T* c = costs + n * RLITG_TORM_NCOST;
+            c[5] = T(0);
+            if (zero_pose_costs) {
+                c[0] = c[1] = c[2] = c[3] = c[4] = T(0);
+                c[6] = c[7] = c[8] = c[9] = T(0);
+            }
+            if (active) active[n] = 0.f;
+        }
+        return;
+    }
     const T* tr = traj + n * (int64_t)Tn * 7;
     const int F = Tn - 1;
     T* o_smooth = inc_smooth ? inc_smooth + n * (int64_t)F * 7 : nullptr;
@@ -664,7 +679,7 @@ static TormP<T> convert_params(const RlitgTormParams& p) {
 template <typename T>
 static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* scene, const Smooth* smooth,
                        const RlitgTormParams* p, int stage_mask, const int32_t* stoch, T* inc_smooth, T* inc_coll,
-                       T* inc_pose, T* costs, float* active, cudaStream_t st) {
+                       T* inc_pose, T* costs, float* active, const int32_t* traj_stage, cudaStream_t st) {
     TormP<T> P = convert_params<T>(*p);
     const int CH = std::min(kTormMaxThreads, ((p->T + 31) / 32) * 32);
     const bool run_pose = (stage_mask & (RLITG_STAGE_POSE | RLITG_STAGE_POSE_GRAD | RLITG_STAGE_EVAL)) != 0;
@@ -716,7 +731,7 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
         if (stage_mask & RLITG_STAGE_SMOOTH)
             band = reinterpret_cast<const T*>(sizeof(T) == 4 ? (const void*)smooth->d_band32 : (const void*)smooth->d_band64);
         kern<<<(unsigned)N, CH, smem, st>>>(P, traj, sd, S, band, stage_mask, run_pose ? 0 : 1, stoch, inc_smooth, inc_coll,
-                                            costs, active);
+                                            costs, active, traj_stage);
         int rc = check_launch("torm_coll_smooth_kernel");
         if (rc) return rc;
     }
@@ -730,7 +745,7 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
             int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "torm_pose_eval_kernel");
             if (rc_attr) return rc_attr;
         }
-        kern<<<(unsigned)N, CH, smem, st_pose>>>(P, traj, targets, stage_mask, run_coll ? 0 : 1, inc_pose, costs);
+        kern<<<(unsigned)N, CH, smem, st_pose>>>(P, traj, targets, stage_mask, run_coll ? 0 : 1, inc_pose, costs, traj_stage);
         int rc = check_launch("torm_pose_eval_kernel");
         if (rc) return rc;
     }
@@ -802,6 +817,15 @@ RLITG_API int rlitg_torm_cost_grad(const void* traj, const void* targets, int64_
                                    const RlitgScene* scene, const RlitgSmooth* smooth, const RlitgTormParams* p,
                                    int stage_mask, const int32_t* stochastic_idx, void* inc_smooth, void* inc_coll,
                                    void* inc_pose, void* costs, float* active, void* stream) {
+    return rlitg_torm_cost_grad_staged(traj, targets, N, dtype, scene, smooth, p, stage_mask, nullptr, stochastic_idx,
+                                       inc_smooth, inc_coll, inc_pose, costs, active, stream);
+}
+
+RLITG_API int rlitg_torm_cost_grad_staged(const void* traj, const void* targets, int64_t N, int dtype,
+                                          const RlitgScene* scene, const RlitgSmooth* smooth, const RlitgTormParams* p,
+                                          int stage_mask, const int32_t* traj_stage, const int32_t* stochastic_idx,
+                                          void* inc_smooth, void* inc_coll, void* inc_pose, void* costs, float* active,
+                                          void* stream) {
     if (!p) return set_error(RLITG_ERR_NULL, "params is NULL");
     if (p->D != 7) return set_error(RLITG_ERR_SHAPE, "TORM runs the 7-joint arm chain (D = 7)");
     if (p->T < 5 || p->T > 8192) return set_error(RLITG_ERR_SHAPE, "T must be in 5..8192");
@@ -821,9 +845,9 @@ RLITG_API int rlitg_torm_cost_grad(const void* traj, const void* targets, int64_
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == RLITG_F32)
         return launch_torm<float>((const float*)traj, (const float*)targets, N, sc, sm, p, stage_mask, stochastic_idx,
-                                  (float*)inc_smooth, (float*)inc_coll, (float*)inc_pose, (float*)costs, active, st);
+                                  (float*)inc_smooth, (float*)inc_coll, (float*)inc_pose, (float*)costs, active, traj_stage, st);
     return launch_torm<double>((const double*)traj, (const double*)targets, N, sc, sm, p, stage_mask, stochastic_idx,
-                               (double*)inc_smooth, (double*)inc_coll, (double*)inc_pose, (double*)costs, active, st);
+                               (double*)inc_smooth, (double*)inc_coll, (double*)inc_pose, (double*)costs, active, traj_stage, st);
 }
 
 }  // extern "C"

@@ -386,6 +386,40 @@ torm_bookkeep_kernel(BookP P, const T* __restrict__ traj, T* __restrict__ best_t
 }
 }  // namespace rlitg
 
+namespace rlitg {
+template <typename T>
+__global__ void torm_stage_decide_kernel(int64_t N, int mode, int stage, T lr_max, const T* __restrict__ lr,
+                                         const uint8_t* __restrict__ infea_col, const uint8_t* __restrict__ infea_vel,
+                                         int32_t* __restrict__ stage_idx) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const bool col = infea_col[n] != 0, vel = infea_vel[n] != 0;
+    bool feasible_stage;
+    if (stage == 0) feasible_stage = !(mode == 1 && lr[n] < T(1e-2) && !col && !vel);
+    else feasible_stage = (mode == 1 && lr[n] == lr_max && col);
+    stage_idx[n] = feasible_stage ? 0 : 1;
+}
+}  // namespace rlitg
+
+extern "C" RLITG_API int rlitg_torm_stage_decide(int64_t N, int dtype, const void* lr, const uint8_t* infea_col,
+                                                 const uint8_t* infea_vel, const RlitgTormSchedule* sch,
+                                                 int32_t* stage_idx, void* stream) {
+    if (!sch) return set_error(RLITG_ERR_NULL, "schedule is NULL");
+    if (dtype != RLITG_F32 && dtype != RLITG_F64) return set_error(RLITG_ERR_DTYPE, "dtype must be RLITG_F32 or RLITG_F64");
+    if (N < 0) return set_error(RLITG_ERR_SHAPE, "N out of range");
+    if (N == 0) return RLITG_OK;
+    if (!lr || !infea_col || !infea_vel || !stage_idx) return set_error(RLITG_ERR_NULL, "lr / infea_* / stage_idx is NULL");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned grid = (unsigned)((N + 255) / 256);
+    if (dtype == RLITG_F32)
+        torm_stage_decide_kernel<float><<<grid, 256, 0, st>>>(N, sch->lr_schedule_mode, sch->stage, (float)sch->learning_rate_max,
+                                                              (const float*)lr, infea_col, infea_vel, stage_idx);
+    else
+        torm_stage_decide_kernel<double><<<grid, 256, 0, st>>>(N, sch->lr_schedule_mode, sch->stage, sch->learning_rate_max,
+                                                               (const double*)lr, infea_col, infea_vel, stage_idx);
+    return check_launch("torm_stage_decide_kernel");
+}
+
 extern "C" RLITG_API int rlitg_torm_bookkeep(const void* traj, void* best_traj, int64_t N, int T, int dtype,
                                              const void* costs, const uint8_t* hits, const uint8_t* singular,
                                              void* alpha, void* lr, uint8_t* infea_col, uint8_t* infea_vel,

@@ -38,6 +38,8 @@ lib.rlitg_smooth_destroy.argtypes = [_vp]
 lib.rlitg_smooth_get.argtypes = [_vp, _vp, C.POINTER(C.c_double), _vp]
 lib.rlitg_torm_cost_grad.argtypes = [_vp, _vp, C.c_int64, C.c_int, _vp, _vp, C.POINTER(RlitgTormParams), C.c_int, _vp,
                                      _vp, _vp, _vp, _vp, _vp, _vp]
+lib.rlitg_torm_cost_grad_staged.argtypes = [_vp, _vp, C.c_int64, C.c_int, _vp, _vp, C.POINTER(RlitgTormParams), C.c_int,
+                                            _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
 
 
 @dataclass
@@ -150,9 +152,11 @@ class TormBatch:
             self._call_cache.clear()
         return t
 
-    def cost_grad(self, traj, stage_mask, stochastic_idx=None, want_active=False):
+    def cost_grad(self, traj, stage_mask, stochastic_idx=None, want_active=False, traj_stage=None):
         """One call of rlitg_torm_cost_grad.  Returns dict(costs [N,10], inc_smooth, inc_coll, inc_pose
-        [N,T-1,7] or None, active [N] or None).  Output tensors are reused between calls."""
+        [N,T-1,7] or None, active [N] or None).  Output tensors are reused between calls.
+        traj_stage: optional int32 [N] device tensor (0 feasible / 1 end-pose per trajectory): each trajectory only gets
+        the increments its stage needs (rlitg_torm_cost_grad_staged); rows of the other stage are left untouched."""
         if not traj.is_contiguous():
             traj = traj.contiguous()
         st = None
@@ -161,7 +165,7 @@ class TormBatch:
                                     and stochastic_idx.is_cuda) else \
                 torch.as_tensor(stochastic_idx).to(self.device, torch.int32).contiguous()
         key = (traj.data_ptr(), tuple(traj.shape), traj.dtype, int(stage_mask), None if st is None else st.data_ptr(),
-               bool(want_active))
+               bool(want_active), None if traj_stage is None else traj_stage.data_ptr())
         hit = self._call_cache.get(key)
         if hit is None:
             N, T, D = traj.shape
@@ -179,13 +183,13 @@ class TormBatch:
             code = _lib.F32 if traj.dtype == torch.float32 else _lib.F64
             args = (traj.data_ptr(), self.endPoses_desired_.data_ptr(), N, code,
                     None if self.scene is None else self.scene.handle, self.joint_costs_.handle, C.byref(self._cp),
-                    int(stage_mask), p(st), p(inc_s), p(inc_c), p(inc_p), costs.data_ptr(), p(active))
+                    int(stage_mask), p(traj_stage), p(st), p(inc_s), p(inc_c), p(inc_p), costs.data_ptr(), p(active))
             hit = (args, dict(costs=costs, inc_smooth=inc_s, inc_coll=inc_c, inc_pose=inc_p, active=active))
             if len(self._call_cache) > 64:
                 self._call_cache.clear()
             self._call_cache[key] = hit
         with _lib.on_device(self.device):
-            rc = lib.rlitg_torm_cost_grad(*hit[0], torch.cuda.current_stream().cuda_stream)
+            rc = lib.rlitg_torm_cost_grad_staged(*hit[0], torch.cuda.current_stream().cuda_stream)
         if rc:
             check(rc)
         return hit[1]
@@ -265,6 +269,7 @@ class RlitgTormSchedule(C.Structure):
                 ("learning_rate_max", C.c_double)]
 
 
+lib.rlitg_torm_stage_decide.argtypes = [C.c_int64, C.c_int, _vp, _vp, _vp, C.POINTER(RlitgTormSchedule), _vp, _vp]
 lib.rlitg_torm_bookkeep.argtypes = [_vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                     C.POINTER(RlitgTormSchedule), _vp]
 lib.rlitg_torm_update_staged.argtypes = [_vp, C.c_int64, C.c_int, _vp, C.POINTER(RlitgTormParams),
@@ -375,12 +380,17 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
 
     def sub_step(stage):
         if mode == 1:
-            mask = full_mask
+            # every optimiser picks its own stage (:400-412) from the state before this half-iteration; the cost kernels
+            # then only do, per trajectory, what that stage needs
+            with _lib.on_device(dev):
+                check(lib.rlitg_torm_stage_decide(N, code, lr.data_ptr(), infea_col.data_ptr(), infea_vel.data_ptr(),
+                                                  C.byref(sch[stage]), stage_idx.data_ptr(),
+                                                  torch.cuda.current_stream(dev).cuda_stream))
+            r = self.cost_grad(traj, full_mask, traj_stage=stage_idx)
         elif stage == 0:
-            mask = STAGE_SMOOTH | STAGE_EVAL | (STAGE_COLL if has_scene else 0)
+            r = self.cost_grad(traj, STAGE_SMOOTH | STAGE_EVAL | (STAGE_COLL if has_scene else 0))
         else:
-            mask = STAGE_POSE_GRAD | STAGE_EVAL
-        r = self.cost_grad(traj, mask)
+            r = self.cost_grad(traj, STAGE_POSE_GRAD | STAGE_EVAL)
         hits = self.scene.collide(traj.reshape(-1, 7)) if sch[stage].use_collision_check else None
         if singular is not None:
             from .pirl_env import manipulability
@@ -392,8 +402,7 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
                                           None if hits is None else hits.data_ptr(),
                                           None if singular is None else singular.data_ptr(), al.data_ptr(), lr.data_ptr(),
                                           infea_col.data_ptr(), infea_vel.data_ptr(), best_cost.data_ptr(),
-                                          stage_idx.data_ptr() if mode == 1 else None,
-                                          lr_iter.data_ptr() if mode == 2 else None, C.byref(sch[stage]),
+                                          None, lr_iter.data_ptr() if mode == 2 else None, C.byref(sch[stage]),
                                           torch.cuda.current_stream(dev).cuda_stream))
         # ---- increments -> trajectory (:562-576)
         inc_c = r["inc_coll"] if r["inc_coll"] is not None else zeros
