@@ -248,13 +248,11 @@ __global__ void __launch_bounds__(kEnvTile, sizeof(T) == 4 ? 4 : 1) pirl_env_ker
         for (int k = 0; k < cfg.z_dim; k++) row[fo + k] = latent[b * cfg.z_dim + k];
 
         if constexpr (kStep) {
-            // ---- _compute_task_reward :495-513 (target index = timestep; clamped into the path as a memory-safety
-            // guard -- the reference raises IndexError when a finished episode is stepped)
-            const int tsc = min(max(ts, 0), Tmax - 1);
+            // ---- _compute_task_reward :495-513 (target index = timestep, loaded above into pf_tp with the index clamped
+            // into the path as a memory-safety guard -- the reference raises IndexError when a finished episode is stepped)
             T tp[7];
 #pragma unroll
             for (int k = 0; k < 7; k++) tp[k] = pf_tp[k];
-            (void)tsc;
             const T dx = tp[0] - ee.p.x, dy = tp[1] - ee.p.y, dz = tp[2] - ee.p.z;
             const T d_err = sqrt_t(dx * dx + dy * dy + dz * dz);
             T ex, ey, ez, ew;
