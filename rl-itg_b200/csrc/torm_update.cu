@@ -209,15 +209,22 @@ torm_update_kernel(UpdP P, T* __restrict__ traj, int64_t N, const T* __restrict_
                 else if (v < P.jmin[j]) amount = P.jmin[j] - v;
                 if (fabs(amount) > best) { best = fabs(amount); idx = i; }  // first maximum wins
             }
-            s_best[gt] = idx >= 0 ? best : 0.0;
-            s_idx[gt] = idx;
+            // winner over the group: largest violation, smallest row index on ties (warp shuffles, then the two warps)
+            double wb = idx >= 0 ? best : 0.0;
+            int wi = idx;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, wb, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+                if (oi >= 0 && (wi < 0 || ob > wb || (ob == wb && oi < wi))) { wb = ob; wi = oi; }
+            }
+            if ((gt & 31) == 0) { s_best[gt >> 5] = wb; s_idx[gt >> 5] = wi; }
             group_sync(g);
-            // every thread resolves the winner the same way: largest violation, smallest row index on ties
-            double wb = 0.0;
-            int wi = -1;
-            for (int t = 0; t < kUpdGroup; t++) {
-                const int ti = s_idx[t];
-                if (ti >= 0 && (s_best[t] > wb || (s_best[t] == wb && ti < wi))) { wb = s_best[t]; wi = ti; }
+            {
+                const double b0 = s_best[0], b1 = s_best[1];
+                const int i0 = s_idx[0], i1 = s_idx[1];
+                wb = b0; wi = i0;
+                if (i1 >= 0 && (wi < 0 || b1 > wb || (b1 == wb && i1 < wi))) { wb = b1; wi = i1; }
             }
             group_sync(g);
             if (wi < 0) break;
