@@ -2,8 +2,9 @@
 
 Stated tolerances.  FP64 build: 1e-10 on everything.  FP32: observation 1e-5 relative (floor 2e-6); dist_err
 2e-6; rot_err compared through cos(r/2) to 5e-7 (r = 2 acos|w| is ill-conditioned near 0: SURVEY section 7);
-reward 1e-4 + the propagated rot_err sensitivity; flags identical except where an error sits within tolerance of
-its threshold (counted)."""
+reward 2e-4 + the propagated rot_err / null-space sensitivities; null-space objective 1e-6 + 1.5 eps32 cond(J) |e|
+(FP64: 1e-12 + 0.3 eps64 cond(J)^2 |e|); flags identical except where an error sits within tolerance of its threshold
+(counted)."""
 import numpy as np
 import pytest
 
