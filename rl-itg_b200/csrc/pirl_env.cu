@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(kEnvTile, sizeof(T) == 4 ? 4 : 1) pirl_env_ker
         const int dr = kEnvTile / G, dg = kEnvTile - dr * G;
         for (int i = tid; i < n * G; i += kEnvTile) {
             const T* sp = s_obs + r * OS + 4 * g;
-            reinterpret_cast<float4*>(dst)[i] = make_float4((float)sp[0], (float)sp[1], (float)sp[2], (float)sp[3]);
+            st_stream(reinterpret_cast<float4*>(dst) + i, make_float4((float)sp[0], (float)sp[1], (float)sp[2], (float)sp[3]));
             r += dr; g += dg;
             if (g >= G) { g -= G; r++; }
         }
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(kEnvTile, sizeof(T) == 4 ? 4 : 1) pirl_env_ker
         int r = tid / O, c = tid - r * O;
         const int dr = kEnvTile / O, dc = kEnvTile - dr * O;
         for (int i = tid; i < n * O; i += kEnvTile) {
-            dst[i] = s_obs[r * OS + c];
+            st_stream(dst + i, s_obs[r * OS + c]);
             r += dr; c += dc;
             if (c >= O) { c -= O; r++; }
         }
