@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 
+#include "rlitg_common.cuh"
 #include "rlitg_internal.h"
 
 namespace rlitg {
@@ -243,9 +244,7 @@ __global__ void __launch_bounds__(128) write_probe_kernel(char* __restrict__ dst
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (threadIdx.x == 0) {
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + t * tile_bytes),
-                         "r"((uint32_t)__cvta_generic_to_shared(stage)), "r"(tile_bytes)
-                         : "memory");
+            rlitg::bulk_store(dst + t * tile_bytes, stage, (uint32_t)tile_bytes);  // same evict-first stores as fk_jac
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
     }
