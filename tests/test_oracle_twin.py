@@ -117,3 +117,45 @@ def test_chain_constants_against_the_reference_data_files():
     with open(os.path.join(REF, "fetch_moveit_assistant/config/joint_limits.yaml")) as f:
         jl = yaml.safe_load(f)["joint_limits"]
     assert [jl[n]["max_velocity"] for n in y["joint_names"]] == fetch.VEL_LIMIT.tolist()
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (GPU box)")
+def test_parameter_defaults_against_the_reference_main():
+    """TormParameters defaults (rl-itg_b200/torm.py) against the assignments of initParameters in the reference's
+    torm/src/torm_main.cpp:50-92, read as text (nothing of the reference is executed), and the PIRL env constants of
+    make_cfg against the literals of pirl/script/envs/PirlEnv.py:122-172."""
+    import re
+    import ctypes as C
+    pytest.importorskip("torch")
+    try:
+        from rlitg_b200.torm import TormParameters
+        from rlitg_b200.pirl_env import make_cfg
+    except OSError:
+        pytest.skip("librlitg.so not built")
+    src = open(os.path.join(REF, "torm/src/torm_main.cpp")).read()
+    body = src[src.index("void initParameters"):src.index("// random_obs_63_1")]
+    found = {}
+    for name, val in re.findall(r"params_\.(\w+)\s*=\s*([^;]+);", body):
+        found.setdefault(name, []).append(val.strip())
+    pr = TormParameters()
+    checked = 0
+    for name, vals in found.items():
+        val = vals[-1]  # the non-debug branch comes last
+        if name == "smoothness_update_weight_":
+            assert val == "30.0/endPose_size" and pr.smoothness_update_weight_ == 30.0
+        elif val in ("true", "false"):
+            assert getattr(pr, name) == (val == "true"), name
+        else:
+            assert float(getattr(pr, name)) == float(val), name
+        checked += 1
+    assert checked >= 22
+    env = open(os.path.join(REF, "pirl/script/envs/PirlEnv.py")).read()
+    lit = lambda n: float(re.search(r"self\.%s\s*=\s*([-0-9.e]+)" % n, env).group(1))
+    lst = lambda n: [float(v) for v in re.search(r"self\.%s\s*=\s*\[([^\]]+)\]" % n, env).group(1).split(",")]
+    c = make_cfg()
+    assert (c.thr_early_stop, c.thr_dist, c.thr_rot, c.thr_imitate) == (lit("threshold_early_stop_dist"), lit("threshold_dist_err"),
+                                                                       lit("threshold_rot_err"), lit("threshold_imitate_err"))
+    assert c.zero_task_dist == 2 * lit("threshold_dist_err")
+    assert list(c.dist_p) == lst("dist_reward_params") and list(c.rot_p) == lst("rot_reward_params")
+    assert list(c.imit_p) == lst("imit_reward_params") and list(c.null_p) == lst("null_space_imit_reward_params")
+    assert (c.w_col, c.w_jlimit, c.w_early_stop) == (lit("w_col"), lit("w_jlimit"), lit("w_early_stop"))
