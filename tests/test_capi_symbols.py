@@ -35,3 +35,16 @@ def test_argument_validation_without_gpu():
     assert b"aligned" in lib.rlitg_last_error()
     assert lib.rlitg_fk_jac(ctypes.c_void_p(16), 4, 7, 0, 0, None, None, None, None, None) == -1  # all outputs NULL
     assert lib.rlitg_fk_jac(None, 0, 7, 0, 0, None, None, None, None, None) == 0  # empty batch is a no-op
+
+
+def test_header_is_strict_c99(tmp_path):
+    """include/rlitg.h is a C header (the reference's Python side would bind it through ctypes / cffi, its C++ side
+    includes it directly): it must compile as pedantic C99 on its own."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "rlitg.h"\nint main(void) { return rlitg_version() > 0 ? 0 : 1; }\n')
+    r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                        "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
