@@ -109,11 +109,12 @@ class Scene:
             check(lib.rlitg_scene_get_dilated(self._h, C.byref(n), radii.ctypes.data, bits.ctypes.data))
         return radii, bits
 
-    def collide(self, q):
-        """cc_srv for a batch: uint8 [B], 1 = some sphere penetrates an occupied region."""
+    def collide(self, q, out=None):
+        """cc_srv for a batch: uint8 [B], 1 = some sphere penetrates an occupied region (`out`: optional result buffer)."""
         q = q.contiguous()
         B = q.shape[0]
-        out = torch.empty(B, dtype=torch.uint8, device=q.device)
+        if out is None:
+            out = torch.empty(B, dtype=torch.uint8, device=q.device)
         dt = _lib.F32 if q.dtype == torch.float32 else _lib.F64
         with _lib.on_device(q.device):
             check(lib.rlitg_sphere_grid_collide(q.data_ptr(), B, dt, self._h, self.base_offset.ctypes.data,

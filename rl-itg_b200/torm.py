@@ -369,6 +369,8 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
     zeros = None if has_scene else torch.zeros(N, self.T - 1, 7, device=dev, dtype=dt)
     full_mask = STAGE_SMOOTH | STAGE_POSE_GRAD | STAGE_EVAL | (STAGE_COLL if has_scene else 0)
 
+    if use_cuda_graph is None:
+        use_cuda_graph = False  # ~10 launches per iteration: eager launching keeps up with the GPU (measured)
     sch = [RlitgTormSchedule(), RlitgTormSchedule()]
     for k in (0, 1):
         sch[k].lr_schedule_mode, sch[k].stage = mode, k
@@ -377,8 +379,20 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
         sch[k].learning_rate, sch[k].learning_rate_min, sch[k].learning_rate_max = lr0, lr_min, lr_max
     code = _lib.F32 if dt == torch.float32 else _lib.F64
     singular = torch.zeros(N, dtype=torch.uint8, device=dev) if pr.use_singularity_check_ else None
+    hits_buf = torch.empty(N * self.T, dtype=torch.uint8, device=dev) if sch[0].use_collision_check else None
+
+    # the sphere-grid flags only read the trajectory, like the cost kernels: they run on a side stream next to them
+    cur_stream = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(device=dev) if (hits_buf is not None and not use_cuda_graph) else None
+    ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
 
     def sub_step(stage):
+        if side is not None:
+            ev_fork.record(cur_stream)
+            side.wait_event(ev_fork)
+            with torch.cuda.stream(side):
+                self.scene.collide(traj.reshape(-1, 7), out=hits_buf)
+                ev_join.record(side)
         if mode == 1:
             # every optimiser picks its own stage (:400-412) from the state before this half-iteration; the cost kernels
             # then only do, per trajectory, what that stage needs
@@ -391,7 +405,13 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
             r = self.cost_grad(traj, STAGE_SMOOTH | STAGE_EVAL | (STAGE_COLL if has_scene else 0))
         else:
             r = self.cost_grad(traj, STAGE_POSE_GRAD | STAGE_EVAL)
-        hits = self.scene.collide(traj.reshape(-1, 7)) if sch[stage].use_collision_check else None
+        hits = None
+        if sch[stage].use_collision_check:
+            if side is not None:
+                cur_stream.wait_event(ev_join)
+                hits = hits_buf
+            else:
+                hits = self.scene.collide(traj.reshape(-1, 7), out=hits_buf)
         if singular is not None:
             from .pirl_env import manipulability
             yosh = manipulability(traj[:, 1:].reshape(-1, 7)).reshape(N, self.T - 1)
@@ -424,8 +444,6 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
             ph = float(it % period) / period
             lr_iter.fill_(lr_min + 0.5 * (lr_max - lr_min) * (1.0 + np.cos(ph * np.pi)))
 
-    if use_cuda_graph is None:
-        use_cuda_graph = False  # ~10 launches per iteration: eager launching keeps up with the GPU (measured)
     graph = None
     start = 0
     if use_cuda_graph and maxiter >= 2:
@@ -436,13 +454,13 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
         start = 1
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
+        cap_stream = torch.cuda.Stream(device=dev)
+        cap_stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(cap_stream):
             set_iter(1)
-            with torch.cuda.graph(graph, stream=side):
+            with torch.cuda.graph(graph, stream=cap_stream):
                 iteration()
-        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.current_stream(dev).wait_stream(cap_stream)
         start = 2  # the capture pass does not execute; replay it once for iteration 1
         graph.replay()
     for it in range(start, maxiter):
