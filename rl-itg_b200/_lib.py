@@ -16,6 +16,14 @@ class RlitgError(RuntimeError):
 
 
 if not os.path.exists(LIB_PATH):
+    # not a fallback: the same `make` __graft_entry__.build() runs, for a checkout that arrives without the built library
+    import shutil
+    import subprocess
+    if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+        subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-j8"], stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL, check=False)
+
+if not os.path.exists(LIB_PATH):
     raise ImportError(
         "librlitg.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` or "
         "`make -C rl-itg_b200/csrc`. There is no CPU fallback." % LIB_PATH)
