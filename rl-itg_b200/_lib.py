@@ -20,8 +20,12 @@ if not os.path.exists(LIB_PATH):
     import shutil
     import subprocess
     if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
-        subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-j8"], stdout=subprocess.DEVNULL,
-                       stderr=subprocess.DEVNULL, check=False)
+        import fcntl
+        with open(os.path.join(_HERE, "csrc", ".build.lock"), "w") as _lock:  # one builder when N ranks start together
+            fcntl.flock(_lock, fcntl.LOCK_EX)
+            if not os.path.exists(LIB_PATH):
+                subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-j8"], stdout=subprocess.DEVNULL,
+                               stderr=subprocess.DEVNULL, check=False)
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
