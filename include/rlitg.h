@@ -130,6 +130,17 @@ RLITG_API int rlitg_scene_get_dilated(const RlitgScene* scene, int32_t* ncls_out
 RLITG_API int rlitg_sphere_grid_collide(const void* q, int64_t B, int dtype, const RlitgScene* scene,
                                         const double* base_off, uint8_t* out, void* stream);
 
+/* TormOptimizer::isCurrentTrajectoryCollisionFree for N trajectories (torm/src/torm_optimizer.cpp:695-717) and the
+ * waypoint choice of use_stochastic_descent_ (:1502-1515) in one launch.  traj [N,T,7]; outputs (each nullable):
+ *   first_hit [N] int32: first colliding row (the reference's collision_point_, row 0 = start) or -1;
+ *   any_hit [N] uint8: 1 = the trajectory collides (feed rlitg_torm_bookkeep with hits_per_trajectory = 1);
+ *   stochastic_idx [N] int32: the free-waypoint index for rlitg_torm_cost_grad -- first_hit - 1 when the trajectory
+ *   collides (-1 when the start row collides: the reference then indexes row -1, here no increment is taken), else
+ *   (int)(u[n] * (T - 2)) for uniform u [N] float32 in [0,1) (NULL: index 0) -- the reference draws random() there. */
+RLITG_API int rlitg_torm_collision_point(const void* traj, int64_t N, int T, int dtype, const RlitgScene* scene,
+                                         const double* base_off, const float* u, int32_t* first_hit, uint8_t* any_hit,
+                                         int32_t* stochastic_idx, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Null-space imitation objective and pseudo-inverse velocity step
  * ------------------------------------------------------------------------------------------------------- */
@@ -223,6 +234,9 @@ typedef struct RlitgTormParams {
 #define RLITG_STAGE_COLL 8       /* performForwardKinematics (:1302-1382) + calculateCollisionIncrements (:1484-1553)
                                     + getCollisionCost (:1448-1463) */
 #define RLITG_STAGE_EVAL 16      /* traj_evaluator::getCost (torm/src/utils/traj_evaluator.cpp:104-132) */
+#define RLITG_STAGE_KEEP_COSTS 32 /* leave the cost entries of the stages that are off untouched instead of zeroing them:
+                                    lets two calls with disjoint stages share one costs buffer (the optimiser loop runs the
+                                    end-pose / evaluator call next to the collision-point test + collision call) */
 #define RLITG_TORM_NCOST 10
 /* costs [N,10]: 0 eval position, 1 eval rotation, 2 velocity, 3 acceleration, 4 jerk (traj_evaluator means),
  *   5 collision cost (mean over the T rows of the summed sphere potentials), 6 weighted = [0] + 0.17 [1]
@@ -263,6 +277,19 @@ RLITG_API int rlitg_torm_cost_grad_staged(const void* traj, const void* targets,
                                           int stage_mask, const int32_t* traj_stage, const int32_t* stochastic_idx,
                                           void* inc_smooth, void* inc_coll, void* inc_pose, void* costs, float* active,
                                           void* stream);
+
+/* The target path as frames, computed once per path and shared by every later call on it: frames [2T-1,12] =
+ * (p, R columns) of the T target poses (KDL Rotation::Quaternion, no normalisation) followed by the T-1 inter-target
+ * poses of traj_evaluator::setInterTargetPoses (torm/src/utils/traj_evaluator.cpp:244-257).  The reference rebuilds
+ * both for every evaluator it constructs (twice per GD iteration, torm/src/torm_optimizer.cpp:421,432). */
+RLITG_API int rlitg_torm_target_frames(const void* targets, int T, int dtype, void* frames, void* stream);
+/* rlitg_torm_cost_grad_staged reading the path from `target_frames` (from rlitg_torm_target_frames; `targets` may then
+ * be NULL).  target_frames = NULL is the plain call. */
+RLITG_API int rlitg_torm_cost_grad_frames(const void* traj, const void* targets, const void* target_frames, int64_t N,
+                                          int dtype, const RlitgScene* scene, const RlitgSmooth* smooth,
+                                          const RlitgTormParams* p, int stage_mask, const int32_t* traj_stage,
+                                          const int32_t* stochastic_idx, void* inc_smooth, void* inc_coll, void* inc_pose,
+                                          void* costs, float* active, void* stream);
 
 /* Host-buffer form of rlitg_torm_cost_grad: traj, targets, stochastic_idx and every output are HOST pointers (the
  * reference's TormOptimizer holds Eigen matrices on the host); copies in / out through an internal device workspace
@@ -316,6 +343,8 @@ typedef struct RlitgTormSchedule {
     int32_t use_collision_check, use_velocity_check;
     double learning_rate;       /* parameters_->learning_rate_ */
     double learning_rate_min, learning_rate_max; /* / 100 and * 1000 (:99-101) */
+    int32_t hits_per_trajectory; /* 0: hits is [N*T] per-waypoint flags; 1: hits is [N] (any_hit of rlitg_torm_collision_point) */
+    int32_t reserved_;
 } RlitgTormSchedule;
 /* The stage choice alone (:400-412), to be made BEFORE the cost evaluation of the half-iteration sch->stage so that
  * rlitg_torm_cost_grad_staged can skip the work the other stage would need; pass stage_idx = NULL to
@@ -341,6 +370,9 @@ RLITG_API int rlitg_greedy_select(const void* costs, int C, int Tseg, int dtype,
  * (2 * ctas * 256 * iters * 16 flops); bench.py times it with CUDA events to get the FP32 FMA-pipe peak that
  * the TORM kernel's roofline fraction is quoted against. */
 RLITG_API int rlitg_fma_probe(int ctas, int iters, float* out, void* stream);
+/* Same for the FP64 FMA pipe (8 independent DFMA chains per thread: 2 * ctas * 256 * iters * 8 flops): the FP32 build of
+ * the TORM collision kernel walks the chain in FP64, which is only affordable where this pipe is not vestigial. */
+RLITG_API int rlitg_dfma_probe(int ctas, int iters, double* out, void* stream);
 
 /* Measurement aid: streams `ntiles` tiles of `tile_bytes` from shared memory to `dst` with TMA bulk stores from
  * `ctas` persistent CTAs (the drain path of rlitg_fk_jac without arithmetic), optionally reading `read_floats`

@@ -221,6 +221,31 @@ extern "C" RLITG_API int rlitg_fma_probe(int ctas, int iters, float* out, void* 
     return rlitg::check_launch("fma_probe_kernel");
 }
 
+// ---- FP64 FMA-pipe probe (same shape as the FP32 one): decides whether an FP64 chain walk inside an FP32 kernel is
+// affordable on this part (kernel 3b, torm_coll.cuh)
+namespace rlitg {
+__global__ void __launch_bounds__(256) dfma_probe_kernel(int iters, double* out) {
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = 1.0 + 1e-3 * (threadIdx.x + k);
+    const double b = 0.999, c = 1e-4;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] = fma(a[k], b, c);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += a[k];
+    if (s == 123.456) *out = s;
+}
+}  // namespace rlitg
+
+extern "C" RLITG_API int rlitg_dfma_probe(int ctas, int iters, double* out, void* stream) {
+    if (ctas < 1 || iters < 1 || !out) return rlitg::set_error(RLITG_ERR_ARG, "bad dfma probe arguments");
+    rlitg::dfma_probe_kernel<<<ctas, 256, 0, static_cast<cudaStream_t>(stream)>>>(iters, out);
+    return rlitg::check_launch("dfma_probe_kernel");
+}
+
 // ---- HBM write-stream probe: the ceiling for a kernel that, like fk_jac, writes ~8x what it reads -----------
 // Persistent CTAs drain `tile_bytes` shared-memory tiles to consecutive global addresses with TMA bulk stores
 // (the fk_jac drain path, no arithmetic) and optionally read `read_bytes_per_tile` first.

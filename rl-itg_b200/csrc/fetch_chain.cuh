@@ -64,24 +64,27 @@ RLITG_DEV V3<T> axis_of(const FrameC<T>& f) {
     return AXIS == AX_Z ? f.c2 : (AXIS == AX_Y ? f.c1 : f.c0);
 }
 
-template <typename T, int J, int D, typename Visit>
-RLITG_DEV void arm_step(FrameC<T>& f, const T* q, Visit& visit) {
+template <typename T, int J, int D, bool kFastTrig64, typename QT, typename Visit>
+RLITG_DEV void arm_step(FrameC<T>& f, const QT* q, Visit& visit) {
     constexpr int A = D - 7;  // index offset of arm joint 0 in q
     constexpr T ox = arm_ox<T>(J), oz = arm_oz<T>(J);
     // translate by the joint origin (y component is zero for every arm joint)
     f.p = axpy(f.p, ox, f.c0);
     if (oz != T(0)) f.p = axpy(f.p, oz, f.c2);
     T s, c;
-    sincos_joint(q[A + J], s, c);
+    if constexpr (kFastTrig64 && sizeof(T) == 8) sincos_joint(T(q[A + J]), s, c, FastTrig64{});
+    else sincos_joint(T(q[A + J]), s, c);
     rotate_axis<arm_axis(J)>(f, s, c);
     visit(jidx<A + J>{}, f);
-    if constexpr (J < 6) arm_step<T, J + 1, D>(f, q, visit);
+    if constexpr (J < 6) arm_step<T, J + 1, D, kFastTrig64>(f, q, visit);
 }
 
 // Walks the chain.  visit(jidx<k>, frame) is called with the frame of the child link of joint k
 // (k = 0..D-1, i.e. KDL segment k's tip frame) and finally with k = D for gripper_link.
-template <typename T, int D, typename Visit>
-RLITG_DEV void walk_chain(const T* q, Visit& visit) {
+// kFastTrig64: a double walk inside an FP32 production kernel uses the lean FP64 sincos (rlitg_common.cuh).
+// The joint values may be stored in another precision than the walk (QT: e.g. FP32 rows in shared memory, FP64 walk).
+template <typename T, int D, bool kFastTrig64 = false, typename QT, typename Visit>
+RLITG_DEV void walk_chain(const QT* q, Visit& visit) {
     static_assert(D == 7 || D == 8, "Fetch chain has 7 (arm) or 8 (torso + arm) joints");
     FrameC<T> f;
     f.c0 = {T(1), T(0), T(0)};
@@ -89,10 +92,10 @@ RLITG_DEV void walk_chain(const T* q, Visit& visit) {
     f.c2 = {T(0), T(0), T(1)};
     f.p = {T(0), T(0), T(0)};
     if constexpr (D == 8) {
-        f.p = {torso_ox<T>(), T(0), torso_oz<T>() + q[0]};
+        f.p = {torso_ox<T>(), T(0), torso_oz<T>() + T(q[0])};
         visit(jidx<0>{}, f);
     }
-    arm_step<T, 0, D>(f, q, visit);
+    arm_step<T, 0, D, kFastTrig64>(f, q, visit);
     f.p = axpy(f.p, tip_ox<T>(), f.c0);
     visit(jidx<D>{}, f);
 }

@@ -219,6 +219,43 @@ RLITG_DEV void pinv_apply(const T (&J)[6 * D], const T (&v6)[6], double eps, T (
     }
 }
 
+// Streaming form of the same QR solve for register-starved callers (kernel 3a): modified Gram-Schmidt over the rows of
+// J (in Q, destroyed) with the forward substitution R^T y = v and the accumulation dq = sum_k y_k q_k folded into the
+// sweep, so neither R nor the finished rows stay live (peak: the 6 x D rows + 13 scalars instead of 2 x 6 x D + 36).
+// Returns min_k R_kk / max_k R_kk; the caller takes the truncated-SVD path when it is below 1e-4 (dq is then discarded).
+template <typename T, int D>
+RLITG_DEV T pinv_qr_stream(T (&Q)[6 * D], T (&v)[6], T (&dq)[D]) {
+    T rmin = T(1e30), rmax = T(0);
+#pragma unroll
+    for (int i = 0; i < D; i++) dq[i] = T(0);
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        T n2 = T(0);
+#pragma unroll
+        for (int i = 0; i < D; i++) n2 += Q[k * D + i] * Q[k * D + i];
+        const T r = sqrt_t(n2);
+        rmin = r < rmin ? r : rmin;
+        rmax = r > rmax ? r : rmax;
+        const T inv = T(1) / (r > T(1e-30) ? r : T(1e-30));
+        const T y = v[k] * inv;
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+            Q[k * D + i] *= inv;
+            dq[i] += y * Q[k * D + i];
+        }
+#pragma unroll
+        for (int j = k + 1; j < 6; j++) {
+            T d = T(0);
+#pragma unroll
+            for (int i = 0; i < D; i++) d += Q[k * D + i] * Q[j * D + i];
+#pragma unroll
+            for (int i = 0; i < D; i++) Q[j * D + i] -= d * Q[k * D + i];
+            v[j] -= d * y;
+        }
+    }
+    return rmin / (rmax > T(1e-30) ? rmax : T(1e-30));
+}
+
 // || (I - J^T (J J^T)^-1 J) e ||   (jaco_srv, pirl/src/kinematic_solver.cpp:332-351)
 template <typename T, int D>
 RLITG_DEV T nullspace_norm(const T (&J)[6 * D], const T (&e)[D]) {

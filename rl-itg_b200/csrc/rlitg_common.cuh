@@ -37,6 +37,8 @@ RLITG_DEV float acos_t(float x) { return acosf(x); }
 RLITG_DEV double acos_t(double x) { return acos(x); }
 RLITG_DEV float exp_t(float x) { return __expf(x); }
 RLITG_DEV double exp_t(double x) { return exp(x); }
+RLITG_DEV float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+RLITG_DEV double fma_t(double a, double b, double c) { return fma(a, b, c); }
 RLITG_DEV float floor_t(float x) { return floorf(x); }
 RLITG_DEV double floor_t(double x) { return floor(x); }
 
@@ -63,6 +65,36 @@ RLITG_DEV void sincos_joint(float x, float& s, float& c) {
     c = ((q + 1) & 2) ? -cc : cc;
 }
 RLITG_DEV void sincos_joint(double x, double& s, double& c) { sincos(x, &s, &c); }
+
+// Lean FP64 sin / cos for the FP32 production kernels that walk the chain in double (TORM collision kernel: sphere
+// centres accurate to ~1e-11 m so that the 1 / dt^2-scaled stencils keep their digits).  Two-constant Cody-Waite
+// reduction by pi/2 and the fdlibm kernel polynomials on [-pi/4, pi/4] (|error| < 1e-15 for |x| < 1e4): ~20 FP64
+// instructions, no large-argument path, no stack frame -- unlike libdevice's sincos, which the FP64 verification
+// build keeps using.
+struct FastTrig64 {};
+RLITG_DEV void sincos_joint(double x, double& s, double& c, FastTrig64) {
+    const double k = rint(x * 0.63661977236758138);
+    double r = fma(k, -1.5707963267948966, x);
+    r = fma(k, -6.123233995736766e-17, r);
+    const double z = r * r;
+    double sp = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    sp = fma(sp, z, 2.75573137070700676789e-06);
+    sp = fma(sp, z, -1.98412698298579493134e-04);
+    sp = fma(sp, z, 8.33333333332248946124e-03);
+    sp = fma(sp, z, -1.66666666666666324348e-01);
+    sp = fma(sp * z, r, r);
+    double cp = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    cp = fma(cp, z, -2.75573143513906633035e-07);
+    cp = fma(cp, z, 2.48015872894767294178e-05);
+    cp = fma(cp, z, -1.38888888888741095749e-03);
+    cp = fma(cp, z, 4.16666666666666019037e-02);
+    cp = fma(cp * z, z, fma(z, -0.5, 1.0));
+    const int q = (int)k;
+    const double ss = (q & 1) ? cp : sp;
+    const double cc = (q & 1) ? sp : cp;
+    s = (q & 2) ? -ss : ss;
+    c = ((q + 1) & 2) ? -cc : cc;
+}
 
 // KDL Rotation::GetQuaternion (trace-branch, sign not canonicalised).  R given by columns c0 c1 c2.
 template <typename T>

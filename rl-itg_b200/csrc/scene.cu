@@ -304,6 +304,58 @@ __global__ void __launch_bounds__(256) sphere_collide_smem_kernel(const T* __res
     }
 }
 
+// isCurrentTrajectoryCollisionFree for N trajectories (torm/src/torm_optimizer.cpp:695-717): the rows of a trajectory
+// are tested from free_vars_start_ - 1 (= row 0 here) upwards and the FIRST colliding row is collision_point_ (-1 when
+// the trajectory is free).  With use_stochastic_descent_ the collision increment of the same half-iteration takes ONE
+// waypoint (:1502-1515): collision_point_ when there is one, else (int)(u (free_end - free_start) + free_start) for a
+// uniform u -- as a free-row index that is first_hit - 1, or (int)(u (F - 1)).  first_hit = 0 (the start row collides)
+// gives index -1, which the reference writes out of bounds; the cost kernel takes no
+// increment for it.  One CTA per trajectory, rows strided over the threads, block-wide minimum.
+template <typename T>
+__global__ void __launch_bounds__(128) collision_point_kernel(const T* __restrict__ traj, int Tn, SceneDev sc, T ox, T oy, T oz,
+                                                             const float* __restrict__ u, int32_t* __restrict__ first_hit,
+                                                             uint8_t* __restrict__ any_hit, int32_t* __restrict__ stoch_idx) {
+    __shared__ float4 s_sph[kMaxSpheres];
+    __shared__ int s_start[kNumLinks + 1];
+    __shared__ int s_first;
+    for (int i = threadIdx.x; i < sc.S; i += blockDim.x) s_sph[i] = sc.spheres[i];
+    if (threadIdx.x <= kNumLinks) s_start[threadIdx.x] = sc.link_start[threadIdx.x];
+    if (threadIdx.x == 0) s_first = 0x7fffffff;
+    __syncthreads();
+    const int64_t n = blockIdx.x;
+    const T* tr = traj + n * (int64_t)Tn * 7;
+    const GridMap<T> gm(sc);
+    int mine = 0x7fffffff;
+    for (int i = threadIdx.x; i < Tn; i += blockDim.x) {
+        if (i > mine) break;
+        T qv[7];
+#pragma unroll
+        for (int j = 0; j < 7; j++) qv[j] = tr[(size_t)i * 7 + j];
+        CollideVisit<T> v{sc, gm, s_sph, s_start, {ox, oy, oz}};
+        walk_chain<T, 7>(qv, v);
+        if (v.hit) mine = min(mine, i);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, o));
+    if ((threadIdx.x & 31) == 0 && mine != 0x7fffffff) atomicMin(&s_first, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int f = s_first == 0x7fffffff ? -1 : s_first;
+        if (first_hit) first_hit[n] = f;
+        if (any_hit) any_hit[n] = f >= 0;
+        if (stoch_idx) {
+            const int F = Tn - 1;
+            int idx;
+            if (f >= 0) idx = f - 1;
+            else {
+                idx = u ? (int)(u[n] * (float)(F - 1)) : 0;
+                idx = idx < 0 ? 0 : (idx > F - 1 ? F - 1 : idx);
+            }
+            stoch_idx[n] = idx;
+        }
+    }
+}
+
 template <typename T>
 int launch_sphere_collide(const T* q, int64_t B, const Scene* s, const double* base_off, uint8_t* out,
                           cudaStream_t st) {
@@ -476,6 +528,26 @@ RLITG_API int rlitg_scene_get_dilated(const RlitgScene* h, int32_t* ncls_out, fl
     if (bits_out)
         CUDA_TRY(cudaMemcpy(bits_out, s->dil, sizeof(uint32_t) * (size_t)s->wx * s->ny * s->nz * s->ncls, cudaMemcpyDeviceToHost), "D2H dilated bits");
     return RLITG_OK;
+}
+
+RLITG_API int rlitg_torm_collision_point(const void* traj, int64_t N, int T, int dtype, const RlitgScene* h,
+                                         const double* base_off, const float* u, int32_t* first_hit, uint8_t* any_hit,
+                                         int32_t* stochastic_idx, void* stream) {
+    const Scene* s = reinterpret_cast<const Scene*>(h);
+    if (N < 0 || N > 0x7fffffff || T < 2) return set_error(RLITG_ERR_SHAPE, "N / T out of range");
+    if (N == 0) return RLITG_OK;
+    if (!traj || !base_off) return set_error(RLITG_ERR_NULL, "traj / base_off is NULL");
+    if (!scene_ready(s, true, true)) return set_error(RLITG_ERR_ARG, "scene needs a grid and a sphere table");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == RLITG_F32)
+        collision_point_kernel<float><<<(unsigned)N, 128, 0, st>>>((const float*)traj, T, s->dev(), (float)base_off[0],
+                                                                   (float)base_off[1], (float)base_off[2], u, first_hit,
+                                                                   any_hit, stochastic_idx);
+    else if (dtype == RLITG_F64)
+        collision_point_kernel<double><<<(unsigned)N, 128, 0, st>>>((const double*)traj, T, s->dev(), base_off[0], base_off[1],
+                                                                    base_off[2], u, first_hit, any_hit, stochastic_idx);
+    else return set_error(RLITG_ERR_DTYPE, "dtype must be RLITG_F32 or RLITG_F64");
+    return check_launch("collision_point_kernel");
 }
 
 RLITG_API int rlitg_sphere_grid_collide(const void* q, int64_t B, int dtype, const RlitgScene* h,

@@ -51,6 +51,9 @@ struct TormP {
     int cj[7];
     T vlim[7];
     T rule_v[7], rule_a[7], rule_j[7];  // DIFF_RULES / dt^(k+1) for the evaluator's finite differences
+    T rv[7], ra[7];                     // the same velocity / acceleration rules for the sphere stencils (kernel 3b)
+    T sqrt_ridge, ridge_t;
+    double off64[3];
 };
 
 RLITG_DEV float fmod_t(float a, float b) { return fmodf(a, b); }
@@ -88,37 +91,17 @@ template <typename T> RLITG_DEV T get_potential(T field_distance, T radius, T cl
     return -d + T(0.5) * clearance;
 }
 
+// rare path of kernel 3a's FP32 pseudo-inverse step (a singular value near KDL's truncation threshold): everything is
+// rebuilt from the joint row so that the common path keeps neither the Jacobian nor the chain walk live across its QR
 template <typename T>
-struct TormVisit {
-    FkJac<T, 7> fj;
-    T* sph_row;  // shared-memory row [S][3] of this waypoint's sphere centres (planning frame); nullptr = skip
-    const float4* sph;
-    const int* link_start;
-    V3<T> off;
-    template <int K>
-    RLITG_DEV void operator()(jidx<K> k, const FrameC<T>& f) {
-        fj(k, f);
-        if (sph_row != nullptr) {
-            for (int s = link_start[K]; s < link_start[K + 1]; s++) {
-                const float4 c = sph[s];
-                sph_row[3 * s + 0] = off.x + f.p.x + f.c0.x * T(c.x) + f.c1.x * T(c.y) + f.c2.x * T(c.z);
-                sph_row[3 * s + 1] = off.y + f.p.y + f.c0.y * T(c.x) + f.c1.y * T(c.y) + f.c2.y * T(c.z);
-                sph_row[3 * s + 2] = off.z + f.p.z + f.c0.z * T(c.x) + f.c1.z * T(c.y) + f.c2.z * T(c.z);
-            }
-        }
-    }
-};
-
-// sphere centres of one halo row (chunked paths only): kept out of line so the chain walk is not inlined twice
-template <typename T>
-__device__ __noinline__ void halo_sphere_row(const T* qrow, T* sph_row, const float4* sph, const int* link_start, V3<T> off) {
-    TormVisit<T> hv;
-    hv.sph = sph; hv.link_start = link_start; hv.off = off;
-    hv.sph_row = sph_row;
-    T hq[7];
+__device__ __noinline__ void pinv_svd_from_row(const T* qrow, const T* tw, double eps, T* dq) {
+    T q[7], J[42];
 #pragma unroll
-    for (int j = 0; j < 7; j++) hq[j] = qrow[j];
-    walk_chain<T, 7>(hq, hv);
+    for (int j = 0; j < 7; j++) q[j] = qrow[j];
+    FkJac<T, 7> fj;
+    walk_chain<T, 7>(q, fj);
+    fill_jac<T, 7>(fj, J);
+    pinv_svd_apply<T, 7>(J, tw, eps, dq);
 }
 
 template <typename T>
@@ -180,14 +163,34 @@ RLITG_DEV void inter_target(const T* __restrict__ a7, const T* __restrict__ b7, 
     c2 = {a0.x * h02 + a1.x * h12 + a2.x * h22, a0.y * h02 + a1.y * h12 + a2.y * h22, a0.z * h02 + a1.z * h12 + a2.z * h22};
 }
 
-template <typename U>
-RLITG_DEV void mat3_inverse(const U (&m)[9], U (&inv)[9]) {
-    const U det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) +
-                  m[2] * (m[3] * m[7] - m[4] * m[6]);
-    const U id = U(1) / det;
-    inv[0] = (m[4] * m[8] - m[5] * m[7]) * id; inv[1] = (m[2] * m[7] - m[1] * m[8]) * id; inv[2] = (m[1] * m[5] - m[2] * m[4]) * id;
-    inv[3] = (m[5] * m[6] - m[3] * m[8]) * id; inv[4] = (m[0] * m[8] - m[2] * m[6]) * id; inv[5] = (m[2] * m[3] - m[0] * m[5]) * id;
-    inv[6] = (m[3] * m[7] - m[4] * m[6]) * id; inv[7] = (m[1] * m[6] - m[0] * m[7]) * id; inv[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+// Target frames precomputed once per path (rlitg_torm_target_frames): frames [2 Tn - 1][12] = (p, c0, c1, c2); rows
+// 0 .. Tn-1 the target poses, rows Tn .. 2 Tn - 2 the evaluator's inter-target poses i + 1/2.  They depend on the path
+// only, so the N trajectories of a batch share them instead of every waypoint thread rebuilding two quaternion
+// frames, an axis-angle and a Rot2 per call (~300 instructions per waypoint).
+template <typename T, bool kFrames>
+RLITG_DEV void waypoint_target(const T* __restrict__ tg, int i, V3<T>& p, V3<T>& c0, V3<T>& c1, V3<T>& c2) {
+    if constexpr (kFrames) {
+        const T* f = tg + (size_t)i * 12;
+        p = {f[0], f[1], f[2]}; c0 = {f[3], f[4], f[5]}; c1 = {f[6], f[7], f[8]}; c2 = {f[9], f[10], f[11]};
+    } else {
+        target_frame(tg + (size_t)i * 7, p, c0, c1, c2);
+    }
+}
+template <typename T, bool kFrames>
+RLITG_DEV void midpoint_target(const T* __restrict__ tg, int Tn, int i, V3<T>& p, V3<T>& c0, V3<T>& c1, V3<T>& c2) {
+    if constexpr (kFrames) waypoint_target<T, true>(tg, Tn + i, p, c0, c1, c2);
+    else inter_target(tg + (size_t)i * 7, tg + (size_t)(i + 1) * 7, p, c0, c1, c2);
+}
+template <typename T>
+__global__ void torm_target_frames_kernel(const T* __restrict__ targets, int Tn, T* __restrict__ frames) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * Tn - 1) return;
+    V3<T> p, c0, c1, c2;
+    if (i < Tn) target_frame(targets + (size_t)i * 7, p, c0, c1, c2);
+    else inter_target(targets + (size_t)(i - Tn) * 7, targets + (size_t)(i - Tn + 1) * 7, p, c0, c1, c2);
+    T* f = frames + (size_t)i * 12;
+    f[0] = p.x; f[1] = p.y; f[2] = p.z; f[3] = c0.x; f[4] = c0.y; f[5] = c0.z;
+    f[6] = c1.x; f[7] = c1.y; f[8] = c1.z; f[9] = c2.x; f[10] = c2.y; f[11] = c2.z;
 }
 
 // block-wide sum of NR per-thread scalars -> tot[] valid on thread 0 (warp shuffles, then one smem round)
@@ -218,12 +221,11 @@ RLITG_DEV void block_reduce(T (&red)[NR], T* s_red, T (&tot)[NR]) {
 }
 
 #define TROW(row) (s_traj + (min(max((row), 0), Tn - 1) - c0 + 6) * 7)
-#define PROW(row) (s_pos + (size_t)(min(max((row), 0), Tn - 1) - c0 + 3) * PS)
 
 // ---- kernel 3a: end-pose error / pinv step (A5) + trajectory evaluator (A8) -------------------------------
 // Writes costs[0..4], [6..9]; costs[5] (collision) is zeroed when the collision kernel does not run.
 constexpr int kNRedPose = 11;
-template <typename T, int MAXREG>
+template <typename T, int MAXREG, bool kFrames>
 __global__ void __launch_bounds__(kTormMaxThreads) __maxnreg__(MAXREG)
 torm_pose_eval_kernel(TormP<T> P, const T* __restrict__ traj, const T* __restrict__ targets, int stage_mask,
                       int zero_coll_cost, T* __restrict__ inc_pose, T* __restrict__ costs,
@@ -264,7 +266,7 @@ torm_pose_eval_kernel(TormP<T> P, const T* __restrict__ traj, const T* __restric
             FkJac<T, 7> fj;
             walk_chain<T, 7>(q, fj);
             V3<T> tp, t0, t1, t2;
-            target_frame(targets + i * 7, tp, t0, t1, t2);
+            waypoint_target<T, kFrames>(targets, i, tp, t0, t1, t2);
             T angle;
             const V3<T> rv = rot_diff_kdl(fj.ee.c0, fj.ee.c1, fj.ee.c2, t0, t1, t2, angle);
             const V3<T> dp = tp - fj.ee.p;
@@ -274,7 +276,12 @@ torm_pose_eval_kernel(TormP<T> P, const T* __restrict__ traj, const T* __restric
                 T J[42], dq[7];
                 fill_jac<T, 7>(fj, J);
                 const T tw[6] = {dp.x, dp.y, dp.z, rv.x, rv.y, rv.z};
-                pinv_apply<T, 7, sizeof(T) == 8>(J, tw, P.vik_eps, dq);
+                if constexpr (sizeof(T) == 8) {
+                    pinv_apply<T, 7, true>(J, tw, P.vik_eps, dq);  // verification build: the literal truncated SVD
+                } else {
+                    T v[6] = {tw[0], tw[1], tw[2], tw[3], tw[4], tw[5]};
+                    if (pinv_qr_stream<T, 7>(J, v, dq) < T(1e-4)) pinv_svd_from_row<T>(TROW(i), tw, P.vik_eps, dq);
+                }
 #pragma unroll
                 for (int j = 0; j < 7; j++) o_pose[(i - 1) * 7 + j] = P.jac_w * dq[j];
             }
@@ -299,7 +306,7 @@ torm_pose_eval_kernel(TormP<T> P, const T* __restrict__ traj, const T* __restric
                     EeOnly<T> ev;
                     walk_chain<T, 7>(qm, ev);
                     V3<T> ip, i0, i1, i2;
-                    inter_target(targets + i * 7, targets + (i + 1) * 7, ip, i0, i1, i2);
+                    midpoint_target<T, kFrames>(targets, Tn, i, ip, i0, i1, i2);
                     T angle;
                     const V3<T> rv = rot_diff_kdl(ev.ee.c0, ev.ee.c1, ev.ee.c2, i0, i1, i2, angle);
                     const V3<T> dp = ip - ev.ee.p;
@@ -355,211 +362,13 @@ torm_pose_eval_kernel(TormP<T> P, const T* __restrict__ traj, const T* __restric
     }
 }
 
-// ---- kernel 3b: sphere potentials + CHOMP increments (A6) + smoothness increments (A7) ---------------------
-// Writes costs[5] and active[]; the other cost entries are zeroed when the pose / evaluator kernel does not run.
-template <typename T, int MAXREG>
-__global__ void __launch_bounds__(kTormMaxThreads) __maxnreg__(MAXREG)
-torm_coll_smooth_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S, const T* __restrict__ Aband,
-                        int stage_mask, int zero_pose_costs, const int32_t* __restrict__ stoch,
-                        T* __restrict__ inc_smooth, T* __restrict__ inc_coll, T* __restrict__ costs,
-                        float* __restrict__ active, const int32_t* __restrict__ traj_stage) {
-    const int CH = blockDim.x, tid = threadIdx.x, Tn = P.Tn;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* s_traj = reinterpret_cast<T*>(smem_raw);  // [(CH + 12)][7]
-    T* s_red = s_traj + (CH + 12) * 7;           // [8][2]
-    T* s_pos = s_red + 8 * 2;                    // [(min(CH, T) + 6)][PS] rows c0-3 .. c0+CH+2, PS = 3 S padded to odd
-    const int PS = (3 * S) | 1;                  // odd row stride: thread-per-row accesses are bank-conflict free
-    __shared__ float4 s_sph[kMaxSpheres];
-    __shared__ int s_start[kNumLinks + 1];
-    __shared__ int s_nanc[kMaxSpheres];  // joints that move sphere s: min(link + 1, 7) (torm_optimizer.cpp:263-309)
-
-    const bool do_coll = (stage_mask & RLITG_STAGE_COLL) != 0;
-    const bool do_smooth = (stage_mask & RLITG_STAGE_SMOOTH) != 0;
-    if (do_coll) {
-        for (int i = tid; i < S; i += CH) {
-            s_sph[i] = sc.spheres[i];
-            int link = 0;
-            while (link < kNumLinks - 1 && i >= sc.link_start[link + 1]) link++;
-            s_nanc[i] = link + 1 < 7 ? link + 1 : 7;
-        }
-        if (tid <= kNumLinks) s_start[tid] = sc.link_start[tid];
-    }
-    const int64_t n = blockIdx.x;
-    if (traj_stage && traj_stage[n] != 0) {  // this trajectory takes the end-pose stage: nothing to do here
-        if (tid == 0) {
-            T* c = costs + n * RLITG_TORM_NCOST;
-            c[5] = T(0);
-            if (zero_pose_costs) {
-                c[0] = c[1] = c[2] = c[3] = c[4] = T(0);
-                c[6] = c[7] = c[8] = c[9] = T(0);
-            }
-            if (active) active[n] = 0.f;
-        }
-        return;
-    }
-    const T* tr = traj + n * (int64_t)Tn * 7;
-    const int F = Tn - 1;
-    T* o_smooth = inc_smooth ? inc_smooth + n * (int64_t)F * 7 : nullptr;
-    T* o_coll = inc_coll ? inc_coll + n * (int64_t)F * 7 : nullptr;
-    const int stoch_row = stoch ? stoch[n] + 1 : -1;  // full-trajectory row of the single stochastic waypoint
-    const V3<T> off = {P.off[0], P.off[1], P.off[2]};
-    const GridMap<T> gm(sc);
-    T red[2] = {T(0), T(0)};  // potential sum, active sphere count
-
-    for (int c0 = 0; c0 < Tn; c0 += CH) {
-        __syncthreads();
-        for (int idx = tid; idx < (CH + 12) * 7; idx += CH) {
-            const int r = idx / 7, j = idx - r * 7;
-            s_traj[idx] = tr[min(max(c0 - 6 + r, 0), Tn - 1) * 7 + j];
-        }
-        __syncthreads();
-        const int i = c0 + tid;
-        const bool valid = i < Tn;
-
-        // ---- smoothness increments: -(2 A_full x) on the free rows (:1466-1473); group row g = i + 5
-        if (do_smooth && valid && i >= 1 && o_smooth) {
-            const T* ab = Aband + (size_t)(i + 5) * 13;
-            T coef[13];
-#pragma unroll
-            for (int k = 0; k < 13; k++) coef[k] = ab[k];
-#pragma unroll
-            for (int j = 0; j < 7; j++) {
-                T sacc = T(0);
-#pragma unroll
-                for (int k = 0; k < 13; k++) sacc += coef[k] * (T(2) * TROW(i + k - 6)[j]);
-                o_smooth[(i - 1) * 7 + j] = -sacc;
-            }
-        }
-        if (!do_coll) continue;
-
-        // ---- phase 1: FK of this row -> sphere centres (+ halo rows of a chunked path)
-        TormVisit<T> v;
-        v.sph = s_sph; v.link_start = s_start; v.off = off;
-        v.sph_row = nullptr;
-        if (valid) {
-            T q[7];
-#pragma unroll
-            for (int j = 0; j < 7; j++) q[j] = TROW(i)[j];
-            v.sph_row = PROW(i);
-            walk_chain<T, 7>(q, v);
-        }
-        if (tid < 6) {
-            const int hr = tid < 3 ? c0 - 3 + tid : c0 + CH + (tid - 3);
-            if (hr >= 0 && hr < Tn) halo_sphere_row<T>(TROW(hr), PROW(hr), s_sph, s_start, off);
-        }
-        __syncthreads();
-
-        // ---- phase 2: potentials, cost, CHOMP increments
-        if (valid) {
-            T acc[7];
-#pragma unroll
-            for (int j = 0; j < 7; j++) acc[j] = T(0);
-            const bool inc_row = (i >= 1) && (stoch_row < 0 || stoch_row == i) && (o_coll != nullptr);
-            const T* prow = PROW(i);
-            const T* nrow[7];  // the seven stencil rows (clamped), resolved once per waypoint
-#pragma unroll
-            for (int k = 0; k < 7; k++) nrow[k] = PROW(i + k - 3);
-            // joint origins / "axes" in the planning frame (computeJointProperties :1125-1162), once per waypoint
-            V3<T> jo[7], ja[7];
-#pragma unroll
-            for (int j = 0; j < 7; j++) {
-                jo[j] = v.fj.o[j] + off;
-                ja[j] = P.quirk ? v.fj.z[j] + jo[j] : v.fj.z[j];  // axis = joint_transform * axis (:1157)
-            }
-            T csum = T(0);
-            int nact = 0;
-            // distance-record gathers run two spheres ahead of the arithmetic (L2 latency off the critical path)
-            auto fetch = [&](int s) -> float4 {
-                const V3<T> x = {prow[3 * s], prow[3 * s + 1], prow[3 * s + 2]};
-                const int64_t c = gm.cell(x);
-                return c >= 0 ? __ldg(sc.field + c) : make_float4(1e30f, 0.f, 0.f, 0.f);
-            };
-            float4 r0 = fetch(0), r1 = S > 1 ? fetch(1) : make_float4(1e30f, 0.f, 0.f, 0.f);
-            for (int s = 0; s < S; s++) {
-                const float4 rec = r0;
-                r0 = r1;
-                if (s + 2 < S) r1 = fetch(s + 2);
-                if (!(rec.x < 1e29f)) continue;
-                const float4 sp = s_sph[s];
-                const T pot = get_potential(T(rec.x), T(sp.w), P.clearance);
-                csum += pot;
-                if (!inc_row || pot < T(0.0001)) continue;
-                nact++;
-                const int nanc = s_nanc[s];  // uniform over the warp: every lane is on sphere s
-                const V3<T> x = {prow[3 * s], prow[3 * s + 1], prow[3 * s + 2]};
-                V3<T> vel = {T(0), T(0), T(0)}, ac = {T(0), T(0), T(0)};
-#pragma unroll
-                for (int k = 0; k < 7; k++) {
-                    const T* pr = nrow[k] + 3 * s;
-                    const V3<T> xk = {pr[0], pr[1], pr[2]};
-                    if (k != 3) vel = axpy(vel, P.inv_dt * diff_rule<T>(0, k), xk);
-                    ac = axpy(ac, P.inv_dt2 * diff_rule<T>(1, k), xk);
-                }
-                T vel_mag, inv_vm;
-                if constexpr (sizeof(T) == 4) {
-                    inv_vm = rsqrtf(dot(vel, vel));
-                    vel_mag = dot(vel, vel) * inv_vm;
-                } else {
-                    vel_mag = sqrt_t(dot(vel, vel));
-                    inv_vm = T(1) / vel_mag;
-                }
-                const V3<T> nv = vel * inv_vm;
-                const V3<T> pg = {-T(rec.y), -T(rec.z), -T(rec.w)};
-                // orthogonal projector P = I - nv nv^T
-                const V3<T> Pa = axpy(ac, -dot(nv, ac), nv);
-                const V3<T> Pg = axpy(pg, -dot(nv, pg), nv);
-                const V3<T> curv = Pa * (inv_vm * inv_vm);
-                const V3<T> cg = (Pg - curv * pot) * vel_mag;
-                // 3 x nanc positional Jacobian (getJacobian :1164-1187); columns past nanc are zero and skipped
-                V3<T> col[7];
-                const T rdg = (T)P.ridge;
-                T M[9] = {rdg, T(0), T(0), T(0), rdg, T(0), T(0), T(0), rdg};
-#pragma unroll
-                for (int j = 0; j < 7; j++) {
-                    if (j < nanc) {
-                        col[j] = cross(ja[j], x - jo[j]);
-                        M[0] += col[j].x * col[j].x; M[1] += col[j].x * col[j].y; M[2] += col[j].x * col[j].z;
-                        M[4] += col[j].y * col[j].y; M[5] += col[j].y * col[j].z; M[8] += col[j].z * col[j].z;
-                    }
-                }
-                V3<T> y = cg;
-                if (P.use_pinv) {
-                    // calculatePseudoInverse :767-772 : J^T (J J^T + ridge I)^-1 ; the ridge bounds cond <= ~1e4
-                    T Mi[9];
-                    M[3] = M[1]; M[6] = M[2]; M[7] = M[5];
-                    mat3_inverse<T>(M, Mi);
-                    y = {Mi[0] * cg.x + Mi[1] * cg.y + Mi[2] * cg.z, Mi[3] * cg.x + Mi[4] * cg.y + Mi[5] * cg.z,
-                         Mi[6] * cg.x + Mi[7] * cg.y + Mi[8] * cg.z};
-                }
-#pragma unroll
-                for (int j = 0; j < 7; j++)
-                    if (j < nanc) acc[j] -= dot(col[j], y);
-            }
-            red[0] += csum;
-            red[1] += T(nact);
-            if (i >= 1 && o_coll) {
-#pragma unroll
-                for (int j = 0; j < 7; j++) o_coll[(i - 1) * 7 + j] = acc[j];
-            }
-        }
-    }
-    T tot[2];
-    block_reduce<T, 2>(red, s_red, tot);
-    if (tid == 0) {
-        T* c = costs + n * RLITG_TORM_NCOST;
-        c[5] = do_coll ? tot[0] / T(Tn) : T(0);
-        if (zero_pose_costs) {
-            c[0] = c[1] = c[2] = c[3] = c[4] = T(0);
-            c[6] = c[7] = c[8] = c[9] = T(0);
-        }
-        if (active) {
-            const int rows = (stoch_row >= 0) ? 1 : Tn - 1;
-            active[n] = do_coll ? (float)(tot[1] / T(rows)) : 0.f;
-        }
-    }
-}
 #undef TROW
-#undef PROW
+
+}  // namespace rlitg
+
+#include "torm_coll.cuh"
+
+namespace rlitg {
 
 // ---- smoothness operator (host, FP64): TormCost ctor + scaling -------------------------------------------
 // (struct Smooth is declared in rlitg_internal.h: the update step in torm_update.cu shares it)
@@ -672,14 +481,18 @@ static TormP<T> convert_params(const RlitgTormParams& p) {
         o.rule_v[k] = (T)(kRules[0][k] / std::pow(p.dt, 1));
         o.rule_a[k] = (T)(kRules[1][k] / std::pow(p.dt, 2));
         o.rule_j[k] = (T)(kRules[2][k] / std::pow(p.dt, 3));
+        o.rv[k] = (T)((1.0 / p.dt) * kRules[0][k]);
+        o.ra[k] = (T)((1.0 / p.dt) * (1.0 / p.dt) * kRules[1][k]);
     }
+    o.sqrt_ridge = (T)std::sqrt(p.pinv_ridge); o.ridge_t = (T)p.pinv_ridge;
+    for (int k = 0; k < 3; k++) o.off64[k] = p.base_off[k];
     return o;
 }
 
 template <typename T>
 static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* scene, const Smooth* smooth,
                        const RlitgTormParams* p, int stage_mask, const int32_t* stoch, T* inc_smooth, T* inc_coll,
-                       T* inc_pose, T* costs, float* active, const int32_t* traj_stage, cudaStream_t st) {
+                       T* inc_pose, T* costs, float* active, const int32_t* traj_stage, const T* frames, cudaStream_t st) {
     TormP<T> P = convert_params<T>(*p);
     const int CH = std::min(kTormMaxThreads, ((p->T + 31) / 32) * 32);
     const bool run_pose = (stage_mask & (RLITG_STAGE_POSE | RLITG_STAGE_POSE_GRAD | RLITG_STAGE_EVAL)) != 0;
@@ -717,35 +530,74 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
             sd = scene_dev(scene);
             S = sd.S;
         }
-        const size_t smem = sizeof(T) * ((size_t)(CH + 12) * 7 + 8 * 2 + (size_t)(std::min(CH, (int)p->T) + 6) * ((3 * S) | 1));
-        if (smem > 220 * 1024) return set_error(RLITG_ERR_SHAPE, "too many spheres for the shared-memory tile");
-        // register budget of the collision kernel: 2 CTAs/SM (128 regs) or 3 (<= 96 regs); RLITG_TORM_COLL_OCC
-        static const int cocc = [] { const char* e = getenv("RLITG_TORM_COLL_OCC"); return e ? atoi(e) : 2; }();
-        auto kern = (sizeof(T) == 4 && cocc == 3) ? torm_coll_smooth_kernel<T, (sizeof(T) == 4 ? 96 : 255)>
-                                                  : torm_coll_smooth_kernel<T, (sizeof(T) == 4 ? 128 : 255)>;
+        // rows per chunk: what fits ~56 KB of shared memory per CTA (four CTAs per SM), at most 64; the chunks of a
+        // trajectory are spread over a cluster of CL CTAs (each CTA loops when the path has more than CL chunks)
+        using CFT = typename std::conditional<sizeof(T) == 4, double, T>::type;  // the FP32 build sizes for the FP64 walk
+        int cap = kCollMaxRows;
+        while (cap > 8 && coll_layout<T, CFT>(cap, S).total > 56u * 1024u * (sizeof(T) / 4)) cap--;
+        static const int cap_env = [] { const char* e = getenv("RLITG_TORM_COLL_ROWS"); return e ? atoi(e) : 0; }();
+        if (cap_env >= 8 && cap_env < cap) cap = cap_env;
+        const int Tn = (int)p->T;
+        const int CL = std::min(kCollMaxCluster, (Tn + cap - 1) / cap);
+        const int nch = CL * ((Tn + cap * CL - 1) / (cap * CL));
+        const int R = (Tn + nch - 1) / nch;
+        const size_t smem = coll_layout<T, CFT>(R, S).total;
+        if (smem > 200 * 1024) return set_error(RLITG_ERR_SHAPE, "too many spheres for the shared-memory tile");
+        if (N * (int64_t)CL > 0x7fffffff) return set_error(RLITG_ERR_SHAPE, "N x chunks out of range");
+        // FP32 build: chain walk of phase 1 in FP64 (accuracy of the 1 / dt^2 stencils, torm_coll.cuh); RLITG_TORM_FK64=0
+        // keeps it in FP32 (measurement knob)
+        static const int fk64 = [] { const char* e = getenv("RLITG_TORM_FK64"); return e ? atoi(e) : 1; }();
+        using KernT = void (*)(TormP<T>, const T*, SceneDev, int, const T*, int, int, const int32_t*, T*, T*, T*, float*,
+                               const int32_t*, int, int);
+        KernT kern;
+        // register budget: 4 CTAs per SM (64 registers, 32 warps) by default, RLITG_TORM_COLL_OCC=3 -> 80 registers
+        static const int cocc = [] { const char* e = getenv("RLITG_TORM_COLL_OCC"); return e ? atoi(e) : 4; }();
+        if constexpr (sizeof(T) == 4) {
+            if (cocc == 3) kern = fk64 ? torm_coll_kernel<T, true, 3> : torm_coll_kernel<T, false, 3>;
+            else kern = fk64 ? torm_coll_kernel<T, true, 4> : torm_coll_kernel<T, false, 4>;
+        } else {
+            kern = torm_coll_kernel<T, false, 1>;
+        }
         {
-            int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "torm_coll_smooth_kernel");
+            int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "torm_coll_kernel");
             if (rc_attr) return rc_attr;
         }
         const T* band = nullptr;
         if (stage_mask & RLITG_STAGE_SMOOTH)
             band = reinterpret_cast<const T*>(sizeof(T) == 4 ? (const void*)smooth->d_band32 : (const void*)smooth->d_band64);
-        kern<<<(unsigned)N, CH, smem, st>>>(P, traj, sd, S, band, stage_mask, run_pose ? 0 : 1, stoch, inc_smooth, inc_coll,
-                                            costs, active, traj_stage);
-        int rc = check_launch("torm_coll_smooth_kernel");
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(N * CL));
+        cfg.blockDim = dim3(kCollThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const int zero_pose = (run_pose || (stage_mask & RLITG_STAGE_KEEP_COSTS)) ? 0 : 1;
+        if (cudaLaunchKernelEx(&cfg, kern, P, traj, sd, S, band, stage_mask, zero_pose, stoch, inc_smooth, inc_coll, costs,
+                               active, traj_stage, R, nch) != cudaSuccess)
+            return set_cuda_error("torm_coll_kernel launch");
+        int rc = check_launch("torm_coll_kernel");
         if (rc) return rc;
     }
     if (run_pose) {
         const size_t smem = sizeof(T) * ((size_t)(CH + 12) * 7 + (size_t)(CH + 3) * 7 + 8 * kNRedPose);
         // register budget of the pose kernel: 2 CTAs/SM (128 regs) or 3 (96 regs at 224 threads); RLITG_TORM_POSE_OCC
         static const int occ = [] { const char* e = getenv("RLITG_TORM_POSE_OCC"); return e ? atoi(e) : 2; }();
-        auto kern = (sizeof(T) == 4 && occ == 3) ? torm_pose_eval_kernel<T, (sizeof(T) == 4 ? 96 : 255)>
-                                                 : torm_pose_eval_kernel<T, (sizeof(T) == 4 ? 128 : 255)>;
+        using PoseK = void (*)(TormP<T>, const T*, const T*, int, int, T*, T*, const int32_t*);
+        constexpr int kR2 = sizeof(T) == 4 ? 128 : 255, kR3 = sizeof(T) == 4 ? 96 : 255;
+        PoseK kern;
+        if (frames) kern = (sizeof(T) == 4 && occ == 3) ? torm_pose_eval_kernel<T, kR3, true> : torm_pose_eval_kernel<T, kR2, true>;
+        else kern = (sizeof(T) == 4 && occ == 3) ? torm_pose_eval_kernel<T, kR3, false> : torm_pose_eval_kernel<T, kR2, false>;
         {
             int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "torm_pose_eval_kernel");
             if (rc_attr) return rc_attr;
         }
-        kern<<<(unsigned)N, CH, smem, st_pose>>>(P, traj, targets, stage_mask, run_coll ? 0 : 1, inc_pose, costs, traj_stage);
+        kern<<<(unsigned)N, CH, smem, st_pose>>>(P, traj, frames ? frames : targets, stage_mask,
+                                                 (run_coll || (stage_mask & RLITG_STAGE_KEEP_COSTS)) ? 0 : 1, inc_pose, costs,
+                                                 traj_stage);
         int rc = check_launch("torm_pose_eval_kernel");
         if (rc) return rc;
     }
@@ -826,13 +678,37 @@ RLITG_API int rlitg_torm_cost_grad_staged(const void* traj, const void* targets,
                                           int stage_mask, const int32_t* traj_stage, const int32_t* stochastic_idx,
                                           void* inc_smooth, void* inc_coll, void* inc_pose, void* costs, float* active,
                                           void* stream) {
+    return rlitg_torm_cost_grad_frames(traj, targets, nullptr, N, dtype, scene, smooth, p, stage_mask, traj_stage,
+                                       stochastic_idx, inc_smooth, inc_coll, inc_pose, costs, active, stream);
+}
+
+RLITG_API int rlitg_torm_target_frames(const void* targets, int T, int dtype, void* frames, void* stream) {
+    if (!targets || !frames) return set_error(RLITG_ERR_NULL, "targets / frames is NULL");
+    if (T < 2 || T > 8192) return set_error(RLITG_ERR_SHAPE, "T must be in 2..8192");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned grid = (unsigned)((2 * T - 1 + 127) / 128);
+    if (dtype == RLITG_F32) torm_target_frames_kernel<float><<<grid, 128, 0, st>>>((const float*)targets, T, (float*)frames);
+    else if (dtype == RLITG_F64) torm_target_frames_kernel<double><<<grid, 128, 0, st>>>((const double*)targets, T, (double*)frames);
+    else return set_error(RLITG_ERR_DTYPE, "dtype must be RLITG_F32 or RLITG_F64");
+    return check_launch("torm_target_frames_kernel");
+}
+
+RLITG_API int rlitg_torm_cost_grad_frames(const void* traj, const void* targets, const void* target_frames, int64_t N,
+                                          int dtype, const RlitgScene* scene, const RlitgSmooth* smooth,
+                                          const RlitgTormParams* p, int stage_mask, const int32_t* traj_stage,
+                                          const int32_t* stochastic_idx, void* inc_smooth, void* inc_coll, void* inc_pose,
+                                          void* costs, float* active, void* stream) {
     if (!p) return set_error(RLITG_ERR_NULL, "params is NULL");
     if (p->D != 7) return set_error(RLITG_ERR_SHAPE, "TORM runs the 7-joint arm chain (D = 7)");
-    if (p->T < 5 || p->T > 8192) return set_error(RLITG_ERR_SHAPE, "T must be in 5..8192");
+    // the evaluator's T - 2 / T - 3 divisors and the smoothness band need five rows; the end-pose and collision terms are
+    // per waypoint and also serve the initialisers' short segments (getNewTrajectory scores segments of 2..10 rows)
+    if (p->T < 2 || p->T > 8192) return set_error(RLITG_ERR_SHAPE, "T must be in 2..8192");
+    if (p->T < 5 && (stage_mask & (RLITG_STAGE_EVAL | RLITG_STAGE_SMOOTH)))
+        return set_error(RLITG_ERR_SHAPE, "the evaluator and smoothness stages need T >= 5");
     if (N < 0 || N > 0x7fffffff) return set_error(RLITG_ERR_SHAPE, "N out of range");
     if (dtype != RLITG_F32 && dtype != RLITG_F64) return set_error(RLITG_ERR_DTYPE, "dtype must be RLITG_F32 or RLITG_F64");
     if (N == 0) return RLITG_OK;
-    if (!traj || !targets || !costs) return set_error(RLITG_ERR_NULL, "traj / targets / costs is NULL");
+    if (!traj || (!targets && !target_frames) || !costs) return set_error(RLITG_ERR_NULL, "traj / targets / costs is NULL");
     const Scene* sc = reinterpret_cast<const Scene*>(scene);
     const Smooth* sm = reinterpret_cast<const Smooth*>(smooth);
     if ((stage_mask & RLITG_STAGE_COLL) && !scene_ready(sc, true, true))
@@ -845,9 +721,11 @@ RLITG_API int rlitg_torm_cost_grad_staged(const void* traj, const void* targets,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == RLITG_F32)
         return launch_torm<float>((const float*)traj, (const float*)targets, N, sc, sm, p, stage_mask, stochastic_idx,
-                                  (float*)inc_smooth, (float*)inc_coll, (float*)inc_pose, (float*)costs, active, traj_stage, st);
+                                  (float*)inc_smooth, (float*)inc_coll, (float*)inc_pose, (float*)costs, active, traj_stage,
+                                  (const float*)target_frames, st);
     return launch_torm<double>((const double*)traj, (const double*)targets, N, sc, sm, p, stage_mask, stochastic_idx,
-                               (double*)inc_smooth, (double*)inc_coll, (double*)inc_pose, (double*)costs, active, traj_stage, st);
+                               (double*)inc_smooth, (double*)inc_coll, (double*)inc_pose, (double*)costs, active, traj_stage,
+                               (const double*)target_frames, st);
 }
 
 }  // extern "C"

@@ -326,7 +326,7 @@ extern "C" RLITG_API int rlitg_torm_update_staged(void* traj, int64_t N, int dty
 // (:436-446), alpha_ (:447-469), learning_rate_ (:471-499) and the best-trajectory record (:506-560).
 namespace rlitg {
 struct BookP {
-    int T, mode, stage, use_col, use_vel;
+    int T, mode, stage, use_col, use_vel, hits_per_traj;
     double lr0, lr_min, lr_max;
 };
 
@@ -344,7 +344,11 @@ torm_bookkeep_kernel(BookP P, const T* __restrict__ traj, T* __restrict__ best_t
     __syncthreads();
     if (P.use_col && hits) {
         int h = 0;
-        for (int i = tid; i < P.T; i += blockDim.x) h |= hits[n * P.T + i];
+        if (P.hits_per_traj) {
+            if (tid == 0) h = hits[n];
+        } else {
+            for (int i = tid; i < P.T; i += blockDim.x) h |= hits[n * P.T + i];
+        }
         if (h) s_hit = 1;  // benign race: every writer stores 1
     }
     __syncthreads();
@@ -443,6 +447,7 @@ extern "C" RLITG_API int rlitg_torm_bookkeep(const void* traj, void* best_traj, 
     BookP P;
     P.T = T; P.mode = sch->lr_schedule_mode; P.stage = sch->stage;
     P.use_col = sch->use_collision_check; P.use_vel = sch->use_velocity_check;
+    P.hits_per_traj = sch->hits_per_trajectory;
     P.lr0 = sch->learning_rate; P.lr_min = sch->learning_rate_min; P.lr_max = sch->learning_rate_max;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == RLITG_F32)

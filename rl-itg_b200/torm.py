@@ -40,6 +40,9 @@ lib.rlitg_torm_cost_grad.argtypes = [_vp, _vp, C.c_int64, C.c_int, _vp, _vp, C.P
                                      _vp, _vp, _vp, _vp, _vp, _vp]
 lib.rlitg_torm_cost_grad_staged.argtypes = [_vp, _vp, C.c_int64, C.c_int, _vp, _vp, C.POINTER(RlitgTormParams), C.c_int,
                                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+lib.rlitg_torm_target_frames.argtypes = [_vp, C.c_int, C.c_int, _vp, _vp]
+lib.rlitg_torm_cost_grad_frames.argtypes = [_vp, _vp, _vp, C.c_int64, C.c_int, _vp, _vp, C.POINTER(RlitgTormParams), C.c_int,
+                                            _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
 
 
 @dataclass
@@ -128,8 +131,10 @@ class TormBatch:
     """N candidate trajectories against one target path: the cost / increment members of TormOptimizer."""
 
     def __init__(self, end_poses, parameters: TormParameters | None = None, scene=None, device="cuda:0",
-                 dtype=torch.float32):
-        """end_poses: [T,7] target path (x y z qx qy qz qw, chain-base frame) -- endPoses_desired_."""
+                 dtype=torch.float32, smoothness=None):
+        """end_poses: [T,7] target path (x y z qx qy qz qw, chain-base frame) -- endPoses_desired_.
+        smoothness: build the TormCost operator (default: when T >= 5; the initialisers' short segments are scored with
+        the end-pose and collision terms only and need none)."""
         self.device, self.dtype = torch.device(device), dtype
         self.parameters = parameters or TormParameters()
         self.scene = scene
@@ -137,12 +142,20 @@ class TormBatch:
         self.T = int(self.endPoses_desired_.shape[0])
         self.num_vars_free_ = self.T - 1
         pr = self.parameters
+        if smoothness is None:
+            smoothness = self.T >= 5
         self.joint_costs_ = TormCost(self.T, pr.time_duration_, (pr.smoothness_cost_velocity_,
                                      pr.smoothness_cost_acceleration_, pr.smoothness_cost_jerk_), pr.ridge_factor_,
-                                     self.device)
+                                     self.device) if smoothness else None
         self._cp = pr.to_c(self.T)
         self._buf = {}
         self._call_cache = {}
+        # the path as frames (targets + the evaluator's inter-target poses), built once and shared by every call
+        self._frames = torch.empty(2 * self.T - 1, 12, device=self.device, dtype=dtype)
+        with _lib.on_device(self.device):
+            check(lib.rlitg_torm_target_frames(self.endPoses_desired_.data_ptr(), self.T,
+                                               _lib.F32 if dtype == torch.float32 else _lib.F64, self._frames.data_ptr(),
+                                               torch.cuda.current_stream(self.device).cuda_stream))
 
     def _out(self, name, shape, dtype=None):
         t = self._buf.get(name)
@@ -181,15 +194,16 @@ class TormBatch:
             active = self._out("active", (N,), torch.float32) if want_active else None
             p = lambda t: None if t is None else t.data_ptr()
             code = _lib.F32 if traj.dtype == torch.float32 else _lib.F64
-            args = (traj.data_ptr(), self.endPoses_desired_.data_ptr(), N, code,
-                    None if self.scene is None else self.scene.handle, self.joint_costs_.handle, C.byref(self._cp),
+            args = (traj.data_ptr(), self.endPoses_desired_.data_ptr(), self._frames.data_ptr(), N, code,
+                    None if self.scene is None else self.scene.handle,
+                    None if self.joint_costs_ is None else self.joint_costs_.handle, C.byref(self._cp),
                     int(stage_mask), p(traj_stage), p(st), p(inc_s), p(inc_c), p(inc_p), costs.data_ptr(), p(active))
             hit = (args, dict(costs=costs, inc_smooth=inc_s, inc_coll=inc_c, inc_pose=inc_p, active=active))
             if len(self._call_cache) > 64:
                 self._call_cache.clear()
             self._call_cache[key] = hit
         with _lib.on_device(self.device):
-            rc = lib.rlitg_torm_cost_grad_staged(*hit[0], torch.cuda.current_stream().cuda_stream)
+            rc = lib.rlitg_torm_cost_grad_frames(*hit[0], torch.cuda.current_stream().cuda_stream)
         if rc:
             check(rc)
         return hit[1]
@@ -266,7 +280,7 @@ lib.rlitg_torm_update.argtypes = [_vp, C.c_int64, C.c_int, _vp, C.POINTER(RlitgT
 class RlitgTormSchedule(C.Structure):
     _fields_ = [("lr_schedule_mode", C.c_int32), ("stage", C.c_int32), ("use_collision_check", C.c_int32),
                 ("use_velocity_check", C.c_int32), ("learning_rate", C.c_double), ("learning_rate_min", C.c_double),
-                ("learning_rate_max", C.c_double)]
+                ("learning_rate_max", C.c_double), ("hits_per_trajectory", C.c_int32), ("reserved_", C.c_int32)]
 
 
 lib.rlitg_torm_stage_decide.argtypes = [C.c_int64, C.c_int, _vp, _vp, _vp, C.POINTER(RlitgTormSchedule), _vp, _vp]
@@ -274,6 +288,7 @@ lib.rlitg_torm_bookkeep.argtypes = [_vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, 
                                     C.POINTER(RlitgTormSchedule), _vp]
 lib.rlitg_torm_update_staged.argtypes = [_vp, C.c_int64, C.c_int, _vp, C.POINTER(RlitgTormParams),
                                          C.POINTER(RlitgTormUpdate), _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+lib.rlitg_torm_collision_point.argtypes = [_vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
 
 
 def _apply_increments(self, traj, feasible_stage, inc_smooth=None, inc_coll=None, inc_pose=None, alpha=None,
@@ -331,7 +346,7 @@ TormBatch.applyIncrements = _apply_increments
 
 
 def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, check_collision=True, lr_schedule_mode=3,
-                         return_state=False, use_cuda_graph=None):
+                         return_state=False, use_cuda_graph=None, stochastic=None, seed=0, rand=None, state=None):
     """Lock-step two-stage gradient descent over the N trajectories of `traj` (in place): the loop body of
     TormOptimizer::localOptimizeTSGD (torm/src/torm_optimizer.cpp:397-598) entirely on the device -- cost +
     increments (kernels 3a / 3b), feasibility checks, the alpha_ / learning_rate_ schedule, the best-trajectory
@@ -344,11 +359,18 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
                           own history (:400-412) -- the batch then mixes feasible and end-pose updates
                        2  alpha_ as in 1, cosine learning rate with period maxiter / 2 (:493-496)
                        3  alpha_ = 0.5, fixed learning rate (:467-468, :497-498)
-    There is no host synchronisation inside an iteration (cost, collision flags, rlitg_torm_bookkeep, update: ~10
-    launches), so one iteration can also be captured in a CUDA graph and replayed (use_cuda_graph=True; identical
-    results; measured no faster than eager launching at 1,024 x 200).
+    stochastic (default: parameters.use_stochastic_descent_, true in every reference main): the collision increment of a
+    feasible half-iteration takes ONE waypoint per trajectory (:1502-1515) -- collision_point_, the first colliding row of
+    this half-iteration's isCurrentTrajectoryCollisionFree (:695-717), else a uniformly drawn free row.  The draws come
+    from `rand` ([maxiter,2,N] float32 uniforms on the device; default: torch.rand seeded with `seed`; the reference
+    calls random()); rlitg_torm_collision_point turns them into indices.  An index of -1 (the start row collides: the
+    reference then writes row -1 of the increment matrix) takes no increment.
+    state: dict(alpha=[N], learning_rate=[N]) carried over from a previous call -- alpha_ / learning_rate_ are members of
+    the reference's optimiser and persist across localOptimizeTSGD calls (infea_col / infea_vel are locals, :383).
+    There is no host synchronisation inside an iteration, so one iteration can also be captured in a CUDA graph and
+    replayed (use_cuda_graph=True; identical results).
     Returns (best_traj [N,T,7], best_cost [N]); best_cost stays +inf for trajectories never found feasible.
-    return_state=True appends a dict with the final alpha / lr / feasibility tensors."""
+    return_state=True appends a dict with the final alpha / lr / feasibility tensors and the draws."""
     pr = self.parameters
     N = traj.shape[0]
     dev, dt = self.device, traj.dtype
@@ -357,61 +379,91 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
     lr0 = float(pr.learning_rate_ if learning_rate is None else learning_rate)
     lr_max, lr_min = lr0 * 1000.0, lr0 / 100.0                      # constructor :99-101
     has_scene = self.scene is not None
+    if stochastic is None:
+        stochastic = bool(pr.use_stochastic_descent_)
+    stochastic = bool(stochastic and has_scene)
     # ---- per-trajectory optimiser state, updated in place (the captured graph keeps pointing at these buffers)
     best_cost = torch.full((N,), float("inf"), device=dev, dtype=dt)
     best_traj = traj.clone()
-    lr = torch.full((N,), lr0, device=dev, dtype=dt)
-    al = torch.full((N,), float(alpha), device=dev, dtype=dt)
+    if state is not None and "learning_rate" in state:
+        lr = state["learning_rate"].to(dev, dt).contiguous()
+        al = state["alpha"].to(dev, dt).contiguous()
+    else:
+        lr = torch.full((N,), lr0, device=dev, dtype=dt)
+        al = torch.full((N,), float(alpha), device=dev, dtype=dt)
     infea_col = torch.zeros(N, dtype=torch.uint8, device=dev)        # :383
     infea_vel = torch.zeros(N, dtype=torch.uint8, device=dev)
     stage_idx = torch.zeros(N, dtype=torch.int32, device=dev)
     lr_iter = torch.full((1,), lr0, device=dev, dtype=dt)            # mode 2: this iteration's scheduled rate
     zeros = None if has_scene else torch.zeros(N, self.T - 1, 7, device=dev, dtype=dt)
-    full_mask = STAGE_SMOOTH | STAGE_POSE_GRAD | STAGE_EVAL | (STAGE_COLL if has_scene else 0)
 
     if use_cuda_graph is None:
-        use_cuda_graph = False  # ~10 launches per iteration: eager launching keeps up with the GPU (measured)
+        use_cuda_graph = False
     sch = [RlitgTormSchedule(), RlitgTormSchedule()]
     for k in (0, 1):
         sch[k].lr_schedule_mode, sch[k].stage = mode, k
         sch[k].use_collision_check = int(has_scene and check_collision and pr.use_collision_check_)
         sch[k].use_velocity_check = int(pr.use_velocity_check_)
         sch[k].learning_rate, sch[k].learning_rate_min, sch[k].learning_rate_max = lr0, lr_min, lr_max
+        sch[k].hits_per_trajectory = 1
     code = _lib.F32 if dt == torch.float32 else _lib.F64
     singular = torch.zeros(N, dtype=torch.uint8, device=dev) if pr.use_singularity_check_ else None
-    hits_buf = torch.empty(N * self.T, dtype=torch.uint8, device=dev) if sch[0].use_collision_check else None
+    need_point = bool(sch[0].use_collision_check or stochastic)
+    any_hit = torch.zeros(N, dtype=torch.uint8, device=dev) if need_point else None
+    stoch_idx = torch.zeros(N, dtype=torch.int32, device=dev) if stochastic else None
+    if stochastic:
+        if rand is None:
+            g = torch.Generator(device=dev)
+            g.manual_seed(int(seed))
+            rand = torch.rand((max(maxiter, 1), 2, N), generator=g, device=dev, dtype=torch.float32)
+        assert rand.shape == (max(maxiter, 1), 2, N) and rand.dtype == torch.float32 and rand.is_cuda
+        u_cur = torch.empty(2, N, dtype=torch.float32, device=dev)   # this iteration's draws (fixed address: graph replay)
+    base_off = (C.c_double * 3)(*pr.base_offset)
 
-    # the sphere-grid flags only read the trajectory, like the cost kernels: they run on a side stream next to them
-    cur_stream = torch.cuda.current_stream(dev)
-    side = torch.cuda.Stream(device=dev) if (hits_buf is not None and not use_cuda_graph) else None
+    # Every half-iteration has two independent parts that only read the trajectory: the end-pose / evaluator kernel, and
+    # the collision-point test followed by the collision / smoothness kernel (which needs the test's waypoint choice).
+    # They run on two streams and share one costs buffer (RLITG_STAGE_KEEP_COSTS).
+    side = torch.cuda.Stream(device=dev)
     ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
+    KEEP = 32
 
     def sub_step(stage):
-        if side is not None:
-            ev_fork.record(cur_stream)
-            side.wait_event(ev_fork)
-            with torch.cuda.stream(side):
-                self.scene.collide(traj.reshape(-1, 7), out=hits_buf)
-                ev_join.record(side)
+        cur_stream = torch.cuda.current_stream(dev)
         if mode == 1:
             # every optimiser picks its own stage (:400-412) from the state before this half-iteration; the cost kernels
             # then only do, per trajectory, what that stage needs
             with _lib.on_device(dev):
                 check(lib.rlitg_torm_stage_decide(N, code, lr.data_ptr(), infea_col.data_ptr(), infea_vel.data_ptr(),
-                                                  C.byref(sch[stage]), stage_idx.data_ptr(),
-                                                  torch.cuda.current_stream(dev).cuda_stream))
-            r = self.cost_grad(traj, full_mask, traj_stage=stage_idx)
+                                                  C.byref(sch[stage]), stage_idx.data_ptr(), cur_stream.cuda_stream))
+            ts = stage_idx
+            pose_mask, coll_mask = STAGE_POSE_GRAD | STAGE_EVAL, STAGE_SMOOTH | (STAGE_COLL if has_scene else 0)
         elif stage == 0:
-            r = self.cost_grad(traj, STAGE_SMOOTH | STAGE_EVAL | (STAGE_COLL if has_scene else 0))
+            ts = None
+            pose_mask, coll_mask = STAGE_EVAL, STAGE_SMOOTH | (STAGE_COLL if has_scene else 0)
         else:
-            r = self.cost_grad(traj, STAGE_POSE_GRAD | STAGE_EVAL)
-        hits = None
-        if sch[stage].use_collision_check:
-            if side is not None:
-                cur_stream.wait_event(ev_join)
-                hits = hits_buf
-            else:
-                hits = self.scene.collide(traj.reshape(-1, 7), out=hits_buf)
+            ts = None
+            pose_mask, coll_mask = STAGE_POSE_GRAD | STAGE_EVAL, 0
+        two = bool(coll_mask or need_point)
+        if two:
+            ev_fork.record(cur_stream)
+            side.wait_event(ev_fork)
+            with torch.cuda.stream(side):
+                r = self.cost_grad(traj, pose_mask | (KEEP if coll_mask else 0), traj_stage=ts)
+                ev_join.record(side)
+        else:
+            r = self.cost_grad(traj, pose_mask, traj_stage=ts)
+        if need_point:
+            with _lib.on_device(dev):
+                check(lib.rlitg_torm_collision_point(traj.data_ptr(), N, self.T, code, self.scene.handle, base_off,
+                                                     u_cur[stage].data_ptr() if stochastic else None, None,
+                                                     any_hit.data_ptr(), stoch_idx.data_ptr() if stochastic else None,
+                                                     cur_stream.cuda_stream))
+        rc = None
+        if coll_mask:
+            rc = self.cost_grad(traj, coll_mask | KEEP, stochastic_idx=stoch_idx if (stochastic and (coll_mask & STAGE_COLL)) else None,
+                                traj_stage=ts)
+        if two:
+            cur_stream.wait_event(ev_join)
         if singular is not None:
             from .pirl_env import manipulability
             yosh = manipulability(traj[:, 1:].reshape(-1, 7)).reshape(N, self.T - 1)
@@ -419,18 +471,20 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
         # stage choice (mode 1), feasibility flags, alpha_ / learning_rate_ and the best-trajectory record: one launch
         with _lib.on_device(dev):
             check(lib.rlitg_torm_bookkeep(traj.data_ptr(), best_traj.data_ptr(), N, self.T, code, r["costs"].data_ptr(),
-                                          None if hits is None else hits.data_ptr(),
+                                          any_hit.data_ptr() if sch[stage].use_collision_check else None,
                                           None if singular is None else singular.data_ptr(), al.data_ptr(), lr.data_ptr(),
                                           infea_col.data_ptr(), infea_vel.data_ptr(), best_cost.data_ptr(),
                                           None, lr_iter.data_ptr() if mode == 2 else None, C.byref(sch[stage]),
-                                          torch.cuda.current_stream(dev).cuda_stream))
+                                          cur_stream.cuda_stream))
         # ---- increments -> trajectory (:562-576)
-        inc_c = r["inc_coll"] if r["inc_coll"] is not None else zeros
+        if rc is not None:
+            inc_s, inc_c = rc["inc_smooth"], (rc["inc_coll"] if rc["inc_coll"] is not None else zeros)
+        else:
+            inc_s = inc_c = None
         if mode == 1:
-            self.applyIncrements(traj, True, r["inc_smooth"], inc_c, r["inc_pose"], al, lr, lr_schedule_mode=mode,
-                                 stage_idx=stage_idx)
+            self.applyIncrements(traj, True, inc_s, inc_c, r["inc_pose"], al, lr, lr_schedule_mode=mode, stage_idx=stage_idx)
         elif stage == 0:
-            self.applyIncrements(traj, True, r["inc_smooth"], inc_c, None, al, lr, lr_schedule_mode=mode)
+            self.applyIncrements(traj, True, inc_s, inc_c, None, al, lr, lr_schedule_mode=mode)
         else:
             self.applyIncrements(traj, False, inc_pose=r["inc_pose"], alpha=al, learning_rate=lr, lr_schedule_mode=mode)
 
@@ -443,6 +497,8 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
             period = max(maxiter // 2, 1)
             ph = float(it % period) / period
             lr_iter.fill_(lr_min + 0.5 * (lr_max - lr_min) * (1.0 + np.cos(ph * np.pi)))
+        if stochastic:
+            u_cur.copy_(rand[it])
 
     graph = None
     start = 0
@@ -457,12 +513,9 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
         cap_stream = torch.cuda.Stream(device=dev)
         cap_stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(cap_stream):
-            set_iter(1)
             with torch.cuda.graph(graph, stream=cap_stream):
                 iteration()
         torch.cuda.current_stream(dev).wait_stream(cap_stream)
-        start = 2  # the capture pass does not execute; replay it once for iteration 1
-        graph.replay()
     for it in range(start, maxiter):
         set_iter(it)
         if graph is not None:
@@ -470,7 +523,8 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
         else:
             iteration()
     if return_state:
-        return best_traj, best_cost, dict(alpha=al, learning_rate=lr, infea_col=infea_col.bool(), infea_vel=infea_vel.bool())
+        return best_traj, best_cost, dict(alpha=al, learning_rate=lr, infea_col=infea_col.bool(), infea_vel=infea_vel.bool(),
+                                          rand=rand if stochastic else None)
     return best_traj, best_cost
 
 
@@ -478,7 +532,7 @@ TormBatch.localOptimizeTSGD = _local_optimize_tsgd
 
 
 def _iterative_exploration(self, init_trajs, new_trajectories=None, max_epochs=1, lr_schedule_mode=0,
-                           return_threshold=-1.0, planning_time_limit=None, check_collision=True):
+                           return_threshold=-1.0, planning_time_limit=None, check_collision=True, seed=0):
     """TormOptimizer::iterativeExploration (torm/src/torm_optimizer.cpp:604-688) with the restarts as the batch axis:
     every row of `init_trajs` [N,T,7] is one optimiser's initial trajectory (Greedy / Linear initialiser, PIRL roll-out,
     ...).  Per epoch: localOptimizeTSGD(exploration_iter_) on all N (:634), stop when the wall clock passes
@@ -495,9 +549,10 @@ def _iterative_exploration(self, init_trajs, new_trajectories=None, max_epochs=1
     best_traj = traj.clone()
     t0 = _time.perf_counter()
     epochs = 0
+    st = None  # alpha_ / learning_rate_ are optimiser members: they carry over from one localOptimizeTSGD call to the next
     for eph in range(max_epochs):
-        bt, bc = self.localOptimizeTSGD(traj, pr.exploration_iter_, lr_schedule_mode=lr_schedule_mode,
-                                        check_collision=check_collision)
+        bt, bc, st = self.localOptimizeTSGD(traj, pr.exploration_iter_, lr_schedule_mode=lr_schedule_mode,
+                                            check_collision=check_collision, return_state=True, state=st, seed=seed + eph)
         better = bc < best_cost
         best_cost = torch.where(better, bc, best_cost)
         best_traj = torch.where(better[:, None, None], bt, best_traj)

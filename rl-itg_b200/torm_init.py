@@ -9,8 +9,8 @@ selection rule (with its pruning quirk) is replayed by
 IK candidates are an INPUT, as in the reference where they come from TRAC-IK random restarts (:963-970).
 `dls_ik_candidates` is this build's own batched damped-least-squares generator on top of rlitg_pose_diff /
 rlitg_pinv_step: new work, checked only by FK(candidate) ~ target (not a parity target).
-After the segments are chosen the reference calls handleJointLimits (:1016); do that with
-TormBatch.applyIncrements(traj, False, inc_pose=zeros) when needed."""
+After the segments are chosen the reference calls handleJointLimits (:1016, :1107): pass the TormBatch of the problem
+as `batch` and the initialisers apply it (the update step with zero increments)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -96,9 +96,19 @@ class TrajectoryInitializer:
         self.simplified_points_ = simplified_points(self.T, gap)
         self.scorer = SegmentScorer(self.parameters, scene, self.device, dtype)
 
-    def getNewTrajectory(self, start_conf, candidates):
+    def _handle_joint_limits(self, traj, batch):
+        """handleJointLimits at the end of both initialisers (torm/src/torm_optimizer.cpp:1016, :1107): the update step with
+        zero increments, on the TormBatch of the same problem."""
+        if batch is not None:
+            t = traj.unsqueeze(0).contiguous()
+            batch.applyIncrements(t, False, inc_pose=torch.zeros(1, self.T - 1, 7, device=self.device, dtype=self.dtype))
+            traj = t[0]
+        return traj
+
+    def getNewTrajectory(self, start_conf, candidates, batch=None):
         """Greedy.  start_conf [7]; candidates: list (one entry per simplified point) of [C_i,7] tensors of IK
-        solutions for endPoses_desired_[simplified_points_[i]].  Returns (traj [T,7], chosen indices, best costs)."""
+        solutions for endPoses_desired_[simplified_points_[i]].  batch: the TormBatch of this problem -- handleJointLimits
+        (:1016) is then applied to the result.  Returns (traj [T,7], chosen indices, best costs)."""
         traj = torch.empty(self.T, 7, device=self.device, dtype=self.dtype)
         traj[0] = torch.as_tensor(start_conf).to(self.device, self.dtype)
         start_point = 0
@@ -112,17 +122,18 @@ class TrajectoryInitializer:
             traj[start_point + 1:sp + 1] = segs[idx.long()[0], 1:]
             chosen.append(idx); bests.append(best)
             start_point = sp
-        return traj, torch.cat(chosen), torch.cat(bests)
+        return self._handle_joint_limits(traj, batch), torch.cat(chosen), torch.cat(bests)
 
-    def getJointInterpolatedTrajectory(self, start_conf, goal_candidates):
+    def getJointInterpolatedTrajectory(self, start_conf, goal_candidates, batch=None):
         """Linear.  goal_candidates [C,7]: IK solutions of the last target pose (C = 1 with
-        use_shortest_goal_conf, 30 otherwise).  Returns (traj [T,7], chosen index, best cost)."""
+        use_shortest_goal_conf, 30 otherwise).  batch: as in getNewTrajectory (:1107).
+        Returns (traj [T,7], chosen index, best cost)."""
         st = torch.as_tensor(start_conf).to(self.device, self.dtype)
         cand = torch.as_tensor(goal_candidates).to(self.device, self.dtype).reshape(-1, 7)
         segs = fill_in_linear_interpolation(st, cand, self.T - 1, self.parameters.continuous)
         costs = self.scorer.score(segs, self.endPoses_desired_)
         idx, best = self.scorer.select(costs, self.T)
-        return segs[idx.long()[0]].clone(), idx, best
+        return self._handle_joint_limits(segs[idx.long()[0]].clone(), batch), idx, best
 
 
 def set_pirl_trajectory(end_poses, start_confs, policy, obsType="Conf+LinkPoses", t=1, gap=10, batch=None,

@@ -79,6 +79,37 @@ def test_greedy_and_linear_match_cpu_replay(cuda_device):
     gsc.close()
 
 
+@pytest.mark.parametrize("T,gap", [(43, 10), (23, 1), (12, 10)])
+def test_greedy_short_segments(cuda_device, T, gap):
+    """Segments of 2..4 rows: the reference's own paths end on them (hello: 553 poses -> last segment 550..552;
+    random_16: 382 poses -> 380..381) and its pirl configurations use gap = 1, where EVERY segment has two rows.  Only the
+    evaluator and the smoothness band need five rows; the end-pose and collision terms are per waypoint."""
+    import torch
+    from oracle import oracle as O
+    from rlitg_b200 import fetch, scene as S, synth, torm as TM, torm_init as TI
+    Cn = 7
+    rng = np.random.default_rng(T)
+    demo = synth.random_joint_paths(1, T, seed=T)[0]
+    targets = np.round(O.fk_quat(demo), 6)
+    occ, _ = synth.random_box_scene((64, 96, 64), (-0.3, -0.96, 0.0), 0.025, seed=4, n_clutter=3)
+    link, center, radius = fetch.default_spheres()
+    osc = O.Scene(O.build_field(occ, 0.025, 1.0), (-0.3, -0.96, 0.0), 0.025, link, center, radius)
+    gsc = S.Scene(cuda_device); gsc.set_occupancy(occ, (-0.3, -0.96, 0.0), 0.025, 1.0)
+    pts = TI.simplified_points(T, gap)
+    assert min(b - a for a, b in zip([0] + pts[:-1], pts)) <= 3   # at least one segment of <= 4 rows
+    cands = []
+    for sp in pts:
+        c = demo[sp] + rng.normal(0, 0.3, size=(Cn, 7)); c[2] = demo[sp]
+        cands.append(np.clip(c, fetch.LL - 3.2, fetch.UL + 3.2))
+    pr = TM.TormParameters(min_clearence_=0.3)
+    ti = TI.TrajectoryInitializer(targets, pr, gsc, cuda_device, torch.float64, gap=gap)
+    traj, chosen, best = ti.getNewTrajectory(demo[0], cands)
+    want, wchosen = cpu_greedy(demo[0], cands, targets, pts, osc, 0.3)
+    assert chosen.cpu().tolist() == wchosen
+    assert np.abs(traj.cpu().numpy() - want).max() < 1e-12
+    gsc.close()
+
+
 def test_dls_ik_candidates(cuda_device):
     """New work (not a parity target): candidates must reproduce the target pose through FK."""
     import torch

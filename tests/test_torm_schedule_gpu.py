@@ -23,8 +23,9 @@ def make_problem(N, T, seed, cuda_device, grid=(64, 96, 64), origin=(-0.3, -0.96
     return traj, targets, osc, gsc
 
 
-def replay_one(traj, targets, osc, op, Aband, Ainv, pr, maxiter, mode, T):
-    """The reference loop for ONE trajectory with scalar state, on the oracle."""
+def replay_one(traj, targets, osc, op, Aband, Ainv, pr, maxiter, mode, T, rand=None):
+    """The reference loop for ONE trajectory with scalar state, on the oracle.  rand [maxiter, 2]: the uniform draws of
+    use_stochastic_descent_ (None = every free waypoint contributes to the collision increment)."""
     from oracle import oracle as O
     from rlitg_b200 import fetch
     traj = traj.copy()
@@ -42,9 +43,18 @@ def replay_one(traj, targets, osc, op, Aband, Ainv, pr, maxiter, mode, T):
             else:
                 feasible_stage = (mode == 1 and lr == lr_max and infea_col)
             mask = (O.STAGE_SMOOTH | O.STAGE_COLL | O.STAGE_EVAL) if feasible_stage else (O.STAGE_POSE_GRAD | O.STAGE_EVAL)
-            r = O.torm_cost_grad(traj[None], targets, osc, op, Aband, mask)
+            # isCurrentTrajectoryCollisionFree :695-717 runs on the same trajectory before the increments: collision_point_
+            hit = O.sphere_collide(traj, osc, fetch.BASE_OFFSET)
+            first = int(np.argmax(hit)) if hit.any() else -1
+            st = None
+            if rand is not None:  # :1502-1515: collision_point_, else (int)(u (free_end - free_start) + free_start)
+                F = T - 1
+                st = first - 1 if first >= 0 else min(max(int(np.float32(rand[it, stage]) * np.float32(F - 1)), 0), F - 1)
+            r = O.torm_cost_grad(traj[None], targets, osc, op, Aband, mask, None if st is None or st < 0 else [st])
+            if st is not None and st < 0 and r["inc_coll"] is not None:
+                r["inc_coll"][:] = 0.0  # collision_point_ = start row: index -1, no increment is taken (appendix B item 4)
             cur = r["costs"][0, 6]
-            infea_col = bool(O.sphere_collide(traj, osc, fetch.BASE_OFFSET).any())
+            infea_col = first >= 0
             infea_vel = bool(r["costs"][0, 7] != 0)
             if mode in (1, 2):
                 if not infea_col and not infea_vel:
@@ -77,8 +87,9 @@ def replay_one(traj, targets, osc, op, Aband, Ainv, pr, maxiter, mode, T):
     return traj, best_traj, best_cost, log
 
 
+@pytest.mark.parametrize("stochastic", [False, True])
 @pytest.mark.parametrize("mode", [0, 1, 2, 3])
-def test_lockstep_schedule_matches_scalar_replay(cuda_device, mode):
+def test_lockstep_schedule_matches_scalar_replay(cuda_device, mode, stochastic):
     import torch
     from oracle import oracle as O
     from rlitg_b200 import torm as TM
@@ -92,16 +103,20 @@ def test_lockstep_schedule_matches_scalar_replay(cuda_device, mode):
         traj[n] = traj[0] + (rng.normal(0, 0.01 * (n + 1), size=(T, 7)) if n else 0.0)
         traj[n, 0] = traj[0, 0]
     traj[4, 1:, 0] += np.linspace(0, 1.4, T - 1) * np.where(np.arange(T - 1) % 2, 1, -1) * 0.2   # zig-zag: too fast
-    pr = TM.TormParameters(min_clearence_=0.3, learning_rate_=0.02)
+    traj[5, :, 1] += 0.9   # leans into the table from the first row on: collision_point_ = the start row (index -1)
+    pr = TM.TormParameters(min_clearence_=0.3, learning_rate_=0.02, use_stochastic_descent_=stochastic)
     op = O.torm_params(T, dt=pr.time_duration_, clearance=0.3)
     Aband, _, Ainv = O.smooth_setup(T, pr.time_duration_, (1.0, 0.0, 0.0), 0.0, want_inverse=True)
     tb = TM.TormBatch(targets, pr, gsc, cuda_device, torch.float64)
     t = torch.tensor(traj, dtype=torch.float64, device=cuda_device)
-    best_traj, best_cost, state = tb.localOptimizeTSGD(t, maxiter, lr_schedule_mode=mode, return_state=True)
+    best_traj, best_cost, state = tb.localOptimizeTSGD(t, maxiter, lr_schedule_mode=mode, return_state=True, seed=5)
     final = t.cpu().numpy()
+    rand = state["rand"].cpu().numpy() if stochastic else None
+    assert (rand is not None) == stochastic
     seen_stage_mix = False
     for n in range(N):
-        ftraj, btraj, bcost, log = replay_one(traj[n], targets, osc, op, Aband, Ainv, pr, maxiter, mode, T)
+        ftraj, btraj, bcost, log = replay_one(traj[n], targets, osc, op, Aband, Ainv, pr, maxiter, mode, T,
+                                              None if rand is None else rand[:, :, n])
         assert np.abs(final[n] - ftraj).max() < 1e-7, (mode, n, np.abs(final[n] - ftraj).max())
         assert abs(float(state["alpha"][n]) - log[-1][1]) < 1e-12 and abs(float(state["learning_rate"][n]) - log[-1][2]) < 1e-12 * max(1, log[-1][2])
         assert bool(state["infea_col"][n]) == log[-1][3] and bool(state["infea_vel"][n]) == log[-1][4]

@@ -35,6 +35,18 @@ def main():
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     from rlitg_b200 import kinematics as K, pirl_env as P, scene as S, synth, torm as TM
+    if a.which in ("probe", "all"):
+        import ctypes as C
+        from rlitg_b200 import _lib
+        lib = _lib.lib
+        lib.rlitg_fma_probe.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        lib.rlitg_dfma_probe.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        of, od = torch.zeros(1, device=dev), torch.zeros(1, device=dev, dtype=torch.float64)
+        st = torch.cuda.current_stream().cuda_stream
+        ms = timeit(lambda: _lib.check(lib.rlitg_fma_probe(148 * 8, 4096, of.data_ptr(), st)), a.iters)
+        print("FP32 FMA pipe: %.1f TFLOP/s" % (2.0 * 148 * 8 * 256 * 4096 * 16 / ms / 1e9))
+        ms = timeit(lambda: _lib.check(lib.rlitg_dfma_probe(148 * 8, 2048, od.data_ptr(), st)), a.iters)
+        print("FP64 FMA pipe: %.2f TFLOP/s" % (2.0 * 148 * 8 * 256 * 2048 * 8 / ms / 1e9))
     if a.which in ("fk", "all"):
         q = torch.tensor(synth.random_configs(a.fkB, seed=1), dtype=torch.float32, device=dev)
         out = {"pos": torch.empty(a.fkB, 3, device=dev), "rot": torch.empty(a.fkB, 3, 3, device=dev),
