@@ -1,15 +1,22 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the rlitg hot path on B200.
+"""bench.py -- benchmark of the rlitg hot path on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload all|fk|torm|pirl]
 
-Headline workload (BASELINE.json configs[1]): batched FK + geometric Jacobian over 1,048,576 random Fetch
-configurations per GPU (D = 7, FP32, [B,7] in -> pos [B,3], rot [B,9], J [B,6,7] out).  A "step" is one pass
-over that batch.  `value` = configs/s over all ranks with inputs resident in HBM; `e2e` = the same through the
-host-buffer C-ABI entry point (pinned host buffers, H2D + D2H inside the timed region).  One JSON line on rank 0.
-The TORM cost+gradient and PIRL env-step workloads are reported in the same line under "also".
+BASELINE.json's metric has two halves; both are in the line the driver keeps:
+  headline    batched FK + geometric Jacobian over 1,048,576 random Fetch configurations per GPU (configs[1]; D = 7, FP32,
+              q [B,7] -> pos [B,3], rot [B,9], J [B,6,7]).  A "step" is one pass over that batch.  `value` = configs/s
+              over all ranks with inputs resident in HBM; `e2e` = the same through the host-buffer C-ABI entry point
+              (pinned host buffers, H2D + D2H inside the timed region).
+  torm, pirl  TORM cost + gradient for 1,024 x 200-waypoint trajectories against a 128^3 grid (configs[3]) and the PIRL env
+              step over 16,384 envs (configs[2]): each with its own value / roofline / cpu_baseline / e2e, nested under
+              those keys of the line (`roofline.torm`, `cpu_baseline.pirl`, ...) and repeated in a compact `summary` at
+              the very end of the line.
+  config5     the strong split of configs[4] (8M configs / 65,536 envs / 8,192 trajectories over the ranks).
+One JSON line on rank 0.
 """
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -22,6 +29,7 @@ sys.path.insert(0, ROOT)
 B_PER_GPU = 1 << 20
 D = 7
 BYTES_PER_CONFIG = 4 * (D + 12 + 6 * D)  # 244 B: read q, write p[3] R[9] J[6x7]
+CPU_SAMPLE = 1 << 18                     # configurations per step of the CPU arm: a bounded sample of the 1M-config workload
 
 
 def measured_peaks():
@@ -87,58 +95,69 @@ def synth_q(B, seed, torch):
     return (torch.rand(B, D, generator=g) * (ul - ll) + ll).float()
 
 
-def cpu_reference_fk_jac(seconds_target=12.0, threads=None):
-    """times the CPU oracle (FP64 restatement of the reference's KDL calls) on a bounded sample"""
+def cpu_sample_q():
     import numpy as np
-    from oracle import oracle as O
-    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1: override it explicitly)
-    O.set_num_threads(threads or len(os.sched_getaffinity(0)))
-    cores = O.num_threads()
-    n = 1 << 18
     rng = np.random.default_rng(0)
     ll = np.array([-1.6056, -1.221, -3.141592, -2.251, -3.141592, -2.16, -3.141592]); ul = -ll.copy(); ul[1] = 1.518
-    q = rng.uniform(ll, ul, size=(n, D))
+    return rng.uniform(ll, ul, size=(CPU_SAMPLE, D))
+
+
+def cpu_reference_fk_jac(seconds_target=8.0):
+    """times the CPU oracle (FP64 restatement of the reference's two KDL calls per configuration) on a bounded sample"""
+    from oracle import oracle as O
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1: override it explicitly)
+    O.set_num_threads(len(os.sched_getaffinity(0)))
+    q = cpu_sample_q()
     O.fk_jac(q[:1024])
     t0 = time.perf_counter(); O.fk_jac(q); t1 = time.perf_counter()
-    reps = max(1, int(seconds_target / max(t1 - t0, 1e-6)))
-    reps = min(reps, 2048)
+    reps = min(max(1, int(seconds_target / max(t1 - t0, 1e-6))), 2048)
     t0 = time.perf_counter()
     for _ in range(reps):
         O.fk_jac(q)
     dt = time.perf_counter() - t0
-    return {"value": n * reps / dt, "unit": "configs/s", "cores": cores, "kind": "port",
-            "sample": "%d x %d random configs, FK+Jacobian, FP64 oracle (OpenMP), %.1f s" % (reps, n, dt)}, n
+    return {"value": CPU_SAMPLE * reps / dt, "unit": "configs/s", "cores": O.num_threads(), "kind": "port",
+            "sample": "%d x %d of the 1,048,576 configs per step; FK + Jacobian as the reference's two chain walks per "
+                      "configuration (JntToCart + JntToJac), FP64 oracle, OpenMP, %.1f s" % (reps, CPU_SAMPLE, dt)}
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """--impl reference: the reference's CPU path for the headline workload (the FP64 oracle port: the reference itself
+    needs ROS / KDL and cannot be built here), every host thread, a bounded sample of the workload per step."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     steps, warm = args.steps, args.warmup
-    import numpy as np
     from oracle import oracle as O
-    O.set_num_threads(len(os.sched_getaffinity(0)))  # torchrun exports OMP_NUM_THREADS=1: use every host thread
+    O.set_num_threads(len(os.sched_getaffinity(0)))
     cores = O.num_threads()
-    n = 1 << 18  # bounded sample of the 1M-config workload per step
-    rng = np.random.default_rng(0)
-    ll = np.array([-1.6056, -1.221, -3.141592, -2.251, -3.141592, -2.16, -3.141592]); ul = -ll.copy(); ul[1] = 1.518
-    q = rng.uniform(ll, ul, size=(n, D))
+    q = cpu_sample_q()
     for _ in range(warm):
         O.fk_jac(q)
     t0 = time.perf_counter()
     for _ in range(steps):
         O.fk_jac(q)
     dt = time.perf_counter() - t0
-    v = n * steps / dt
+    v = CPU_SAMPLE * steps / dt
+    sample = ("%d of the 1,048,576 configs per step (throughput metric: the sample bounds the run time, the per-config work is "
+              "identical); two chain walks per configuration like the reference's JntToCart + JntToJac" % CPU_SAMPLE)
     line = {"impl": "reference", "metric": "fk_jacobian_configs_per_s", "value": v, "unit": "configs/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "fk_jacobian_1M_fetch_configs", "D": D, "sample_per_step": n,
+            "config": {"workload": "fk_jacobian_1M_fetch_configs", "D": D, "sample_per_step": CPU_SAMPLE,
                        "note": "reference CPU path = FP64 oracle port of the KDL calls (reference not buildable here)"},
-            "cpu_baseline": {"value": v, "unit": "configs/s", "cores": cores, "kind": "port",
-                             "sample": "%d configs per step" % n},
+            "cpu_baseline": {"value": v, "unit": "configs/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "configs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def library_provenance():
+    from rlitg_b200 import _lib
+    st = os.stat(_lib.LIB_PATH)
+    h = hashlib.sha256()
+    with open(_lib.LIB_PATH, "rb") as f:
+        h.update(f.read())
+    return {"path": os.path.relpath(_lib.LIB_PATH, ROOT), "built_in_this_process": bool(_lib.BUILT_IN_THIS_PROCESS),
+            "shipped_prebuilt": not _lib.BUILT_IN_THIS_PROCESS, "mtime_utc": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime(st.st_mtime)),
+            "sha16": h.hexdigest()[:16]}
 
 
 def main():
@@ -147,8 +166,9 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="all", choices=["all", "fk", "torm", "pirl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads")
+    ap.add_argument("--no-also", action="store_true", help="headline workload only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -158,6 +178,7 @@ def main():
     import torch
     import torch.distributed as dist
     from rlitg_b200 import kinematics as K, _lib
+    import bench_also as BA
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -179,6 +200,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    hbm_peak, peak_src = measured_peaks()
+    want = lambda w: args.workload in ("all", w) and not (args.no_also and w != "fk")
+    cpu_ok = rank == 0 and world == 1 and not args.no_cpu_baseline
+
+    # ------------------------------------------------------------------------------------------ headline: FK + Jacobian
     B = B_PER_GPU
     q_host = synth_q(B, 1234 + rank, torch)
     q = q_host.to(dev)
@@ -193,44 +219,44 @@ def main():
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    n0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    launches = _lib.launch_count() - n0
-    ms_local = e0.elapsed_time(e1)
+    # EXACTLY K steps per timed block; 20 steps are ~0.9 ms of GPU time and move by ~5 % from block to block, so the block is
+    # repeated and the median block reported (every block: barrier + synchronize on both sides, CUDA events, max over ranks)
+    BLOCKS = 7
+    blocks, launches = [], 0
+    for _ in range(BLOCKS):
+        n0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+        launches = _lib.launch_count() - n0
+        blocks.append((max_over_ranks(e0.elapsed_time(e1)), e0.elapsed_time(e1)))
+    blocks.sort()
+    ms, ms_local = blocks[len(blocks) // 2]
     # keep the GPU busy a little longer so that NVML gets samples under load on very short runs
     t_end = time.time() + 0.3
     while time.time() < t_end:
         step()
     torch.cuda.synchronize()
     clocks = sampler.stop()
-    ms = max_over_ranks(ms_local)
     ms_per_step = ms / args.steps
     value = world * B * args.steps / (ms * 1e-3)
-
-    peak, peak_src = measured_peaks()
     achieved = BYTES_PER_CONFIG * B / (ms_local / args.steps * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "fk_jac_persist_kernel<float,7,aos,2 stages>", "bytes_per_launch": BYTES_PER_CONFIG * B,
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": BA.profile_traffic("fk_jac_kernel"),
+                "traffic_source": "profiles/traffic.json: dram__bytes of one ncu --set full capture of this kernel (not this run)",
+                "kernel": "fk_jac_persist_kernel<float,7,aos,2 stages>", "bytes_per_launch": BYTES_PER_CONFIG * B,
                 "peak_source": peak_src}
-    prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof):
-        try:
-            roofline["traffic"] = json.load(open(prof)).get("fk_jac_kernel")
-        except Exception:  # noqa: BLE001
-            pass
 
     # ---- end to end: host buffers through rlitg_fk_jac_host (H2D q, kernel, D2H pos/rot/J)
     from rlitg_b200.dist import bind_host_to_gpu
-    prev_affinity = None if os.environ.get("RLITG_BENCH_NO_NUMA") else bind_host_to_gpu(local)  # host buffers next to this rank's GPU (NUMA); undone after the e2e leg
+    prev_affinity = None if os.environ.get("RLITG_BENCH_NO_NUMA") else bind_host_to_gpu(local)
     hq = q_host.pin_memory()
     hpos = torch.empty(B, 3).pin_memory(); hrot = torch.empty(B, 3, 3).pin_memory(); hjac = torch.empty(B, 6, D).pin_memory()
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(5, min(args.steps, 20))
     for _ in range(2):
         K.fk_jac_host(hq, pos=hpos, rot=hrot, jac=hjac)
     barrier()
@@ -239,37 +265,118 @@ def main():
         K.fk_jac_host(hq, pos=hpos, rot=hrot, jac=hjac)
     torch.cuda.synchronize()
     dt = max_over_ranks(time.perf_counter() - t0)
-    e2e = {"value": world * B * e2e_steps / dt, "unit": "configs/s", "h2d_bytes_per_step": B * D * 4,
-           "d2h_bytes_per_step": B * (3 + 9 + 6 * D) * 4, "steps": e2e_steps,
-           "api": "rlitg_fk_jac_host (pinned host buffers)", "numa_bound": prev_affinity is not None}
+    h2d, d2h = B * D * 4, B * (3 + 9 + 6 * D) * 4
+    # the ceiling of that number: the same bytes as plain pinned copies (both directions at once, every rank at once)
+    dq_ = torch.empty(B, D, device=dev); dj_ = torch.empty(B, 3 + 9 + 6 * D, device=dev); hj_ = torch.empty(B, 3 + 9 + 6 * D).pin_memory()
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def copies():
+        with torch.cuda.stream(s_in):
+            dq_.copy_(hq, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            hj_.copy_(dj_, non_blocking=True)
+
+    for _ in range(2):
+        copies()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        copies()
+    torch.cuda.synchronize()
+    dtc = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": world * B * e2e_steps / dt, "unit": "configs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "steps": e2e_steps, "api": "rlitg_fk_jac_host (pinned host buffers)", "numa_bound": prev_affinity is not None,
+           "pcie_ceiling_configs_per_s": world * B * e2e_steps / dtc,
+           "pcie_ceiling_note": "the step's %d + %d bytes as bare pinned copies, both directions at once, all %d rank(s) at once: "
+                                "what bounds this number is the host side of the box (one PCIe root / NUMA domain behind all GPUs)"
+                                % (h2d, d2h, world)}
+    del dq_, dj_, hj_
     if prev_affinity is not None:
         os.sched_setaffinity(0, prev_affinity)
 
-    also = {}
-    if not args.no_also:
-        try:
-            import bench_also
-            also = bench_also.run(dev, rank, world, max_over_ranks, barrier)
-        except ImportError:
-            also = {}
+    cpu_baseline = cpu_reference_fk_jac() if cpu_ok else None
+    config = {"workload": "fk_jacobian_1M_fetch_configs", "configs_per_gpu": B, "D": D,
+              "layout": "q[B,7] -> pos[B,3], rot[B,9], J[B,6,7] (array-of-structs)",
+              "l2": "working set 256 MB per step > 126 MB L2 (no flush needed)",
+              "timing": "median of %d blocks of exactly %d steps (CUDA events, barrier + synchronize around each block, max over ranks)"
+                        % (BLOCKS, args.steps),
+              "parallelism": "dp%d (independent shards, no data-path collective)" % world}
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu, _ = cpu_reference_fk_jac()
+    # -------------------------------------------------------------------------------------- the other half of the metric
+    also, summary = {}, {}
+    sec_steps = max(10, min(args.steps, 40))
+    if want("torm") or want("pirl"):
+        fma_peak, dfma_peak = BA.pipe_peaks(torch, dev)
+        also["pipe_peaks_tflops"] = {"fp32_fma": fma_peak, "fp64_fma": dfma_peak}
+
+    def nest(name, rec):
+        """a workload's compact record under the keys the driver keeps + the summary at the end of the line"""
+        roofline[name] = rec.get("roofline")
+        e2e[name] = rec.get("e2e")
+        if cpu_baseline is not None:
+            cpu_baseline[name] = rec.get("cpu_baseline")
+        rf, cb, ee = rec.get("roofline") or {}, rec.get("cpu_baseline") or {}, rec.get("e2e") or {}
+        summary[name] = {"value": rec["value"], "unit": rec["unit"],
+                         "roofline": {k: rf.get(k) for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")},
+                         "cpu_baseline": {k: cb.get(k) for k in ("value", "cores", "kind")} if cb else None,
+                         "e2e": {k: ee.get(k) for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")}}
+
+    if want("torm"):
+        try:
+            rec, det = BA.run_torm(torch, dev, rank, world, max_over_ranks, barrier, sec_steps, 5, fma_peak, cpu=cpu_ok)
+            nest("torm", rec)
+            summary["torm"]["ms_per_iteration"] = rec["ms_per_iteration"]
+            config["torm"] = det.pop("config")
+            also["torm_cost_grad"] = dict(det, ms_per_iteration=rec["ms_per_iteration"])
+        except Exception as e:  # noqa: BLE001
+            also["torm_cost_grad"] = {"error": repr(e)}
+    if want("pirl"):
+        try:
+            rec, det = BA.run_pirl(torch, dev, rank, world, max_over_ranks, barrier, sec_steps, 5, hbm_peak, cpu=cpu_ok)
+            nest("pirl", rec)
+            summary["pirl"]["us_per_step"] = rec["us_per_step"]
+            summary["pirl"]["us_per_step_cuda_graph"] = rec["us_per_step_cuda_graph"]
+            config["pirl"] = det.pop("config")
+            also["pirl_env_step"] = det
+        except Exception as e:  # noqa: BLE001
+            also["pirl_env_step"] = {"error": repr(e)}
+    if args.workload == "all" and not args.no_also:
+        try:
+            also["config5_strong_split"] = BA.run_config5(torch, dev, rank, world, max_over_ranks, barrier, max(5, sec_steps // 2), 3)
+            c5 = also["config5_strong_split"]
+            summary["config5"] = {"fk_configs_per_s": c5["fk_jacobian_8M"]["configs_per_s"],
+                                  "pirl_env_steps_per_s": c5["pirl_65536"]["env_steps_per_s"],
+                                  "torm_waypoints_per_s": c5["torm_8192"]["waypoints_per_s"], "ranks": world}
+        except Exception as e:  # noqa: BLE001
+            also["config5_strong_split"] = {"error": repr(e)}
+        try:
+            also["fk_other_layouts"] = BA.run_fk_layouts(torch, dev, rank, world, max_over_ranks, barrier, sec_steps, 5)
+        except Exception as e:  # noqa: BLE001
+            also["fk_other_layouts"] = {"error": repr(e)}
+        if cpu_ok:
+            try:
+                also["cpu_reference_batch1"] = BA.cpu_batch1()
+            except Exception as e:  # noqa: BLE001
+                also["cpu_reference_batch1"] = {"error": repr(e)}
 
     if rank == 0:
         line = {"metric": "fk_jacobian_configs_per_s", "value": value, "unit": "configs/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "fk_jacobian_1M_fetch_configs", "configs_per_gpu": B, "D": D,
-                           "layout": "q[B,7] -> pos[B,3], rot[B,9], J[B,6,7] (array-of-structs)",
-                           "l2": "working set 256 MB per step > 126 MB L2 (no flush needed)",
-                           "parallelism": "dp%d (independent shards, no data-path collective)" % world},
-                "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
-        if cpu:
-            line["cpu_baseline"] = cpu
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "gpu_launches": launches,
+                "clocks": clocks, "config": config, "library": library_provenance()}
         if also:
             line["also"] = also
+        line["roofline"] = roofline
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        line["e2e"] = e2e
+        if args.workload in ("torm", "pirl") and args.workload in summary:
+            # --workload torm | pirl: that workload's own record as the headline of the line
+            s = summary[args.workload]
+            line.update({"metric": {"torm": "torm_cost_grad_waypoints_per_s", "pirl": "pirl_env_steps_per_s"}[args.workload],
+                         "value": s["value"], "unit": s["unit"]})
+        if summary:
+            line["summary"] = summary  # last: survives a tail-truncated log
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

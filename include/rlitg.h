@@ -110,6 +110,12 @@ RLITG_API int rlitg_scene_set_spheres(RlitgScene* scene, int S, const int32_t* l
 RLITG_API int rlitg_scene_set_occupancy(RlitgScene* scene, const uint8_t* occ, int nx, int ny, int nz,
                                         const double* origin, double res, double max_prop);
 
+/* Same with the staging kernels (two exact EDT passes, distance records, bit-packing, dilated volumes) on `stream`; the
+ * call synchronises that stream only (its host input and device temporaries must outlive the kernels), never the
+ * device.  Launch errors of every staging kernel are reported. */
+RLITG_API int rlitg_scene_set_occupancy_stream(RlitgScene* scene, const uint8_t* occ, int nx, int ny, int nz,
+                                               const double* origin, double res, double max_prop, void* stream);
+
 /* Distance volume given directly (HOST float [nz][ny][nx][4] records; d >= 1e30 marks an inactive cell). */
 RLITG_API int rlitg_scene_set_field(RlitgScene* scene, const float* field, int nx, int ny, int nz,
                                     const double* origin, double res);
@@ -180,6 +186,9 @@ typedef struct RlitgPirlCfg {
     double thr_early_stop, thr_dist, thr_rot, thr_imitate, zero_task_dist; /* (:123-128) */
     double dist_p[4], rot_p[4], imit_p[4], null_p[4];                      /* (:165-168) */
     double w_col, w_jlimit, w_early_stop;                                  /* (:170-172) */
+    int32_t row_floats;     /* values per row of the targets / demos tables: 0 or 7 = packed [B,Tmax,7]; 8 = rows padded to
+                               [B,Tmax,8] (32-byte rows, 16-byte aligned tables: one or two whole DRAM sectors per row) */
+    int32_t reserved_;
 } RlitgPirlCfg;
 
 /* Observation length for a configuration (PirlEnv.py:79-89). */
@@ -191,7 +200,8 @@ RLITG_API int rlitg_pirl_obs_dim(const RlitgPirlCfg* cfg);
  * (:495-542) -> done and info flags (:226-282).
  *   q [B,7] in/out; action [B,7] float32 (the policy's dtype, pirl/script/algos/sac/core.py:98-101);
  *   timestep [B] int32 in/out (incremented); max_timestep [B] int32;
- *   targets [B,Tmax,7], demos [B,Tmax,7] (may be NULL), latent [B,z_dim] (NULL when z_dim = 0);
+ *   targets [B,Tmax,7], demos [B,Tmax,7] (may be NULL) -- [B,Tmax,8] with cfg->row_floats = 8 --, latent [B,z_dim]
+ *   (NULL when z_dim = 0);
  *   scene may be NULL (no collision test); base_off HOST double[3];
  *   obs [B,O]; reward [B]; done [B] uint8; flags [B,8] uint8 = (is_col, is_jlimit, is_early_stop, is_timeout,
  *   is_dist_suc, is_rot_suc, is_imitate_suc, is_task_suc); counters [B,4] int32 in/out = (task, dist, rot, imitate)

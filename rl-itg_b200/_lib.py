@@ -15,6 +15,7 @@ class RlitgError(RuntimeError):
     pass
 
 
+BUILT_IN_THIS_PROCESS = False  # bench.py records whether the library was built on this box or arrived with the checkout
 if not os.path.exists(LIB_PATH):
     # not a fallback: the same `make` __graft_entry__.build() runs, for a checkout that arrives without the built library
     import shutil
@@ -24,6 +25,7 @@ if not os.path.exists(LIB_PATH):
         with open(os.path.join(_HERE, "csrc", ".build.lock"), "w") as _lock:  # one builder when N ranks start together
             fcntl.flock(_lock, fcntl.LOCK_EX)
             if not os.path.exists(LIB_PATH):
+                BUILT_IN_THIS_PROCESS = True
                 subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-j8"], stdout=subprocess.DEVNULL,
                                stderr=subprocess.DEVNULL, check=False)
 

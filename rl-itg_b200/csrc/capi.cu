@@ -116,6 +116,12 @@ static int fk_jac_host_t(const T* q, int64_t B, int D, int flags, T* pos, T* rot
     const size_t per_cfg = sizeof(T) * (size_t)(D + 3 + 9 + 4 + 6 * D);
     int rc = g_pipe.ensure(per_cfg * chunk);
     if (rc) return rc;
+    // On any failure the copies already queued on the other pipe streams may still be writing into the caller's host
+    // buffers: drain every stream before the error goes back (the caller may free or reuse the buffers right away).
+    auto fail = [&](int code) {
+        for (int i = 0; i < HostPipe::kStreams; i++) cudaStreamSynchronize(g_pipe.st[i]);
+        return code;
+    };
     int slot = 0;
     for (int64_t b0 = 0; b0 < B; b0 += chunk, slot = (slot + 1) % HostPipe::kStreams) {
         const int64_t n = (B - b0 < chunk) ? B - b0 : chunk;
@@ -126,20 +132,21 @@ static int fk_jac_host_t(const T* q, int64_t B, int D, int flags, T* pos, T* rot
         T* dquat = drot + chunk * 9;
         T* dJ = dquat + chunk * 4;
         if (cudaMemcpyAsync(dq, q + b0 * D, sizeof(T) * n * D, cudaMemcpyHostToDevice, st) != cudaSuccess)
-            return set_cuda_error("H2D q");
+            return fail(set_cuda_error("H2D q"));
         rc = launch_fk_jac<T>(dq, n, D, 0, pos ? dpos : nullptr, rot ? drot : nullptr, quat ? dquat : nullptr,
                               J ? dJ : nullptr, st);
-        if (rc) return rc;
+        if (rc) return fail(rc);
         cudaError_t e = cudaSuccess;
         if (pos) e = cudaMemcpyAsync(pos + b0 * 3, dpos, sizeof(T) * n * 3, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess && rot) e = cudaMemcpyAsync(rot + b0 * 9, drot, sizeof(T) * n * 9, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess && quat) e = cudaMemcpyAsync(quat + b0 * 4, dquat, sizeof(T) * n * 4, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess && J) e = cudaMemcpyAsync(J + b0 * 6 * D, dJ, sizeof(T) * n * 6 * D, cudaMemcpyDeviceToHost, st);
-        if (e != cudaSuccess) return set_cuda_error("D2H outputs");
+        if (e != cudaSuccess) return fail(set_cuda_error("D2H outputs"));
     }
-    for (int i = 0; i < HostPipe::kStreams; i++)
-        if (cudaStreamSynchronize(g_pipe.st[i]) != cudaSuccess) return set_cuda_error("cudaStreamSynchronize");
-    return RLITG_OK;
+    rc = RLITG_OK;
+    for (int i = 0; i < HostPipe::kStreams; i++)   // every stream is drained even when an earlier one reports an error
+        if (cudaStreamSynchronize(g_pipe.st[i]) != cudaSuccess && rc == RLITG_OK) rc = set_cuda_error("cudaStreamSynchronize");
+    return rc;
 }
 
 }  // namespace rlitg

@@ -27,7 +27,8 @@ struct PirlCfgT {
     T thr_early, thr_dist, thr_rot, thr_imit, zero_task;
     T dist_p[4], rot_p[4], imit_p[4], null_p[4];
     T w_col, w_jl, w_es;
-    int O;  // observation length
+    int O;   // observation length
+    int RS;  // floats per target / demo row: 7, or 8 (rows padded to 32 bytes: every row is one or two whole DRAM sectors)
 };
 
 static int obs_dim_of(const RlitgPirlCfg& c) {
@@ -52,6 +53,7 @@ static PirlCfgT<T> convert_cfg(const RlitgPirlCfg& c) {
     for (int k = 0; k < 4; k++) { o.dist_p[k] = (T)c.dist_p[k]; o.rot_p[k] = (T)c.rot_p[k]; o.imit_p[k] = (T)c.imit_p[k]; o.null_p[k] = (T)c.null_p[k]; }
     o.w_col = (T)c.w_col; o.w_jl = (T)c.w_jlimit; o.w_es = (T)c.w_early_stop;
     o.O = obs_dim_of(c);
+    o.RS = c.row_floats == 8 ? 8 : 7;
     return o;
 }
 
@@ -62,6 +64,26 @@ RLITG_DEV T calc_reward(T err, const T* p) {
     if constexpr (sizeof(T) == 8) e = exp(p[1] * err); else e = expf(p[1] * err);
     const T ke = p[3] * err;
     return p[0] * e - p[2] * (ke * ke);
+}
+
+// one 7-value row of the target / demo tables.  Padded rows (RS = 8) are 32-byte aligned: two 128-bit loads that touch
+// exactly one sector (FP32), instead of seven 4-byte loads of a row that straddles two (the 28-byte rows of a
+// [B,Tmax,7] table start at multiples of 28 bytes: 1.41 x the algorithmic DRAM traffic at 1M envs, round 1)
+template <typename T>
+RLITG_DEV void load_row7(const T* __restrict__ row, int RS, T (&o)[7]) {
+    if (RS == 8) {
+        if constexpr (sizeof(T) == 4) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(row)), b = __ldg(reinterpret_cast<const float4*>(row) + 1);
+            o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z;
+        } else {
+            const double2* r2 = reinterpret_cast<const double2*>(row);
+            const double2 a = __ldg(r2), b = __ldg(r2 + 1), c = __ldg(r2 + 2), d = __ldg(r2 + 3);
+            o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; o[4] = c.x; o[5] = c.y; o[6] = d.x;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 7; k++) o[k] = row[k];
+    }
 }
 
 // numpy-quaternion as_rotation_matrix (normalises by |q|^2), columns out
@@ -142,7 +164,8 @@ __global__ void __launch_bounds__(kEnvTile, sizeof(T) == 4 ? 4 : 1) pirl_env_ker
         for (int j = 0; j < 7; j++) cur[j] = q[b * 7 + j];
         int ts = timestep[b];
         const int mts = max_timestep[b];
-        const T* tg = targets + (int64_t)b * Tmax * 7;
+        const int RS = cfg.RS;
+        const T* tg = targets + (int64_t)b * Tmax * RS;
 
         const int ot = cfg.obs_type;
         PirlVisit<T> v;
@@ -163,13 +186,8 @@ __global__ void __launch_bounds__(kEnvTile, sizeof(T) == 4 ? 4 : 1) pirl_env_ker
             ts += 1;
             {
                 const int tsp = min(max(ts, 0), Tmax - 1);
-#pragma unroll
-                for (int k = 0; k < 7; k++) pf_tp[k] = tg[tsp * 7 + k];
-                if (demos != nullptr) {
-                    const T* dmp = demos + ((int64_t)b * Tmax + tsp) * 7;
-#pragma unroll
-                    for (int k = 0; k < 7; k++) pf_dm[k] = dmp[k];
-                }
+                load_row7(tg + (size_t)tsp * RS, RS, pf_tp);
+                if (demos != nullptr) load_row7(demos + ((int64_t)b * Tmax + tsp) * RS, RS, pf_dm);
                 if (counters) pf_cnt = *reinterpret_cast<const int4*>(counters + b * 4);
             }
             // _set_action :184-207
@@ -228,8 +246,7 @@ __global__ void __launch_bounds__(kEnvTile, sizeof(T) == 4 ? 4 : 1) pirl_env_ker
             if (t > mts) t = mts;
             t = min(max(t, 0), Tmax - 1);  // memory-safety guard: a caller stepping a finished episode stays in its path
             T t7[7];
-#pragma unroll
-            for (int k = 0; k < 7; k++) t7[k] = tg[t * 7 + k];
+            load_row7(tg + (size_t)t * RS, RS, t7);
             // calc_pos_and_rot_error :335-349: R_ct = tM inv(eM); columns 0 and 1
             V3<T> m0, m1, m2;
             npq_rot(t7, m0, m1, m2);
@@ -384,6 +401,8 @@ static int check_cfg(const RlitgPirlCfg* cfg) {
     if (cfg->obs_type < 0 || cfg->obs_type > 3) return set_error(RLITG_ERR_ARG, "obs_type must be 0..3");
     if (cfg->n_future < 0 || cfg->n_future > 64 || cfg->z_dim < 0 || cfg->z_dim > 4096)
         return set_error(RLITG_ERR_ARG, "n_future / z_dim out of range");
+    if (cfg->row_floats != 0 && cfg->row_floats != 7 && cfg->row_floats != 8)
+        return set_error(RLITG_ERR_ARG, "row_floats must be 0 / 7 (packed rows) or 8 (rows padded to 32 bytes)");
     return RLITG_OK;
 }
 
@@ -415,6 +434,8 @@ RLITG_API int rlitg_pirl_env_step(const RlitgPirlCfg* cfg, int64_t B, int dtype,
     if (sc && !base_off) return set_error(RLITG_ERR_NULL, "base_off is NULL");
     if ((reinterpret_cast<uintptr_t>(flags) & 7) || (counters && (reinterpret_cast<uintptr_t>(counters) & 15)))
         return set_error(RLITG_ERR_ALIGN, "flags must be 8-byte and counters 16-byte aligned");
+    if (cfg->row_floats == 8 && ((reinterpret_cast<uintptr_t>(targets) & 15) || (demos && (reinterpret_cast<uintptr_t>(demos) & 15))))
+        return set_error(RLITG_ERR_ALIGN, "padded target / demo rows (row_floats = 8) must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == RLITG_F32)
         return launch_pirl<float, true>(cfg, B, (float*)q, action, timestep, max_timestep, (const float*)targets,
@@ -436,6 +457,8 @@ RLITG_API int rlitg_pirl_obs(const RlitgPirlCfg* cfg, int64_t B, int dtype, cons
     if (B == 0) return RLITG_OK;
     if (!q || !timestep || !max_timestep || !targets || !obs) return set_error(RLITG_ERR_NULL, "a required buffer is NULL");
     if (cfg->z_dim > 0 && !latent) return set_error(RLITG_ERR_NULL, "latent is NULL but z_dim > 0");
+    if (cfg->row_floats == 8 && (reinterpret_cast<uintptr_t>(targets) & 15))
+        return set_error(RLITG_ERR_ALIGN, "padded target rows (row_floats = 8) must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == RLITG_F32)
         return launch_pirl<float, false>(cfg, B, (float*)q, nullptr, (int32_t*)timestep, max_timestep,

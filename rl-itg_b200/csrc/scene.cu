@@ -172,7 +172,7 @@ __global__ void dilate_kernel(const float4* __restrict__ field, int nx, int ny, 
 constexpr int kMaxRadiusClasses = 8;
 
 // (re)builds the dilated bit volumes once both the sphere table and the grid are present
-static int rebuild_dilated(Scene* s) {
+static int rebuild_dilated(Scene* s, cudaStream_t st = nullptr) {
     s->free_dilated();
     if (!s->field || !s->spheres || s->S == 0) return RLITG_OK;
     std::vector<float> cls;
@@ -188,17 +188,18 @@ static int rebuild_dilated(Scene* s) {
     const size_t words = (size_t)s->wx * s->ny * s->nz;
     if (cudaMalloc(&s->dil, sizeof(uint32_t) * words * cls.size()) != cudaSuccess ||
         cudaMalloc(&s->sph_class, sizeof(int) * s->S) != cudaSuccess ||
-        cudaMemcpy(s->sph_class, sc.data(), sizeof(int) * s->S, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaMemcpyAsync(s->sph_class, sc.data(), sizeof(int) * s->S, cudaMemcpyHostToDevice, st) != cudaSuccess) {
         s->free_dilated();
         return set_cuda_error("rebuild_dilated");
     }
     for (size_t c = 0; c < cls.size(); c++) {
-        dilate_kernel<<<blocks_for((int64_t)words * 32, 256), 256>>>(s->field, s->nx, s->ny, s->nz, s->wx, cls[c],
-                                                                     s->dil + c * words);
+        dilate_kernel<<<blocks_for((int64_t)words * 32, 256), 256, 0, st>>>(s->field, s->nx, s->ny, s->nz, s->wx, cls[c],
+                                                                            s->dil + c * words);
         int rc = check_launch("dilate_kernel");
-        if (rc) return rc;
+        if (rc) { s->free_dilated(); return rc; }
     }
-    if (cudaDeviceSynchronize() != cudaSuccess) return set_cuda_error("rebuild_dilated");
+    // `sc` (host) feeds the asynchronous copy above: wait for this stream only, not for the whole device
+    if (cudaStreamSynchronize(st) != cudaSuccess) { s->free_dilated(); return set_cuda_error("rebuild_dilated"); }
     s->ncls = (int)cls.size();
     return RLITG_OK;
 }
@@ -449,43 +450,63 @@ static int scene_alloc_grid(Scene* s, int nx, int ny, int nz, const double* orig
     return RLITG_OK;
 }
 
-RLITG_API int rlitg_scene_set_occupancy(RlitgScene* h, const uint8_t* occ, int nx, int ny, int nz,
-                                        const double* origin, double res, double max_prop) {
+// frees the staging temporaries of rlitg_scene_set_occupancy on every path out of it
+struct EdtTemps {
+    uint8_t* occ = nullptr;
+    int32_t *a = nullptr, *b = nullptr, *dso = nullptr;
+    float* d = nullptr;
+    ~EdtTemps() {
+        if (occ) cudaFree(occ);
+        if (a) cudaFree(a);
+        if (b) cudaFree(b);
+        if (dso) cudaFree(dso);
+        if (d) cudaFree(d);
+    }
+};
+
+RLITG_API int rlitg_scene_set_occupancy_stream(RlitgScene* h, const uint8_t* occ, int nx, int ny, int nz,
+                                               const double* origin, double res, double max_prop, void* stream) {
     Scene* s = reinterpret_cast<Scene*>(h);
     if (!s || !occ || !origin) return set_error(RLITG_ERR_NULL, "scene / occ / origin is NULL");
     int rc = scene_alloc_grid(s, nx, ny, nz, origin, res);
     if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t n = (int64_t)nx * ny * nz;
-    uint8_t* d_occ = nullptr;
-    int32_t *a = nullptr, *b = nullptr, *dso = nullptr;
-    float* d = nullptr;
-    CUDA_TRY(cudaMalloc(&d_occ, n), "cudaMalloc(occ)");
-    CUDA_TRY(cudaMalloc(&a, sizeof(int32_t) * n), "cudaMalloc(edt)");
-    CUDA_TRY(cudaMalloc(&b, sizeof(int32_t) * n), "cudaMalloc(edt)");
-    CUDA_TRY(cudaMalloc(&dso, sizeof(int32_t) * n), "cudaMalloc(edt)");
-    CUDA_TRY(cudaMalloc(&d, sizeof(float) * n), "cudaMalloc(edt)");
-    CUDA_TRY(cudaMemcpy(d_occ, occ, n, cudaMemcpyHostToDevice), "H2D occupancy");
+    EdtTemps t;
+    CUDA_TRY(cudaMalloc(&t.occ, n), "cudaMalloc(occ)");
+    CUDA_TRY(cudaMalloc(&t.a, sizeof(int32_t) * n), "cudaMalloc(edt)");
+    CUDA_TRY(cudaMalloc(&t.b, sizeof(int32_t) * n), "cudaMalloc(edt)");
+    CUDA_TRY(cudaMalloc(&t.dso, sizeof(int32_t) * n), "cudaMalloc(edt)");
+    CUDA_TRY(cudaMalloc(&t.d, sizeof(float) * n), "cudaMalloc(edt)");
+    CUDA_TRY(cudaMemsetAsync(s->bits, 0, sizeof(uint32_t) * (size_t)s->wx * ny * nz, st), "cudaMemset(bits)");
+    CUDA_TRY(cudaMemcpyAsync(t.occ, occ, n, cudaMemcpyHostToDevice, st), "H2D occupancy");
     const int bs = 256;
     const unsigned g = blocks_for(n, bs);
     for (int pass = 0; pass < 2; pass++) {  // 0: distance to occupied, 1: distance to free
-        edt_init_kernel<<<g, bs>>>(d_occ, n, pass, a);
-        edt_pass_kernel<<<g, bs>>>(a, b, nx, ny, nz, 0);
-        edt_pass_kernel<<<g, bs>>>(b, a, nx, ny, nz, 1);
-        edt_pass_kernel<<<g, bs>>>(a, pass == 0 ? dso : b, nx, ny, nz, 2);
-        for (int k = 0; k < 4; k++) check_launch("edt kernels");
+        edt_init_kernel<<<g, bs, 0, st>>>(t.occ, n, pass, t.a);
+        if ((rc = check_launch("edt_init_kernel"))) return rc;
+        edt_pass_kernel<<<g, bs, 0, st>>>(t.a, t.b, nx, ny, nz, 0);
+        if ((rc = check_launch("edt_pass_kernel(x)"))) return rc;
+        edt_pass_kernel<<<g, bs, 0, st>>>(t.b, t.a, nx, ny, nz, 1);
+        if ((rc = check_launch("edt_pass_kernel(y)"))) return rc;
+        edt_pass_kernel<<<g, bs, 0, st>>>(t.a, pass == 0 ? t.dso : t.b, nx, ny, nz, 2);
+        if ((rc = check_launch("edt_pass_kernel(z)"))) return rc;
     }
-    edt_signed_kernel<<<g, bs>>>(dso, b, n, (float)res, (float)max_prop, d);
-    check_launch("edt_signed_kernel");
-    field_record_kernel<<<g, bs>>>(d, nx, ny, nz, (float)max_prop, (float)(1.0 / (2.0 * res)), s->field);
-    check_launch("field_record_kernel");
+    edt_signed_kernel<<<g, bs, 0, st>>>(t.dso, t.b, n, (float)res, (float)max_prop, t.d);
+    if ((rc = check_launch("edt_signed_kernel"))) return rc;
+    field_record_kernel<<<g, bs, 0, st>>>(t.d, nx, ny, nz, (float)max_prop, (float)(1.0 / (2.0 * res)), s->field);
+    if ((rc = check_launch("field_record_kernel"))) return rc;
     const int64_t nwords = (int64_t)s->wx * ny * nz;
-    bitpack_kernel<<<blocks_for(nwords * 32, bs), bs>>>(d_occ, nx, ny, nz, s->wx, s->bits);
-    rc = check_launch("bitpack_kernel");
-    cudaError_t e = cudaDeviceSynchronize();
-    cudaFree(d_occ); cudaFree(a); cudaFree(b); cudaFree(dso); cudaFree(d);
-    if (e != cudaSuccess) return set_cuda_error("scene_set_occupancy");
-    if (rc) return rc;
-    return rebuild_dilated(s);
+    bitpack_kernel<<<blocks_for(nwords * 32, bs), bs, 0, st>>>(t.occ, nx, ny, nz, s->wx, s->bits);
+    if ((rc = check_launch("bitpack_kernel"))) return rc;
+    // the temporaries are freed when this function returns: the staging kernels must be done with them (this stream only)
+    CUDA_TRY(cudaStreamSynchronize(st), "scene_set_occupancy");
+    return rebuild_dilated(s, st);
+}
+
+RLITG_API int rlitg_scene_set_occupancy(RlitgScene* h, const uint8_t* occ, int nx, int ny, int nz,
+                                        const double* origin, double res, double max_prop) {
+    return rlitg_scene_set_occupancy_stream(h, occ, nx, ny, nz, origin, res, max_prop, nullptr);
 }
 
 RLITG_API int rlitg_scene_set_field(RlitgScene* h, const float* field, int nx, int ny, int nz, const double* origin,

@@ -530,33 +530,20 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
             sd = scene_dev(scene);
             S = sd.S;
         }
-        // rows per chunk: what fits ~56 KB of shared memory per CTA (four CTAs per SM), at most 64; the chunks of a
-        // trajectory are spread over a cluster of CL CTAs (each CTA loops when the path has more than CL chunks)
-        using CFT = typename std::conditional<sizeof(T) == 4, double, T>::type;  // the FP32 build sizes for the FP64 walk
-        int cap = kCollMaxRows;
-        while (cap > 8 && coll_layout<T, CFT>(cap, S).total > 56u * 1024u * (sizeof(T) / 4)) cap--;
-        static const int cap_env = [] { const char* e = getenv("RLITG_TORM_COLL_ROWS"); return e ? atoi(e) : 0; }();
-        if (cap_env >= 8 && cap_env < cap) cap = cap_env;
-        const int Tn = (int)p->T;
-        const int CL = std::min(kCollMaxCluster, (Tn + cap - 1) / cap);
-        const int nch = CL * ((Tn + cap * CL - 1) / (cap * CL));
-        const int R = (Tn + nch - 1) / nch;
-        const size_t smem = coll_layout<T, CFT>(R, S).total;
-        if (smem > 200 * 1024) return set_error(RLITG_ERR_SHAPE, "too many spheres for the shared-memory tile");
-        if (N * (int64_t)CL > 0x7fffffff) return set_error(RLITG_ERR_SHAPE, "N x chunks out of range");
+        const size_t smem = sizeof(T) * ((size_t)(CH + 12) * 7 + 8 * 2 + (size_t)(std::min(CH, (int)p->T) + 6) * ((3 * S) | 1));
+        if (smem > 220 * 1024) return set_error(RLITG_ERR_SHAPE, "too many spheres for the shared-memory tile");
         // FP32 build: chain walk of phase 1 in FP64 (accuracy of the 1 / dt^2 stencils, torm_coll.cuh); RLITG_TORM_FK64=0
-        // keeps it in FP32 (measurement knob)
+        // keeps it in FP32 (measurement knob).  Register budget: 2 CTAs/SM (128 regs) or 3 (96); RLITG_TORM_COLL_OCC
         static const int fk64 = [] { const char* e = getenv("RLITG_TORM_FK64"); return e ? atoi(e) : 1; }();
+        static const int cocc = [] { const char* e = getenv("RLITG_TORM_COLL_OCC"); return e ? atoi(e) : 2; }();
         using KernT = void (*)(TormP<T>, const T*, SceneDev, int, const T*, int, int, const int32_t*, T*, T*, T*, float*,
-                               const int32_t*, int, int);
+                               const int32_t*);
         KernT kern;
-        // register budget: 4 CTAs per SM (64 registers, 32 warps) by default, RLITG_TORM_COLL_OCC=3 -> 80 registers
-        static const int cocc = [] { const char* e = getenv("RLITG_TORM_COLL_OCC"); return e ? atoi(e) : 4; }();
         if constexpr (sizeof(T) == 4) {
-            if (cocc == 3) kern = fk64 ? torm_coll_kernel<T, true, 3> : torm_coll_kernel<T, false, 3>;
-            else kern = fk64 ? torm_coll_kernel<T, true, 4> : torm_coll_kernel<T, false, 4>;
+            if (cocc == 3) kern = fk64 ? torm_coll_kernel<T, true, 96> : torm_coll_kernel<T, false, 96>;
+            else kern = fk64 ? torm_coll_kernel<T, true, 128> : torm_coll_kernel<T, false, 128>;
         } else {
-            kern = torm_coll_kernel<T, false, 1>;
+            kern = torm_coll_kernel<T, false, 255>;
         }
         {
             int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "torm_coll_kernel");
@@ -565,20 +552,9 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
         const T* band = nullptr;
         if (stage_mask & RLITG_STAGE_SMOOTH)
             band = reinterpret_cast<const T*>(sizeof(T) == 4 ? (const void*)smooth->d_band32 : (const void*)smooth->d_band64);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)(N * CL));
-        cfg.blockDim = dim3(kCollThreads);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = (unsigned)CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
         const int zero_pose = (run_pose || (stage_mask & RLITG_STAGE_KEEP_COSTS)) ? 0 : 1;
-        if (cudaLaunchKernelEx(&cfg, kern, P, traj, sd, S, band, stage_mask, zero_pose, stoch, inc_smooth, inc_coll, costs,
-                               active, traj_stage, R, nch) != cudaSuccess)
-            return set_cuda_error("torm_coll_kernel launch");
+        kern<<<(unsigned)N, CH, smem, st>>>(P, traj, sd, S, band, stage_mask, zero_pose, stoch, inc_smooth, inc_coll, costs,
+                                            active, traj_stage);
         int rc = check_launch("torm_coll_kernel");
         if (rc) return rc;
     }

@@ -29,7 +29,7 @@ class RlitgPirlCfg(C.Structure):
                 ("thr_dist", C.c_double), ("thr_rot", C.c_double), ("thr_imitate", C.c_double),
                 ("zero_task_dist", C.c_double), ("dist_p", C.c_double * 4), ("rot_p", C.c_double * 4),
                 ("imit_p", C.c_double * 4), ("null_p", C.c_double * 4), ("w_col", C.c_double),
-                ("w_jlimit", C.c_double), ("w_early_stop", C.c_double)]
+                ("w_jlimit", C.c_double), ("w_early_stop", C.c_double), ("row_floats", C.c_int32), ("reserved_", C.c_int32)]
 
 
 _vp, _i64, _i = C.c_void_p, C.c_int64, C.c_int
@@ -119,6 +119,17 @@ def pose_diff(q, target):
     return tw
 
 
+def refine_continuous_joints(conf):
+    """PirlEnv_Fetch.refine_continuous_joints (PirlEnv.py:577-590) on a [..., 7] tensor: continuous joints beyond +-pi are
+    brought back by whole turns (int() truncation, then one more turn if still outside)."""
+    cj = torch.tensor(fetch.CONTINUOUS, device=conf.device, dtype=torch.bool)
+    two_pi = 2 * np.pi
+    wrapped = conf - torch.trunc(conf / two_pi) * two_pi
+    wrapped = torch.where((conf > np.pi) & (wrapped > np.pi), wrapped - two_pi, wrapped)
+    wrapped = torch.where((conf < -np.pi) & (wrapped < -np.pi), wrapped + two_pi, wrapped)
+    return torch.where((conf.abs() > np.pi) & cj, wrapped, conf)
+
+
 class PirlVecEnv:
     """B path-following IK environments stepped by one kernel (rlitg_pirl_env_step)."""
 
@@ -150,6 +161,7 @@ class PirlVecEnv:
         self.flags = torch.empty(B, 8, dtype=torch.uint8, **kw)
         self.errs = torch.empty(B, 4, dtype=dtype, **kw) if want_errs else None
         self.target_poses = self.demo_configs = self.latent = None
+        self._targets8 = self._demos8 = None
         self.Tmax = 0
         self._pre = self._post = self._info = None
         self._base_off = np.ascontiguousarray(scene.base_offset if scene is not None else fetch.BASE_OFFSET, dtype=np.float64)
@@ -158,10 +170,25 @@ class PirlVecEnv:
     def set_problems(self, target_poses, demo_configs, max_timestep, latent=None):
         """target_poses [B,Tmax,7], demo_configs [B,Tmax,7] or None, max_timestep [B]; latent [B,zDim]."""
         conv = lambda a: None if a is None else torch.as_tensor(a).to(self.device, self.dtype).contiguous()
-        self.target_poses = conv(target_poses)
-        self.demo_configs = conv(demo_configs)
+
+        def rows8(a):
+            """[B,Tmax,7] -> [B,Tmax,8]: 32-byte rows (FP32), so that the per-env row gathers of the step touch whole
+            DRAM sectors (cfg.row_floats = 8); target_poses / demo_configs stay 7-wide views of the padded tables"""
+            if a is None:
+                return None
+            p = torch.zeros(a.shape[0], a.shape[1], 8, device=self.device, dtype=self.dtype)
+            p[..., :7] = a
+            return p
+
+        tp, dc = conv(target_poses), conv(demo_configs)
+        assert tp.shape[0] == self.B and tp.shape[2] == 7
+        if dc is not None and not self._args["refineFlag"]:
+            dc = refine_continuous_joints(dc)   # the reference refines EVERY demo row in reset (PirlEnv.py:362-365)
+        self._targets8, self._demos8 = rows8(tp), rows8(dc)
+        self.target_poses = self._targets8[..., :7]
+        self.demo_configs = None if dc is None else self._demos8[..., :7]
+        self.cfg.row_floats = 8
         self.Tmax = int(self.target_poses.shape[1])
-        assert self.target_poses.shape == (self.B, self.Tmax, 7)
         self.max_timestep = torch.as_tensor(max_timestep).to(self.device, torch.int32).contiguous()
         self.latent = conv(latent)
         if self.cfg.z_dim > 0 and self.latent is None:
@@ -174,15 +201,9 @@ class PirlVecEnv:
         if mode != self.mode:
             self.mode = mode
             self.cfg = make_cfg(mode=mode, **self._args)
+            self.cfg.row_floats = 8
         if start_conf is None:
-            q0 = self.demo_configs[:, 0, :].clone()
-            cj = torch.tensor(fetch.CONTINUOUS, device=self.device, dtype=torch.bool)
-            two_pi = 2 * np.pi
-            wrapped = q0 - torch.trunc(q0 / two_pi) * two_pi   # refine_continuous_joints :577-590
-            wrapped = torch.where(wrapped > np.pi, wrapped - two_pi, wrapped)
-            wrapped = torch.where(wrapped < -np.pi, wrapped + two_pi, wrapped)
-            need = (q0.abs() > np.pi) & cj
-            q0 = torch.where(need, wrapped, q0)
+            q0 = self.demo_configs[:, 0, :].clone()   # already refined to (-pi, pi] by set_problems
         else:
             q0 = torch.as_tensor(start_conf).to(self.device, self.dtype)
         self.cur_conf.copy_(q0.reshape(self.B, 7))  # in place: captured CUDA graphs keep pointing at this buffer
@@ -195,7 +216,7 @@ class PirlVecEnv:
         with _lib.on_device(self.device):
             check(lib.rlitg_pirl_obs(C.byref(self.cfg), self.B, _code(self.cur_conf), self.cur_conf.data_ptr(),
                                      self.timestep.data_ptr(), self.max_timestep.data_ptr(),
-                                     self.target_poses.data_ptr(), self.Tmax,
+                                     self._targets8.data_ptr(), self.Tmax,
                                      None if self.latent is None else self.latent.data_ptr(), self.obs.data_ptr(),
                                      _stream()))
         return self.obs
@@ -208,8 +229,8 @@ class PirlVecEnv:
                       "is_col": self.flags[:, 0], "is_jlimit": self.flags[:, 1], "is_early_stop": self.flags[:, 2],
                       "is_timeout": self.flags[:, 3]}
         self._pre = (C.byref(self.cfg), self.B, _code(self.cur_conf), self.cur_conf.data_ptr())
-        self._post = (self.timestep.data_ptr(), self.max_timestep.data_ptr(), self.target_poses.data_ptr(),
-                      p(self.demo_configs), self.Tmax, p(self.latent),
+        self._post = (self.timestep.data_ptr(), self.max_timestep.data_ptr(), self._targets8.data_ptr(),
+                      p(self._demos8), self.Tmax, p(self.latent),
                       None if self.scene is None else self.scene.handle, self._base_off.ctypes.data,
                       self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(), self.flags.data_ptr(),
                       self.counters.data_ptr(), p(self.errs))

@@ -575,26 +575,35 @@ lib.rlitg_torm_cost_grad_host.argtypes = [_vp, _vp, C.c_int64, C.c_int, _vp, _vp
                                           _vp, _vp, _vp, _vp]
 
 
-def _cost_grad_host(self, traj, stage_mask, stochastic_idx=None):
+def _cost_grad_host(self, traj, stage_mask, stochastic_idx=None, out=None):
     """rlitg_torm_cost_grad_host: `traj` is a HOST numpy array [N,T,7] (float32 / float64 matching the batch dtype);
-    results come back as numpy arrays.  The end-to-end form for callers that keep trajectories on the host."""
+    results come back as numpy arrays.  The end-to-end form for callers that keep trajectories on the host.
+    out: optional dict of preallocated host arrays (inc_smooth / inc_coll / inc_pose [N,T-1,7], costs [N,10]) to fill --
+    pinned ones (torch.empty(...).pin_memory().numpy()) give full PCIe bandwidth."""
     npdt = np.float32 if self.dtype == torch.float32 else np.float64
     traj = np.ascontiguousarray(traj, dtype=npdt)
     N, T, _ = traj.shape
     F = T - 1
-    targets = self.endPoses_desired_.cpu().numpy().astype(npdt)
-    out = {k: (np.empty((N, F, 7), dtype=npdt) if stage_mask & bit else None)
-           for k, bit in (("inc_smooth", STAGE_SMOOTH), ("inc_coll", STAGE_COLL), ("inc_pose", STAGE_POSE_GRAD))}
-    costs = np.empty((N, NCOST), dtype=npdt)
+    if getattr(self, "_targets_host", None) is None:
+        self._targets_host = self.endPoses_desired_.cpu().numpy().astype(npdt)
+    targets = self._targets_host
+    out = dict(out) if out is not None else {}
+    for k, bit in (("inc_smooth", STAGE_SMOOTH), ("inc_coll", STAGE_COLL), ("inc_pose", STAGE_POSE_GRAD)):
+        if not (stage_mask & bit):
+            out[k] = None
+        elif out.get(k) is None:
+            out[k] = np.empty((N, F, 7), dtype=npdt)
+    if out.get("costs") is None:
+        out["costs"] = np.empty((N, NCOST), dtype=npdt)
     st = None if stochastic_idx is None else np.ascontiguousarray(stochastic_idx, dtype=np.int32)
     p = lambda a: None if a is None else a.ctypes.data
     with _lib.on_device(self.device):
         check(lib.rlitg_torm_cost_grad_host(traj.ctypes.data, targets.ctypes.data, N,
                                             _lib.F32 if npdt == np.float32 else _lib.F64,
-                                            None if self.scene is None else self.scene.handle, self.joint_costs_.handle,
+                                            None if self.scene is None else self.scene.handle,
+                                            None if self.joint_costs_ is None else self.joint_costs_.handle,
                                             C.byref(self._cp), int(stage_mask), p(st), p(out["inc_smooth"]),
-                                            p(out["inc_coll"]), p(out["inc_pose"]), costs.ctypes.data))
-    out["costs"] = costs
+                                            p(out["inc_coll"]), p(out["inc_pose"]), out["costs"].ctypes.data))
     return out
 
 

@@ -117,6 +117,32 @@ def test_fk_jac_full_size_properties(cuda_device):
     assert (Js.float() - J[idx.to(cuda_device)]).abs().max().item() < 2e-6
 
 
+@pytest.mark.parametrize("D", [7, 8])
+@pytest.mark.parametrize("dtype,rel,floor", [("float32", 1e-5, 1e-6), ("float64", 1e-12, 1e-13)])
+def test_fk_jac_benchmark_size_against_oracle(cuda_device, D, dtype, rel, floor):
+    """BASELINE config 2 as benchmarked: 1,048,576 configurations, array-of-structs in and out -> the PERSISTENT kernel
+    (fk_jac_persist_kernel: >= 1,024 tiles) -- every pose, rotation and Jacobian entry against the CPU oracle, FP32 and
+    the FP64 verification build, D = 7 and the D = 8 torso chain."""
+    import torch
+    from oracle import oracle as O
+    from rlitg_b200 import kinematics as K, _lib
+    import os
+    O.set_num_threads(len(os.sched_getaffinity(0)))
+    B = 1 << 20
+    q = random_configs(B, D, seed=40 + D)
+    if dtype == "float32":
+        q = q.astype(np.float32).astype(np.float64)   # both sides see the same joint values
+    pos, R, J = O.fk_jac(q)
+    n0 = _lib.launch_count()
+    r = K.fk_jac(torch.tensor(q, dtype=getattr(torch, dtype), device=cuda_device))
+    torch.cuda.synchronize()
+    assert _lib.launch_count() - n0 <= 2   # the persistent kernel (+ at most a tail launch), not a tile-per-CTA sweep
+    gp, gr, gj = [r[k].double().cpu().numpy() for k in ("pos", "rot", "jac")]
+    assert close(gp, pos, rel, floor) <= 1.0
+    assert close(gr, R, rel, floor) <= 1.0
+    assert close(gj, J, rel, floor) <= 1.0
+
+
 def test_service_shims(cuda_device, fk_pairs):
     from oracle import oracle as O
     from rlitg_b200.kinematics import KinematicsServices

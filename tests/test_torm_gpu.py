@@ -2,7 +2,8 @@
 
 Stated tolerances.  FP64 build: 1e-8 relative on costs and increments (SVD vs Cholesky, summation order).
 FP32 (errors are relative to the row's largest component, floor 1e-6):
-  costs                 <= 1e-4 relative (collision cost 2e-3: potentials are differences of O(1) distances)
+  costs                 <= 1e-4 relative, the collision cost included (the potentials read the same FP32 distance records on
+                        both sides; sphere centres come from an FP64 chain walk rounded once to FP32)
   smoothness increments <= 2e-6 * sum_k |a_k| |2 x_k| per element (13-tap FP32 sums: bounded by the magnitudes, not by the
                         cancelling result), <= 2e-4 of the row maximum
   end-pose increments   <= max(1e-4, 1e-6 / sigma_min(J)^2, 3e-6 / sin(theta)): FP32 Jacobian entries carry up to ~1e-6
@@ -12,9 +13,11 @@ FP32 (errors are relative to the row's largest component, floor 1e-6):
                         tracking trajectory does not).  So <= 1e-4 for sigma_min > 0.1 and theta < pi - 0.03.
                         Waypoints with sqrt(det(J J^T)) < 1e-3 are excluded and counted
   collision increments  rows with a sphere centre within 1e-6 m of a voxel boundary are excluded and counted (< 4 %:
-                        nearest-cell lookup); elsewhere median < 2e-5, >= 90 % of rows <= 1e-4, every row <= 5e-3 (explicit
-                        3 x 3 inverse of J J^T + ridge I in FP32, cond up to ~1e4, and 7-point differences of FP32 sphere
-                        positions scaled by 1 / dt^2).
+                        nearest-cell lookup); elsewhere 1e-4 of the row maximum: median < 5e-6, every row <= 1e-3,
+                        at most 1 % of the rows above 1e-4 at the benchmark shape (203,776 rows; 2 % on the 200-row test
+                        problems, where one row is 0.5 %).  What made this reachable in FP32: the chain walk in FP64 with one
+                        rounding per sphere centre, centre-relative stencils, and the QR form of J^T (J J^T + ridge I)^-1 g
+                        (tools/coll_fp32_study.py separates the error sources on the CPU).
 The suite is meant to hold on any data: RLITG_TEST_SEED=k (tests/conftest.py) shifts every seed."""
 import numpy as np
 import pytest
@@ -58,16 +61,15 @@ def voxel_boundary_rows(traj, origin, res, margin=1e-6):
 
 def check_fp32_collision_increments(got, want, traj, origin, res):
     """FP32 collision increments against the oracle, relative to each row's largest component.  Rows with a sphere on a
-    voxel boundary are excluded and counted (< 4 %; ~0.6 % expected).  Elsewhere: median < 2e-5, at most 10 % of the rows above 1e-4 and
-    every row below 5e-3 (ten shifted-seed runs of the whole suite: worst 6.7 % and 2.9e-3) -- the tail comes from the explicit 3 x 3 inverse of J J^T + ridge I in FP32 (cond up to ~1e4;
-    a QR formulation halves the error but costs 23 % of the kernel, measured) and from 7-point differences of FP32
-    sphere positions scaled by 1 / dt^2."""
+    voxel boundary are excluded and counted (< 4 %; ~0.6 % expected).  Elsewhere: median < 5e-6, every row below 1e-3 and at
+    most 2 % of the rows above 1e-4 (these problems have 100 - 900 rows; the 1 % bound is asserted on the 203,776 rows of
+    the benchmark shape, test_cost_grad_benchmark_shape_all_trajectories)."""
     skip = voxel_boundary_rows(traj, origin, res)  # expected share: 24 spheres x 3 axes x 2 margin / res ~ 0.6 %
     assert skip.mean() < 0.04, skip.mean()
     err = np.abs(got - want).max(axis=-1)
     scale = np.abs(want).max(axis=-1)
     rr = (err / (scale + 1e-6))[~skip]
-    assert np.median(rr) < 2e-5 and (rr > 1e-4).mean() < 0.10 and rr.max() < 5e-3, \
+    assert np.median(rr) < 5e-6 and (rr > 1e-4).mean() < 0.02 and rr.max() < 1e-3, \
         (np.median(rr), (rr > 1e-4).mean(), rr.max(), int(skip.sum()))
 
 
@@ -141,7 +143,7 @@ def test_cost_grad_parity(cuda_device, dtype, T, N, dt, clearance, quirk, use_pi
         assert np.abs(got["active"].cpu().numpy() - want["active"]).max() < 1e-6
     else:
         check_fp32_collision_increments(gc, want["inc_coll"], traj, (-0.3, -0.96, 0.0), 0.025)
-        assert np.abs(costs[:, 5] - want["costs"][:, 5]).max() <= 2e-3 * np.abs(want["costs"][:, 5]).max()
+        assert np.abs(costs[:, 5] - want["costs"][:, 5]).max() <= 1e-4 * np.abs(want["costs"][:, 5]).max()
     gsc.close()
 
 
@@ -169,6 +171,47 @@ def test_stochastic_index_and_stage_masks(cuda_device, dtype):
     ev = tb.evaluate(tt)
     we = O.traj_eval(traj, targets, op)
     assert np.abs(ev["cost_pose"].double().cpu().numpy() - we[:, 0]).max() < (1e-10 if dtype == "float64" else 1e-5)
+    gsc.close()
+
+
+def test_cost_grad_benchmark_shape_all_trajectories(cuda_device):
+    """BASELINE config 4 as benchmarked: 1,024 trajectories x 200 waypoints, 24 spheres, 128^3 grid @ 0.02 m, clearance
+    0.3 -- the FP32 production kernels (torm_coll_kernel<float>, torm_pose_eval_kernel<float>) on ALL trajectories
+    against the oracle: costs 1e-4, smoothness by its magnitude bound, collision increments 1e-4 of the row maximum with
+    the voxel-boundary rows excluded and counted, end-pose increments on the well-conditioned rows."""
+    import os
+    import torch
+    from oracle import oracle as O
+    from rlitg_b200 import fetch, scene as S, synth, torm as TM
+    O.set_num_threads(len(os.sched_getaffinity(0)))
+    N, T = 1024, 200
+    origin, res = (-0.64, -1.28, -0.20), 0.02
+    traj = synth.linear_trajectories(N, T, seed=100, noise=0.05).astype(np.float32).astype(np.float64)
+    targets = synth.random_ee_paths(1, T, seed=7)[0]
+    occ, _ = synth.random_box_scene((128, 128, 128), origin, res, seed=0)
+    link, center, radius = fetch.default_spheres()
+    osc = O.Scene(O.build_field(occ, res, 1.0), origin, res, link, center, radius)
+    gsc = S.Scene(cuda_device); gsc.set_occupancy(occ, origin, res, 1.0)
+    op = O.torm_params(T, dt=0.1, clearance=0.3)
+    Aband, _, _ = O.smooth_setup(T, 0.1, (1.0, 0.0, 0.0), 0.0)
+    mask = O.STAGE_POSE_GRAD | O.STAGE_SMOOTH | O.STAGE_COLL | O.STAGE_EVAL
+    want = O.torm_cost_grad(traj, targets, osc, op, Aband, mask)
+    tb = TM.TormBatch(targets, TM.TormParameters(min_clearence_=0.3), gsc, cuda_device, torch.float32)
+    got = tb.cost_grad(torch.tensor(traj, dtype=torch.float32, device=cuda_device), mask, want_active=True)
+    torch.cuda.synchronize()
+    costs = got["costs"].double().cpu().numpy()
+    for k in (0, 1, 2, 3, 4, 5, 6, 8, 9):
+        assert np.abs(costs[:, k] - want["costs"][:, k]).max() <= 1e-4 * np.abs(want["costs"][:, k]).max() + 1e-12, k
+    assert np.array_equal(costs[:, 7], want["costs"][:, 7])
+    assert abs(float(got["active"].mean()) - float(want["active"].mean())) < 1e-3
+    assert rel_rows(got["inc_smooth"].double().cpu().numpy(), want["inc_smooth"], 1e-9).max() < 2e-4
+    skip = voxel_boundary_rows(traj, origin, res)
+    assert skip.mean() < 0.04
+    rr = rel_rows(got["inc_coll"].double().cpu().numpy(), want["inc_coll"], 1e-6)[~skip]
+    assert np.median(rr) < 5e-6 and (rr > 1e-4).mean() < 0.01 and rr.max() < 1e-3, (np.median(rr), (rr > 1e-4).mean(), rr.max())
+    man = O.manipulability(traj[:, 1:].reshape(-1, 7)).reshape(N, T - 1)
+    rp = rel_rows(got["inc_pose"].double().cpu().numpy(), want["inc_pose"], 1e-6)
+    assert np.median(rp[man > 1e-2]) < 1e-5 and (rp[man > 1e-2] > 1e-3).mean() < 0.01
     gsc.close()
 
 
