@@ -247,6 +247,9 @@ typedef struct RlitgTormParams {
 #define RLITG_STAGE_KEEP_COSTS 32 /* leave the cost entries of the stages that are off untouched instead of zeroing them:
                                     lets two calls with disjoint stages share one costs buffer (the optimiser loop runs the
                                     end-pose / evaluator call next to the collision-point test + collision call) */
+#define RLITG_STAGE_COLL_ROW_ONLY 64 /* with stochastic_idx: compute the collision stage for that one waypoint only (chain
+                                    walks of its seven stencil rows, potentials of one row); costs[5] is then 0.  What the optimiser
+                                    loop needs with use_stochastic_descent_: getCollisionCost is not part of localOptimizeTSGD */
 #define RLITG_TORM_NCOST 10
 /* costs [N,10]: 0 eval position, 1 eval rotation, 2 velocity, 3 acceleration, 4 jerk (traj_evaluator means),
  *   5 collision cost (mean over the T rows of the summed sphere potentials), 6 weighted = [0] + 0.17 [1]

@@ -9,6 +9,8 @@
 //
 // HBM-bound in principle (536 B/env at the trained setting), launch/latency-bound at 16k envs.  Observation rows
 // are staged in shared memory (odd row stride -> conflict-free) and written back coalesced.
+#include <cstdlib>
+
 #include "fetch_chain.cuh"
 #include "linalg.cuh"
 #include "rlitg_internal.h"
@@ -369,12 +371,320 @@ __global__ void __launch_bounds__(kEnvTile, sizeof(T) == 4 ? 4 : 1) pirl_env_ker
     }
 }
 
+// ---- kernel 2b: the same step with EIGHT LANES PER ENVIRONMENT, for small batches ----------------------------------
+// Below one wave the thread-per-env kernel's time is the serial instruction chain of one thread (~2,200 instructions
+// per warp at ~7 cycles each with one warp per scheduler: profiles/r02_pirl_16k_thread_full.json).  Here the chain is
+// cut (to ~1,370 instructions per warp) by data-parallel splits inside a group of 8 lanes (4 environments per warp,
+// group shuffles only):
+//   sin / cos        lane j = joint j
+//   chain walk       lane r = coordinate r: every row of [c0 c1 c2 | p] evolves independently under right-multiplication
+//                    by the joint transforms (3 lanes busy, ~45 dependent FMAs instead of ~230); link frames go to a
+//                    per-environment shared-memory scratch that every lane reads afterwards
+//   collision test   sphere s on lane s mod 8
+//   observation      link k on lane k (9 values each), staged in shared memory, written back 8 floats per store
+//   Jacobian / QR    column j on lane j; the dot products of the modified Gram-Schmidt sweep and of the null-space
+//                    projection are 3-step group reductions
+// The scalar parts (task reward, flags) are executed redundantly by all lanes: free in latency, but 5 x the total work of
+// the thread-per-env kernel -- which is why this kernel only wins while the GPU is nearly empty (launch_pirl).
+constexpr int kLaneEnvs = 16;  // environments per CTA: 128 threads
+
+template <typename T>
+RLITG_DEV T group_sum(T x, unsigned gmask) {
+    x += __shfl_xor_sync(gmask, x, 1);
+    x += __shfl_xor_sync(gmask, x, 2);
+    x += __shfl_xor_sync(gmask, x, 4);
+    return x;
+}
+
+// FK of one environment by its lane group: qv = joint value of lane l (< 7); frames fr[k][12] = (p, c0, c1, c2) of link k
+template <typename T>
+RLITG_DEV void group_fk(T qv, int l, unsigned gmask, T* __restrict__ sc, T* __restrict__ fr) {
+    if (l < 7) {
+        T sn, cs;
+        sincos_joint(qv, sn, cs);
+        sc[2 * l] = sn;
+        sc[2 * l + 1] = cs;
+    }
+    __syncwarp(gmask);
+    if (l < 3) {
+        const int r = l;
+        T e0 = r == 0 ? T(1) : T(0), e1 = r == 1 ? T(1) : T(0), e2 = r == 2 ? T(1) : T(0), pp = T(0);
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            pp = fma_t(arm_ox<T>(j), e0, pp);
+            if (arm_oz<T>(j) != T(0)) pp = fma_t(arm_oz<T>(j), e2, pp);
+            const T sn = sc[2 * j], cs = sc[2 * j + 1];
+            if (arm_axis(j) == AX_Z) { const T a = e0, b = e1; e0 = cs * a + sn * b; e1 = cs * b - sn * a; }
+            else if (arm_axis(j) == AX_Y) { const T a = e0, b = e2; e0 = cs * a - sn * b; e2 = sn * a + cs * b; }
+            else { const T a = e1, b = e2; e1 = cs * a + sn * b; e2 = cs * b - sn * a; }
+            T* f = fr + j * 12;
+            f[r] = pp; f[3 + r] = e0; f[6 + r] = e1; f[9 + r] = e2;
+        }
+        pp = fma_t(tip_ox<T>(), e0, pp);
+        T* f = fr + 7 * 12;
+        f[r] = pp; f[3 + r] = e0; f[6 + r] = e1; f[9 + r] = e2;
+    }
+    __syncwarp(gmask);
+}
+
+template <typename T, bool kStep>
+__global__ void __launch_bounds__(kLaneEnvs * 8) pirl_env_lanes_kernel(
+    PirlCfgT<T> cfg, int64_t B, T* __restrict__ q, const float* __restrict__ action, int32_t* __restrict__ timestep,
+    const int32_t* __restrict__ max_timestep, const T* __restrict__ targets, const T* __restrict__ demos, int Tmax,
+    const T* __restrict__ latent, SceneDev sc, int has_scene, T ox, T oy, T oz, T* __restrict__ obs,
+    T* __restrict__ reward, uint8_t* __restrict__ done, uint8_t* __restrict__ flags, int32_t* __restrict__ counters,
+    T* __restrict__ errs) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int O = cfg.O;
+    T* s_fr = reinterpret_cast<T*>(smem_raw);        // [kLaneEnvs][8][12] link frames
+    T* s_sc = s_fr + kLaneEnvs * 96;                 // [kLaneEnvs][14] sin, cos
+    T* s_obs = s_sc + kLaneEnvs * 14;                // [kLaneEnvs][O] observation rows
+    __shared__ float4 s_sph[kMaxSpheres];
+    __shared__ int s_link[kMaxSpheres];
+    if (has_scene) {
+        for (int i = threadIdx.x; i < sc.S; i += blockDim.x) {
+            s_sph[i] = sc.spheres[i];
+            int link = 0;
+            while (link < kNumLinks - 1 && i >= sc.link_start[link + 1]) link++;
+            s_link[i] = link;
+        }
+        __syncthreads();
+    }
+    const int g = threadIdx.x >> 3, l = threadIdx.x & 7;
+    const unsigned gmask = 0xffu << (8 * ((threadIdx.x & 31) >> 3));
+    const int64_t b = (int64_t)blockIdx.x * kLaneEnvs + g;
+    if (b >= B) return;  // whole groups leave together; there is no CTA-wide barrier below
+    T* fr = s_fr + g * 96;
+    T* scv = s_sc + g * 14;
+    T* row = s_obs + (size_t)g * O;
+    const int RS = cfg.RS;
+    const T* tg = targets + (int64_t)b * Tmax * RS;
+    const int ot = cfg.obs_type;
+
+    T cur = l < 7 ? q[b * 7 + l] : T(0);
+    int ts = timestep[b];
+    const int mts = max_timestep[b];
+    bool collision_flag = false, joint_limit_flag = false;
+    T tp[7], dm[7];
+    int cnt = 0;
+    if constexpr (kStep) {
+        ts += 1;
+        const int tsp = min(max(ts, 0), Tmax - 1);
+        load_row7(tg + (size_t)tsp * RS, RS, tp);  // every lane holds the whole row (one broadcast transaction per load)
+        if (demos != nullptr) load_row7(demos + ((int64_t)b * Tmax + tsp) * RS, RS, dm);
+        if (counters && l < 4) cnt = counters[b * 4 + l];
+        // _set_action :184-207, joint l on lane l
+        T o2 = cur + (l < 7 ? T(action[b * 7 + l]) : T(0));
+        const int j = l < 7 ? l : 0;
+        if (l < 7 && cfg.cj[j]) {
+            const T pi = T(3.14159265358979323846);
+            if (o2 > pi) o2 -= T(2) * pi;
+            else if (o2 < -pi) o2 += T(2) * pi;
+        }
+        const T lo = cfg.ll[j], hi = cfg.ul[j];
+        const T c = l < 7 ? (o2 < lo ? lo : (o2 > hi ? hi : o2)) : T(0);
+        // np.allclose(o2, clip(o2)): |a - b| <= 1e-8 + 1e-5 |b|
+        const bool ok = l >= 7 || (abs_t(o2 - c) <= T(1e-8) + T(1e-5) * abs_t(c));
+        const bool no_out = (__ballot_sync(gmask, ok) & gmask) == gmask;
+        if (cfg.train_mode) {
+            if (no_out) {
+                group_fk<T>(c, l, gmask, scv, fr);
+                bool hit = false;
+                if (has_scene) {
+                    const GridMap<T> gm(sc);
+                    for (int s = l; s < sc.S; s += 8) {
+                        const float4 cc = s_sph[s];
+                        const T* f = fr + s_link[s] * 12;
+                        const V3<T> x = {ox + f[0] + f[3] * T(cc.x) + f[6] * T(cc.y) + f[9] * T(cc.z),
+                                         oy + f[1] + f[4] * T(cc.x) + f[7] * T(cc.y) + f[10] * T(cc.z),
+                                         oz + f[2] + f[5] * T(cc.x) + f[8] * T(cc.y) + f[11] * T(cc.z)};
+                        if (sphere_hits(sc, gm, x, s, cc.w, sc.dil)) hit = true;
+                    }
+                }
+                if (__ballot_sync(gmask, hit) & gmask) {
+                    collision_flag = true;
+                    __syncwarp(gmask);
+                    group_fk<T>(cur, l, gmask, scv, fr);  // the move is rejected: pose of the unchanged configuration
+                } else {
+                    cur = c;
+                }
+            } else {
+                joint_limit_flag = true;
+                group_fk<T>(cur, l, gmask, scv, fr);
+            }
+        } else {
+            cur = c;
+            group_fk<T>(cur, l, gmask, scv, fr);
+        }
+        if (l < 7) q[b * 7 + l] = cur;
+        if (l == 0) timestep[b] = ts;
+    } else {
+        group_fk<T>(cur, l, gmask, scv, fr);
+    }
+    const T* ee = fr + 7 * 12;  // p, c0, c1, c2 of gripper_link
+
+    // ---- _get_obs :292-320, staged in shared memory
+    if (ot != 3 && l < 7) row[l] = cur;
+    {
+        const int link_off = (ot == 1) ? 7 : (ot == 3 ? 0 : -1);
+        if (link_off >= 0) {  // calc_pos_and_rot :322-333: p, R[:,0], R[:,1] of link l
+#pragma unroll
+            for (int k = 0; k < 9; k++) row[link_off + 9 * l + k] = fr[l * 12 + k];
+        } else if (ot == 2 && l == 7) {
+#pragma unroll
+            for (int k = 0; k < 9; k++) row[7 + k] = ee[k];
+        }
+    }
+    int fo = (ot == 0) ? 7 : (ot == 1 ? 79 : (ot == 2 ? 16 : 72));
+    for (int i = l; i < cfg.n_future; i += 8) {  // future target i on lane i mod 8
+        int t = ts + (i + 1);
+        if (t > mts) t = mts;
+        t = min(max(t, 0), Tmax - 1);  // memory-safety guard: a caller stepping a finished episode stays in its path
+        T t7[7];
+        load_row7(tg + (size_t)t * RS, RS, t7);
+        // calc_pos_and_rot_error :335-349: R_ct = tM inv(eM); columns 0 and 1
+        V3<T> m0, m1, m2;
+        npq_rot(t7, m0, m1, m2);
+        T* o = row + fo + 9 * i;
+        o[0] = t7[0] - ee[0]; o[1] = t7[1] - ee[1]; o[2] = t7[2] - ee[2];
+        // inv(eM) = eM^T: column c of R_ct = tM * (row c of eM); row 0 of eM = (c0.x, c1.x, c2.x)
+        const V3<T> r0 = {ee[3], ee[6], ee[9]}, r1 = {ee[4], ee[7], ee[10]};
+        o[3] = m0.x * r0.x + m1.x * r0.y + m2.x * r0.z;
+        o[4] = m0.y * r0.x + m1.y * r0.y + m2.y * r0.z;
+        o[5] = m0.z * r0.x + m1.z * r0.y + m2.z * r0.z;
+        o[6] = m0.x * r1.x + m1.x * r1.y + m2.x * r1.z;
+        o[7] = m0.y * r1.x + m1.y * r1.y + m2.y * r1.z;
+        o[8] = m0.z * r1.x + m1.z * r1.y + m2.z * r1.z;
+    }
+    fo += 9 * cfg.n_future;
+    for (int k = l; k < cfg.z_dim; k += 8) row[fo + k] = latent[b * cfg.z_dim + k];
+    __syncwarp(gmask);
+    for (int k = l; k < O; k += 8) st_stream(obs + b * O + k, row[k]);
+
+    if constexpr (kStep) {
+        // ---- _compute_task_reward :495-513, redundantly on every lane
+        const T dx = tp[0] - ee[0], dy = tp[1] - ee[1], dz = tp[2] - ee[2];
+        const T d_err = sqrt_t(dx * dx + dy * dy + dz * dz);
+        T ex, ey, ez, ew;
+        rot_to_quat_kdl(V3<T>{ee[3], ee[4], ee[5]}, V3<T>{ee[6], ee[7], ee[8]}, V3<T>{ee[9], ee[10], ee[11]}, ex, ey, ez, ew);
+        const T dw = tp[6] * ew + tp[3] * ex + tp[4] * ey + tp[5] * ez;
+        const T adw = abs_t(dw);
+        const T r_err = (adw > T(1)) ? T(0) : T(2) * acos_t(adw);
+        const T dist_rwd = calc_reward(d_err, cfg.dist_p);
+        const T rot_rwd = calc_reward(r_err, cfg.rot_p);
+
+        // ---- imitation :515-526 and null-space imitation :528-539, joint l on lane l
+        T imitate_rwd = T(0), imitate_err = T(0), null_rwd = T(0), null_obj = T(0);
+        if (demos != nullptr) {
+            T e = T(0);
+            if (l < 7) {
+                T dv = dm[0];
+#pragma unroll
+                for (int k = 1; k < 7; k++) dv = (l == k) ? dm[k] : dv;
+                e = dv - cur;
+                if (cfg.cj[l]) {
+                    const T pi = T(3.14159265358979323846);
+                    if (e > pi) e -= T(2) * pi;
+                    else if (e < -pi) e += T(2) * pi;
+                }
+            }
+            const T l1 = group_sum(abs_t(e), gmask);
+            if (!cfg.refine_flag) {
+                imitate_err = l1 / T(7);
+                imitate_rwd = calc_reward(imitate_err, cfg.imit_p);
+            }
+            if ((cfg.null_flag && !cfg.refine_flag) || errs != nullptr) {
+                // column l of the Jacobian (KDL JntToJac): [z x (p_ee - o); z]; lane 7 carries a zero column
+                T Q[6];
+#pragma unroll
+                for (int k = 0; k < 6; k++) Q[k] = T(0);
+                if (l < 7) {
+                    const int ci = (l == 0) ? 2 : ((l & 1) ? 1 : 0);  // axis z, y, x, y, x, y, x -> rotation column
+                    const T* f = fr + l * 12;
+                    const V3<T> z = {f[3 + 3 * ci], f[4 + 3 * ci], f[5 + 3 * ci]};
+                    const V3<T> dlt = {ee[0] - f[0], ee[1] - f[1], ee[2] - f[2]};
+                    const V3<T> lin = cross(z, dlt);
+                    Q[0] = lin.x; Q[1] = lin.y; Q[2] = lin.z; Q[3] = z.x; Q[4] = z.y; Q[5] = z.z;
+                }
+                // modified Gram-Schmidt over the six rows of J (this lane holds one column), then e - Q^T Q e
+#pragma unroll
+                for (int k = 0; k < 6; k++) {
+                    const T n2 = group_sum(Q[k] * Q[k], gmask);
+                    const T rn = sqrt_t(n2);
+                    Q[k] *= T(1) / (rn > T(1e-30) ? rn : T(1e-30));
+#pragma unroll
+                    for (int jj = k + 1; jj < 6; jj++) {
+                        const T d = group_sum(Q[k] * Q[jj], gmask);
+                        Q[jj] -= d * Q[k];
+                    }
+                }
+                T r = e;
+#pragma unroll
+                for (int k = 0; k < 6; k++) {
+                    const T c = group_sum(Q[k] * r, gmask);
+                    r -= c * Q[k];
+                }
+                null_obj = sqrt_t(group_sum(r * r, gmask));
+                null_rwd = calc_reward(null_obj, cfg.null_p);
+            }
+        }
+
+        const int is_time_out = (ts == mts);
+        const int is_col = collision_flag, is_jl = joint_limit_flag;
+        const int is_es = d_err > cfg.thr_early;
+        const int is_ds = d_err < cfg.thr_dist;
+        const int is_rs = r_err < cfg.thr_rot;
+        const int is_is = (!cfg.refine_flag) ? (imitate_err < cfg.thr_imit) : 0;
+        T rw = -cfg.w_col * T(is_col) - cfg.w_jl * T(is_jl) - cfg.w_es * T(is_es);
+        if (cfg.task_flag) {
+            const bool near_t = d_err < cfg.zero_task;
+            rw += (dist_rwd + cfg.dist_suc_r * T(is_ds) + (near_t ? rot_rwd : T(0)) +
+                   (near_t ? cfg.rot_suc_r * T(is_rs) : T(0)) + cfg.task_suc_r * T(is_ds * is_rs));
+        }
+        if (cfg.imit_flag && !cfg.refine_flag) rw += (imitate_rwd + cfg.imit_suc_r * T(is_is));
+        if (cfg.null_flag && !cfg.refine_flag) rw += null_rwd;
+        if (l == 0) {
+            reward[b] = rw;
+            done[b] = (uint8_t)(is_col || is_es || is_time_out);
+            const uint32_t lo32 = (uint32_t)is_col | ((uint32_t)is_jl << 8) | ((uint32_t)is_es << 16) | ((uint32_t)is_time_out << 24);
+            const uint32_t hi32 = (uint32_t)is_ds | ((uint32_t)is_rs << 8) | ((uint32_t)is_is << 16) | ((uint32_t)(is_ds * is_rs) << 24);
+            *reinterpret_cast<uint2*>(flags + b * 8) = make_uint2(lo32, hi32);
+            if (errs) {
+                errs[b * 4 + 0] = d_err; errs[b * 4 + 1] = r_err; errs[b * 4 + 2] = imitate_err; errs[b * 4 + 3] = null_obj;
+            }
+        }
+        if (counters && l < 4) {
+            const int add = l == 0 ? is_ds * is_rs : (l == 1 ? is_ds : (l == 2 ? is_rs : (cfg.refine_flag ? 0 : is_is)));
+            counters[b * 4 + l] = cnt + add;
+        }
+    }
+}
+
 template <typename T, bool kStep>
 static int launch_pirl(const RlitgPirlCfg* cfg, int64_t B, T* q, const float* action, int32_t* timestep,
                        const int32_t* max_timestep, const T* targets, const T* demos, int Tmax, const T* latent,
                        const Scene* scene, const double* base_off, T* obs, T* reward, uint8_t* done, uint8_t* flags,
                        int32_t* counters, T* errs, cudaStream_t st) {
     PirlCfgT<T> c = convert_cfg<T>(*cfg);
+    // small batches (down to the reference's own mode of use, one environment): eight lanes per environment (kernel 2b).
+    // Measured as 50 steps per CUDA graph (profiles/README.md): 5.9 vs 6.4 us at 1,024 envs, equal at 4,096, and
+    // SLOWER from there on (10.6 vs 6.6 us at 16,384: 8 x the threads with redundant scalar work, 5.6 M warp
+    // instructions against 1.1 M) -- so the switch point sits at 2,048; RLITG_PIRL_LANES_MAX moves it
+    static const int64_t lanes_max = [] { const char* e = getenv("RLITG_PIRL_LANES_MAX"); return e ? atoll(e) : 2048ll; }();
+    if (B <= lanes_max && c.O <= 1024) {
+        auto kl = pirl_env_lanes_kernel<T, kStep>;
+        const size_t sm = sizeof(T) * kLaneEnvs * (size_t)(96 + 14 + c.O);
+        int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kl), sm, "pirl_env_lanes_kernel");
+        if (rc_attr) return rc_attr;
+        SceneDev sdl{};
+        int hs = 0;
+        double offl[3] = {0, 0, 0};
+        if (scene) { sdl = scene_dev(scene); hs = 1; offl[0] = base_off[0]; offl[1] = base_off[1]; offl[2] = base_off[2]; }
+        const unsigned gl = (unsigned)((B + kLaneEnvs - 1) / kLaneEnvs);
+        kl<<<gl, kLaneEnvs * 8, sm, st>>>(c, B, q, action, timestep, max_timestep, targets, demos, Tmax, latent, sdl, hs,
+                                          (T)offl[0], (T)offl[1], (T)offl[2], obs, reward, done, flags, counters, errs);
+        return check_launch("pirl_env_lanes_kernel");
+    }
     const size_t smem = sizeof(T) * kEnvTile * (size_t)(c.O | 1);
     if (smem > 200 * 1024) return set_error(RLITG_ERR_SHAPE, "observation too long for the shared-memory tile");
     auto kern = pirl_env_kernel<T, kStep>;

@@ -233,6 +233,9 @@ torm_coll_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S, con
     T* o_smooth = inc_smooth ? inc_smooth + n * (int64_t)F * 7 : nullptr;
     T* o_coll = inc_coll ? inc_coll + n * (int64_t)F * 7 : nullptr;
     const int stoch_row = stoch ? stoch[n] + 1 : -1;  // full-trajectory row of the single stochastic waypoint
+    // RLITG_STAGE_COLL_ROW_ONLY: only that waypoint's increment is wanted (the optimiser loop with use_stochastic_descent_:
+    // getCollisionCost is not part of localOptimizeTSGD) -> chain walks for rows stoch_row - 3 .. + 3, potentials of one row
+    const bool row_only = stoch != nullptr && (stage_mask & RLITG_STAGE_COLL_ROW_ONLY) != 0;
     const GridMap<T> gm(sc);
     T red[2] = {T(0), T(0)};  // potential sum, active sphere count
 
@@ -267,19 +270,24 @@ torm_coll_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S, con
         CollVisit<T, FT, true> v;
         v.sph = s_sph; v.link_start = s_start; v.quirk = P.quirk;
         v.off = {FT(P.off64[0]), FT(P.off64[1]), FT(P.off64[2])};
-        if (valid) {
+        if (valid && (!row_only || abs(i - stoch_row) <= 3)) {
             v.pos_row = PROW(i);
             walk_chain<FT, 7, kFk64>(TROW(i), v);
         }
         if (tid < 6) {
             const int hr = tid < 3 ? c0 - 3 + tid : c0 + CH + (tid - 3);
-            if (hr >= 0 && hr < Tn && (hr < c0 || hr >= c0 + CH))
+            if (hr >= 0 && hr < Tn && (hr < c0 || hr >= c0 + CH) && (!row_only || abs(hr - stoch_row) <= 3))
                 halo_sphere_row<T, FT, kFk64>(TROW(hr), PROW(hr), s_sph, s_start, v.off.x, v.off.y, v.off.z, P.quirk);
         }
         __syncthreads();
 
         // ---- phase 2: potentials and cost over all spheres, then the CHOMP increments of this row's active spheres
-        if (valid) {
+        if (valid && row_only && i != stoch_row) {
+            if (i >= 1 && o_coll) {  // rows that take no increment are zero (:1495)
+#pragma unroll
+                for (int j = 0; j < 7; j++) o_coll[(i - 1) * 7 + j] = T(0);
+            }
+        } else if (valid) {
             const T* prow = PROW(i);
             const bool inc_row = (i >= 1) && (stoch_row < 0 || stoch_row == i) && (o_coll != nullptr);
             T acc[7];
@@ -329,7 +337,7 @@ torm_coll_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S, con
     block_reduce<T, 2>(red, s_red, tot);
     if (tid == 0) {
         T* c = costs + n * RLITG_TORM_NCOST;
-        c[5] = do_coll ? tot[0] / T(Tn) : T(0);  // getCollisionCost :1448-1463: mean over the T real rows
+        c[5] = (do_coll && !row_only) ? tot[0] / T(Tn) : T(0);  // getCollisionCost :1448-1463: mean over the T real rows
         if (zero_pose_costs) {
             c[0] = c[1] = c[2] = c[3] = c[4] = T(0);
             c[6] = c[7] = c[8] = c[9] = T(0);

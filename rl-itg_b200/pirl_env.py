@@ -80,6 +80,13 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+try:  # the raw handle of the current stream without building a torch.cuda.Stream object (hot path of PirlVecEnv.step)
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+except AttributeError:  # pragma: no cover
+    def _raw_stream(index):
+        return torch.cuda.current_stream(index).cuda_stream
+
+
 def nullspace_norm(err, q):
     """jaco_srv(err, q).objective_value for a batch (pirl/src/kinematic_solver.cpp:332-351)."""
     err, q = err.contiguous(), q.contiguous()
@@ -137,6 +144,7 @@ class PirlVecEnv:
                  refineFlag=False, scene=None, device="cuda:0", dtype=torch.float32, want_errs=False):
         self.B = int(num_envs)
         self.device = torch.device(device)
+        self._dev_index = self.device.index if self.device.index is not None else 0
         self.dtype = dtype
         self.scene = scene
         self.mode = "train"
@@ -240,12 +248,18 @@ class PirlVecEnv:
         Returns obs [B,O], reward [B], done [B] (uint8), info dict of tensors (keys of PirlEnv.py:273-282).
         The returned tensors are the env's own buffers (overwritten by the next step)."""
         a = action
-        if not (torch.is_tensor(a) and a.dtype == torch.float32 and a.is_cuda and a.is_contiguous()):
+        if not (type(a) is torch.Tensor and a.dtype == torch.float32 and a.is_cuda and a.is_contiguous()):
             a = torch.as_tensor(action, device=self.device).to(torch.float32).contiguous()
         if self._pre is None:
             self._bind()
-        with _lib.on_device(self.device):
-            rc = lib.rlitg_pirl_env_step(*self._pre, a.data_ptr(), *self._post, _stream())
+        # at 16k envs the kernel takes ~5 us: the launch path is kept short (the argument tuples are bound once; no
+        # stream / device objects are built when this env's device is already current)
+        idx = self._dev_index
+        if torch.cuda.current_device() == idx:
+            rc = lib.rlitg_pirl_env_step(*self._pre, a.data_ptr(), *self._post, _raw_stream(idx))
+        else:
+            with torch.cuda.device(idx):
+                rc = lib.rlitg_pirl_env_step(*self._pre, a.data_ptr(), *self._post, _raw_stream(idx))
         if rc:
             check(rc)
         return self.obs, self.reward, self.done, self._info

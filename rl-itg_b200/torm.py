@@ -20,6 +20,7 @@ from . import _lib, fetch
 from ._lib import check, lib
 
 STAGE_POSE, STAGE_POSE_GRAD, STAGE_SMOOTH, STAGE_COLL, STAGE_EVAL = 1, 2, 4, 8, 16
+STAGE_KEEP_COSTS, STAGE_COLL_ROW_ONLY = 32, 64
 NCOST = 10
 COST_NAMES = ("pose", "rot", "vel", "acc", "jerk", "collision", "weighted", "n_vel_violation", "endpose_pos_sum",
               "endpose_rot_sum")
@@ -346,7 +347,7 @@ TormBatch.applyIncrements = _apply_increments
 
 
 def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, check_collision=True, lr_schedule_mode=3,
-                         return_state=False, use_cuda_graph=None, stochastic=None, seed=0, rand=None, state=None):
+                         return_state=False, use_cuda_graph=None, stochastic=None, seed=0, rand=None, state=None, overlap=True):
     """Lock-step two-stage gradient descent over the N trajectories of `traj` (in place): the loop body of
     TormOptimizer::localOptimizeTSGD (torm/src/torm_optimizer.cpp:397-598) entirely on the device -- cost +
     increments (kernels 3a / 3b), feasibility checks, the alpha_ / learning_rate_ schedule, the best-trajectory
@@ -368,7 +369,7 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
     state: dict(alpha=[N], learning_rate=[N]) carried over from a previous call -- alpha_ / learning_rate_ are members of
     the reference's optimiser and persist across localOptimizeTSGD calls (infea_col / infea_vel are locals, :383).
     There is no host synchronisation inside an iteration, so one iteration can also be captured in a CUDA graph and
-    replayed (use_cuda_graph=True; identical results).
+    replayed (use_cuda_graph=True; identical results).  overlap=False keeps every launch on one stream (measurement).
     Returns (best_traj [N,T,7], best_cost [N]); best_cost stays +inf for trajectories never found feasible.
     return_state=True appends a dict with the final alpha / lr / feasibility tensors and the draws."""
     pr = self.parameters
@@ -425,7 +426,7 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
     # They run on two streams and share one costs buffer (RLITG_STAGE_KEEP_COSTS).
     side = torch.cuda.Stream(device=dev)
     ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
-    KEEP = 32
+    KEEP = STAGE_KEEP_COSTS
 
     def sub_step(stage):
         cur_stream = torch.cuda.current_stream(dev)
@@ -443,7 +444,7 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
         else:
             ts = None
             pose_mask, coll_mask = STAGE_POSE_GRAD | STAGE_EVAL, 0
-        two = bool(coll_mask or need_point)
+        two = bool(overlap and (coll_mask or need_point))
         if two:
             ev_fork.record(cur_stream)
             side.wait_event(ev_fork)
@@ -451,7 +452,7 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
                 r = self.cost_grad(traj, pose_mask | (KEEP if coll_mask else 0), traj_stage=ts)
                 ev_join.record(side)
         else:
-            r = self.cost_grad(traj, pose_mask, traj_stage=ts)
+            r = self.cost_grad(traj, pose_mask | (KEEP if coll_mask else 0), traj_stage=ts)
         if need_point:
             with _lib.on_device(dev):
                 check(lib.rlitg_torm_collision_point(traj.data_ptr(), N, self.T, code, self.scene.handle, base_off,
@@ -460,8 +461,10 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
                                                      cur_stream.cuda_stream))
         rc = None
         if coll_mask:
-            rc = self.cost_grad(traj, coll_mask | KEEP, stochastic_idx=stoch_idx if (stochastic and (coll_mask & STAGE_COLL)) else None,
-                                traj_stage=ts)
+            use_st = bool(stochastic and (coll_mask & STAGE_COLL))
+            # one waypoint per trajectory takes the collision increment: only its seven stencil rows are walked
+            rc = self.cost_grad(traj, coll_mask | KEEP | (STAGE_COLL_ROW_ONLY if use_st else 0),
+                                stochastic_idx=stoch_idx if use_st else None, traj_stage=ts)
         if two:
             cur_stream.wait_event(ev_join)
         if singular is not None:

@@ -163,7 +163,16 @@ def test_stochastic_index_and_stage_masks(cuda_device, dtype):
     got = tb.calculateCollisionIncrements(tt, st).double().cpu().numpy()
     nz = np.abs(want["inc_coll"]).max(axis=-1) > 0
     assert (nz.sum(axis=1) <= 1).all() and nz.any()  # one waypoint per trajectory contributes
-    assert rel_rows(got, want["inc_coll"], 1e-6).max() < (1e-8 if dtype == "float64" else 5e-3)
+    assert rel_rows(got, want["inc_coll"], 1e-6).max() < (1e-8 if dtype == "float64" else 1e-3)
+    # RLITG_STAGE_COLL_ROW_ONLY (what localOptimizeTSGD asks for): the same increments from seven chain walks per trajectory
+    # instead of T; index -1 (collision_point_ = the start row) takes no increment in either form
+    st2 = st.copy(); st2[0] = -1; st2[1] = 0; st2[2] = T - 2
+    full = tb.cost_grad(tt, TM.STAGE_COLL | TM.STAGE_SMOOTH, st2)
+    inc_full, sm_full = full["inc_coll"].clone(), full["inc_smooth"].clone()
+    ro = tb.cost_grad(tt, TM.STAGE_COLL | TM.STAGE_SMOOTH | TM.STAGE_COLL_ROW_ONLY, st2)
+    assert torch.equal(ro["inc_coll"], inc_full) and torch.equal(ro["inc_smooth"], sm_full)
+    assert float(inc_full[0].abs().max()) == 0.0 and float(inc_full[1, 1:].abs().max()) == 0.0
+    assert float(ro["costs"][:, 5].abs().max()) == 0.0
     # facade members agree with the fused call
     c = tb.getEndPoseCost(tt).double().cpu().numpy()
     w = O.torm_cost_grad(traj, targets, None, op, None, O.STAGE_POSE)["costs"]

@@ -70,6 +70,14 @@ def main():
         act = env.random_action() * 0.1
         ms = timeit(lambda: env.step(act), a.iters)
         print("pirl_env_step B=%d: %.2f us  %.1f GB/s  %.2f G env-steps/s" % (B, ms * 1e3, 536 * B / ms / 1e6, B / ms / 1e6))
+        # the kernel without the Python launch path: 50 steps captured in one CUDA graph
+        env.step(act); torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(50):
+                env.step(act)
+        msg = timeit(g.replay, max(a.iters // 5, 3)) / 50
+        print("pirl_env_step B=%d (50 steps per graph): %.2f us per step  %.1f GB/s" % (B, msg * 1e3, 536 * B / msg / 1e6))
     if a.which in ("torm", "all"):
         N, T = a.N, a.T
         traj = torch.tensor(synth.linear_trajectories(N, T, seed=100, noise=0.05), dtype=torch.float32, device=dev)

@@ -64,17 +64,29 @@ def main():
     print("cost end-pose   (graph replay, GPU only) %.1f us" % graphed(lambda: tb.cost_grad(tw, pose)))
     print("copy only       %.1f us" % (1e3 * ev_time(lambda: tw.copy_(traj))))
     print("collide N*T     %.1f us" % (1e3 * ev_time(lambda: sc.collide(tw.reshape(-1, 7)))))
+    import ctypes as C
+    from rlitg_b200 import _lib
+    any_hit = torch.zeros(N, dtype=torch.uint8, device=dev); st_idx = torch.zeros(N, dtype=torch.int32, device=dev)
+    u = torch.rand(N, device=dev)
+    off = (C.c_double * 3)(*tb.parameters.base_offset)
+    cp = lambda: _lib.check(_lib.lib.rlitg_torm_collision_point(tw.data_ptr(), N, T, 0, sc.handle, off, u.data_ptr(), None,
+                                                                any_hit.data_ptr(), st_idx.data_ptr(),
+                                                                torch.cuda.current_stream().cuda_stream))
+    print("collision point (graph replay, GPU only) %.1f us" % graphed(cp))
+    print("cost feasible stochastic (graph)          %.1f us" % graphed(lambda: tb.cost_grad(tw, feas, stochastic_idx=st_idx)))
     for mode in (3, 1):
-        for use_graph in (False, True):
-            tw.copy_(traj)
-            tb.localOptimizeTSGD(tw, 2, lr_schedule_mode=mode, use_cuda_graph=False)
-            for iters in (20, 100):
-                tw.copy_(traj)
-                torch.cuda.synchronize(); t0 = time.perf_counter()
-                tb.localOptimizeTSGD(tw, iters, lr_schedule_mode=mode, use_cuda_graph=use_graph)
-                torch.cuda.synchronize()
-                print("localOptimizeTSGD mode %d graph=%d, %3d iterations: %.3f ms per iteration (wall)" %
-                      (mode, use_graph, iters, (time.perf_counter() - t0) * 1e3 / iters))
+        for stoch in (True, False):
+            for use_graph in (False, True):
+                for overlap in (True, False):
+                    tw.copy_(traj)
+                    tb.localOptimizeTSGD(tw, 3, lr_schedule_mode=mode, use_cuda_graph=use_graph, stochastic=stoch, overlap=overlap)
+                    iters = 60
+                    tw.copy_(traj)
+                    torch.cuda.synchronize(); t0 = time.perf_counter()
+                    tb.localOptimizeTSGD(tw, iters, lr_schedule_mode=mode, use_cuda_graph=use_graph, stochastic=stoch, overlap=overlap)
+                    torch.cuda.synchronize()
+                    print("localOptimizeTSGD mode %d stochastic=%d graph=%d overlap=%d: %.3f ms per iteration (wall, %d iterations)" %
+                          (mode, stoch, use_graph, overlap, (time.perf_counter() - t0) * 1e3 / iters, iters))
 
 
 if __name__ == "__main__":
