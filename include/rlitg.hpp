@@ -26,6 +26,7 @@
 #include <stdexcept>
 #include <string>
 #include <utility>
+#include <random>
 #include <vector>
 
 #include "rlitg.h"
@@ -283,6 +284,7 @@ struct TormParameters {
     double rotation_scale_factor_ = 0.17;
     double smoothness_cost_velocity_ = 1.0, smoothness_cost_acceleration_ = 0.0, smoothness_cost_jerk_ = 0.0;
     bool use_velocity_check_ = true, use_collision_check_ = true, use_pseudo_inverse_ = true;
+    bool use_stochastic_descent_ = true;  // true in every reference main
     double ridge_factor_ = 0.0;
     double pseudo_inverse_ridge_factor_ = 1e-4;
     double joint_update_limit_ = 0.17;
@@ -380,10 +382,12 @@ class TormBatchOptimizer {
     void setLearningRate(float lr) { lr_.upload(std::vector<float>((size_t)N_, lr)); }
 
     // TormOptimizer::localOptimizeTSGD (:397-598) in lock step over the N trajectories, entirely on the device: per
-    // half-iteration one cost call, the sphere-grid feasibility flags, rlitg_torm_bookkeep (stage choice of
-    // lr_schedule_mode_ 1, alpha_ / learning_rate_ schedule, best-trajectory record of :506-560) and the update step.
+    // half-iteration the collision-point test (isCurrentTrajectoryCollisionFree :695-717 + the waypoint choice of
+    // use_stochastic_descent_ :1502-1515, draws from a host mt19937 seeded with `seed`), one cost call,
+    // rlitg_torm_bookkeep (stage choice of lr_schedule_mode_ 1, alpha_ / learning_rate_ schedule, best-trajectory record
+    // of :506-560) and the update step.
     // Returns the best cost per trajectory (+inf if never feasible); getBestTrajectories() holds the rows.
-    std::vector<double> localOptimizeTSGD(int maxiter, int lr_schedule_mode = 3) {
+    std::vector<double> localOptimizeTSGD(int maxiter, int lr_schedule_mode = 3, unsigned seed = 0) {
         const float inf = std::numeric_limits<float>::infinity();
         best_cost_.upload(std::vector<float>((size_t)N_, inf));
         check(rlitg_copy_d2d(best_.data(), traj_.data(), traj_.size() * sizeof(float), nullptr));
@@ -394,6 +398,11 @@ class TormBatchOptimizer {
         stage_idx_.resize((size_t)N_);
         lr_iter_.resize(1);
         const bool check_col = scene_ && par_.use_collision_check_;
+        const bool stochastic = scene_ && par_.use_stochastic_descent_;
+        std::mt19937 rng(seed);
+        std::uniform_real_distribution<float> uni(0.0f, 1.0f);
+        std::vector<float> u_host((size_t)N_);
+        if (check_col || stochastic) { any_hit_.resize((size_t)N_); stoch_idx_.resize((size_t)N_); u_.resize((size_t)N_); }
         const double lr0 = par_.learning_rate_, lr_max = lr0 * 1000.0, lr_min = lr0 / 100.0;
         const int full = RLITG_STAGE_SMOOTH | RLITG_STAGE_POSE_GRAD | RLITG_STAGE_EVAL | (scene_ ? RLITG_STAGE_COLL : 0);
         for (int it = 0; it < maxiter; it++) {
@@ -409,20 +418,29 @@ class TormBatchOptimizer {
                 sch.lr_schedule_mode = lr_schedule_mode; sch.stage = stage;
                 sch.use_collision_check = check_col; sch.use_velocity_check = par_.use_velocity_check_;
                 sch.learning_rate = lr0; sch.learning_rate_min = lr_min; sch.learning_rate_max = lr_max;
+                sch.hits_per_trajectory = 1;
+                if (check_col || stochastic) {
+                    if (stochastic) {
+                        for (auto& v : u_host) v = uni(rng);
+                        u_.upload(u_host);
+                    }
+                    check(rlitg_torm_collision_point(traj_.data(), N_, T_, RLITG_F32, scene_->handle(), cp_.base_off,
+                                                     stochastic ? u_.data() : nullptr, nullptr, any_hit_.data(),
+                                                     stochastic ? stoch_idx_.data() : nullptr, nullptr));
+                }
+                const int32_t* st = stochastic ? stoch_idx_.data() : nullptr;
+                const int row_only = stochastic ? RLITG_STAGE_COLL_ROW_ONLY : 0;
                 if (lr_schedule_mode == 1) {  // every optimiser picks its stage; the cost kernels skip the other one's work
                     check(rlitg_torm_stage_decide(N_, RLITG_F32, lr_.data(), infea_col_.data(), infea_vel_.data(), &sch,
                                                   stage_idx_.data(), nullptr));
-                    run(full, nullptr, stage_idx_.data());
+                    run(full | row_only, st, stage_idx_.data());
                 } else if (stage == 0) {
-                    run(RLITG_STAGE_SMOOTH | RLITG_STAGE_EVAL | (scene_ ? RLITG_STAGE_COLL : 0));
+                    run(RLITG_STAGE_SMOOTH | RLITG_STAGE_EVAL | (scene_ ? (RLITG_STAGE_COLL | row_only) : 0), st);
                 } else {
                     run(RLITG_STAGE_POSE_GRAD | RLITG_STAGE_EVAL);
                 }
-                if (check_col)
-                    check(rlitg_sphere_grid_collide(traj_.data(), N_ * T_, RLITG_F32, scene_->handle(), cp_.base_off,
-                                                    hits_.data(), nullptr));
                 check(rlitg_torm_bookkeep(traj_.data(), best_.data(), N_, T_, RLITG_F32, costs_.data(),
-                                          check_col ? hits_.data() : nullptr, nullptr, alpha_.data(), lr_.data(),
+                                          check_col ? any_hit_.data() : nullptr, nullptr, alpha_.data(), lr_.data(),
                                           infea_col_.data(), infea_vel_.data(), best_cost_.data(), nullptr,
                                           lr_schedule_mode == 2 ? lr_iter_.data() : nullptr, &sch, nullptr));
                 update(stage, lr_schedule_mode, lr_schedule_mode == 1 ? stage_idx_.data() : nullptr);
@@ -481,8 +499,9 @@ class TormBatchOptimizer {
     DeviceArray<float> targets_, traj_, best_, smoothness_increments_, collision_increments_, endPose_increments_, costs_,
         alpha_, lr_;
     DeviceArray<float> best_cost_, lr_iter_;
-    DeviceArray<uint8_t> hits_, infea_col_, infea_vel_;
-    DeviceArray<int32_t> stage_idx_;
+    DeviceArray<uint8_t> hits_, infea_col_, infea_vel_, any_hit_;
+    DeviceArray<int32_t> stage_idx_, stoch_idx_;
+    DeviceArray<float> u_;
 };
 
 // ---- PIRL path-wise IK environment --------------------------------------------------------------------------

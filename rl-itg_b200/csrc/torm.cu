@@ -523,7 +523,34 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
             return set_cuda_error("torm fork");
         st_pose = fk->side;
     }
-    if (run_coll) {
+    // use_stochastic_descent_ inside the optimiser loop (RLITG_STAGE_COLL_ROW_ONLY): one waypoint per trajectory takes the
+    // collision increment -> kernel 3c (a warp per trajectory, spheres on lanes); the smoothness stage, if asked for, keeps
+    // the thread-per-waypoint kernel without its collision part
+    const bool row_only = (stage_mask & RLITG_STAGE_COLL) && (stage_mask & RLITG_STAGE_COLL_ROW_ONLY) && stoch && inc_coll;
+    int coll_kernel_mask = stage_mask;
+    if (row_only) {
+        static const int fk64r = [] { const char* e = getenv("RLITG_TORM_FK64"); return e ? atoi(e) : 1; }();
+        SceneDev sd = scene_dev(scene);
+        const int S = sd.S;
+        const size_t smem = sizeof(T) * kRowWarps * (size_t)(7 * ((3 * S) | 1) + 42);
+        using RowK = void (*)(TormP<T>, const T*, SceneDev, int, int, int64_t, const int32_t*, T*, T*, float*, const int32_t*);
+        RowK rk;
+        if constexpr (sizeof(T) == 4) rk = fk64r ? torm_coll_row_kernel<T, true> : torm_coll_row_kernel<T, false>;
+        else rk = torm_coll_row_kernel<T, false>;
+        int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(rk), smem, "torm_coll_row_kernel");
+        if (rc_attr) return rc_attr;
+        coll_kernel_mask = stage_mask & ~RLITG_STAGE_COLL;
+        const bool other_coll_kernel = (coll_kernel_mask & RLITG_STAGE_SMOOTH) != 0;
+        // who zeroes what: 1 = costs[5] only, 2 = the pose entries too; nothing when the smoothness launch below does it
+        const int zero = other_coll_kernel ? 0 : ((run_pose || (stage_mask & RLITG_STAGE_KEEP_COSTS)) ? 1 : 2);
+        rk<<<(unsigned)((N + kRowWarps - 1) / kRowWarps), kRowWarps * 32, smem, st>>>(P, traj, sd, S, zero, N, stoch, inc_coll,
+                                                                                   costs, active, traj_stage);
+        int rc = check_launch("torm_coll_row_kernel");
+        if (rc) return rc;
+    }
+    if (run_coll && (coll_kernel_mask & (RLITG_STAGE_COLL | RLITG_STAGE_SMOOTH))) {
+        const int stage_mask_pose = stage_mask;
+        stage_mask = coll_kernel_mask;
         SceneDev sd{};
         int S = 0;
         if (stage_mask & RLITG_STAGE_COLL) {
@@ -553,10 +580,11 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
         if (stage_mask & RLITG_STAGE_SMOOTH)
             band = reinterpret_cast<const T*>(sizeof(T) == 4 ? (const void*)smooth->d_band32 : (const void*)smooth->d_band64);
         const int zero_pose = (run_pose || (stage_mask & RLITG_STAGE_KEEP_COSTS)) ? 0 : 1;
-        kern<<<(unsigned)N, CH, smem, st>>>(P, traj, sd, S, band, stage_mask, zero_pose, stoch, inc_smooth, inc_coll, costs,
-                                            active, traj_stage);
+        kern<<<(unsigned)N, CH, smem, st>>>(P, traj, sd, S, band, stage_mask, zero_pose, stoch, inc_smooth,
+                                            row_only ? nullptr : inc_coll, costs, row_only ? nullptr : active, traj_stage);
         int rc = check_launch("torm_coll_kernel");
         if (rc) return rc;
+        stage_mask = stage_mask_pose;
     }
     if (run_pose) {
         const size_t smem = sizeof(T) * ((size_t)(CH + 12) * 7 + (size_t)(CH + 3) * 7 + 8 * kNRedPose);

@@ -351,4 +351,126 @@ torm_coll_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S, con
 #undef TROW
 #undef PROW
 
+// ---- kernel 3c: the collision increment of ONE waypoint per trajectory (use_stochastic_descent_, :1502-1515) ----------
+// With a single waypoint per trajectory the thread-per-waypoint kernel above keeps two CTAs per SM busy with one thread
+// each walking 24 spheres in turn (89 us for 1,024 trajectories, measured: pure latency).  Here a WARP takes a
+// trajectory and the sphere axis goes on the lanes: lanes 0..6 walk the chain of the seven stencil rows, then lane s
+// takes sphere s (gather, potential, stencil, projector, Jacobian columns from the centre row's table in shared memory,
+// solve), and the seven joint contributions are summed over the lanes by a fixed butterfly.  All other rows of the
+// increment are written as zeros (:1495).
+constexpr int kRowWarps = 4;  // trajectories per CTA
+
+template <typename T, bool kFk64>
+__global__ void __launch_bounds__(kRowWarps * 32)
+torm_coll_row_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S, int zero_costs, int64_t N,
+                     const int32_t* __restrict__ stoch, T* __restrict__ inc_coll, T* __restrict__ costs,
+                     float* __restrict__ active, const int32_t* __restrict__ traj_stage) {
+    using FT = typename std::conditional<kFk64, double, T>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int PS = (3 * S) | 1, Tn = P.Tn, F = Tn - 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    T* s_pos = reinterpret_cast<T*>(smem_raw) + (size_t)warp * (7 * PS + 42);  // [7][PS] stencil rows
+    T* s_tab = s_pos + 7 * PS;                                                // [42] (a_j, b_j) of the centre row
+    __shared__ float4 s_sph[kMaxSpheres];
+    __shared__ int s_start[kNumLinks + 1];
+    __shared__ int s_nanc[kMaxSpheres];
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+        s_sph[i] = sc.spheres[i];
+        int link = 0;
+        while (link < kNumLinks - 1 && i >= sc.link_start[link + 1]) link++;
+        s_nanc[i] = link + 1 < 7 ? link + 1 : 7;
+    }
+    if (threadIdx.x <= kNumLinks) s_start[threadIdx.x] = sc.link_start[threadIdx.x];
+    __syncthreads();
+    const int64_t n = (int64_t)blockIdx.x * kRowWarps + warp;
+    if (n >= N) return;
+    T* c = costs + n * RLITG_TORM_NCOST;
+    if (lane == 0 && zero_costs) {
+        c[5] = T(0);
+        if (zero_costs > 1) {
+            c[0] = c[1] = c[2] = c[3] = c[4] = T(0);
+            c[6] = c[7] = c[8] = c[9] = T(0);
+        }
+    }
+    if (traj_stage && traj_stage[n] != 0) {  // end-pose stage: the increment rows are left untouched
+        if (lane == 0 && active) active[n] = 0.f;
+        return;
+    }
+    const T* tr = traj + n * (int64_t)Tn * 7;
+    T* o_coll = inc_coll + n * (int64_t)F * 7;
+    const int row = stoch[n] + 1;  // full-trajectory row; 0 = the start row (index -1): no increment is taken
+    for (int k = lane; k < F * 7; k += 32) o_coll[k] = T(0);
+    if (row < 1 || row > Tn - 1) {
+        if (lane == 0 && active) active[n] = 0.f;
+        return;
+    }
+    CollVisit<T, FT, true> v;
+    if (lane < 7) {
+        v.sph = s_sph; v.link_start = s_start; v.quirk = P.quirk;
+        v.off = {FT(P.off64[0]), FT(P.off64[1]), FT(P.off64[2])};
+        v.pos_row = s_pos + lane * PS;
+        const int r = min(max(row - 3 + lane, 0), Tn - 1);  // clamped at the ends of the path (torm_trajectory.cpp:81-96)
+        walk_chain<FT, 7, kFk64>(tr + (size_t)r * 7, v);
+        if (lane == 3) {
+#pragma unroll
+            for (int j = 0; j < 7; j++) {
+                s_tab[6 * j + 0] = v.a[j].x; s_tab[6 * j + 1] = v.a[j].y; s_tab[6 * j + 2] = v.a[j].z;
+                s_tab[6 * j + 3] = v.b[j].x; s_tab[6 * j + 4] = v.b[j].y; s_tab[6 * j + 5] = v.b[j].z;
+            }
+        }
+    }
+    __syncwarp();
+    T acc[7];
+#pragma unroll
+    for (int j = 0; j < 7; j++) acc[j] = T(0);
+    int nact = 0;
+    for (int s = lane; s < S; s += 32) {
+        const T* nrow[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) nrow[k] = s_pos + k * PS;
+        const T* pc = nrow[3] + 3 * s;
+        const V3<T> x = {pc[0], pc[1], pc[2]};
+        const GridMap<T> gm(sc);
+        const int64_t cell = gm.cell(x);
+        if (cell < 0) continue;
+        const float4 rec = __ldg(sc.field + cell);
+        if (!(rec.x < 1e29f)) continue;
+        const T pot = get_potential(T(rec.x), T(s_sph[s].w), P.clearance);
+        if (pot < T(0.0001)) continue;
+        nact++;
+        V3<T> ja[7], jb[7];
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            ja[j] = {s_tab[6 * j], s_tab[6 * j + 1], s_tab[6 * j + 2]};
+            jb[j] = {s_tab[6 * j + 3], s_tab[6 * j + 4], s_tab[6 * j + 5]};
+        }
+        switch (s_nanc[s]) {
+            case 1: coll_sphere<T, 1>(P, rec, pot, nrow, ja, jb, s, acc); break;
+            case 2: coll_sphere<T, 2>(P, rec, pot, nrow, ja, jb, s, acc); break;
+            case 3: coll_sphere<T, 3>(P, rec, pot, nrow, ja, jb, s, acc); break;
+            case 4: coll_sphere<T, 4>(P, rec, pot, nrow, ja, jb, s, acc); break;
+            case 5: coll_sphere<T, 5>(P, rec, pot, nrow, ja, jb, s, acc); break;
+            case 6: coll_sphere<T, 6>(P, rec, pot, nrow, ja, jb, s, acc); break;
+            default: coll_sphere<T, 7>(P, rec, pot, nrow, ja, jb, s, acc); break;
+        }
+    }
+    // sum over the lanes: butterfly, the same order on every run (the thread-per-waypoint kernel adds the spheres in table
+    // order instead: the two agree to rounding, not bit for bit)
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nact += __shfl_xor_sync(0xffffffffu, nact, o);
+    __syncwarp();  // the zero fill above and the row below come from different lanes
+    if (lane < 7) {
+        T val = acc[0];
+#pragma unroll
+        for (int j = 1; j < 7; j++) val = (lane == j) ? acc[j] : val;
+        o_coll[(size_t)(row - 1) * 7 + lane] = val;
+    }
+    if (lane == 0 && active) active[n] = (float)nact;
+}
+
 }  // namespace rlitg

@@ -164,15 +164,22 @@ def test_stochastic_index_and_stage_masks(cuda_device, dtype):
     nz = np.abs(want["inc_coll"]).max(axis=-1) > 0
     assert (nz.sum(axis=1) <= 1).all() and nz.any()  # one waypoint per trajectory contributes
     assert rel_rows(got, want["inc_coll"], 1e-6).max() < (1e-8 if dtype == "float64" else 1e-3)
-    # RLITG_STAGE_COLL_ROW_ONLY (what localOptimizeTSGD asks for): the same increments from seven chain walks per trajectory
-    # instead of T; index -1 (collision_point_ = the start row) takes no increment in either form
+    # RLITG_STAGE_COLL_ROW_ONLY (what localOptimizeTSGD asks for): kernel 3c, a warp per trajectory with the spheres on
+    # its lanes -- the same increments (summed over the lanes instead of in table order: equal to rounding); index -1
+    # (collision_point_ = the start row) takes no increment in either form
     st2 = st.copy(); st2[0] = -1; st2[1] = 0; st2[2] = T - 2
-    full = tb.cost_grad(tt, TM.STAGE_COLL | TM.STAGE_SMOOTH, st2)
-    inc_full, sm_full = full["inc_coll"].clone(), full["inc_smooth"].clone()
-    ro = tb.cost_grad(tt, TM.STAGE_COLL | TM.STAGE_SMOOTH | TM.STAGE_COLL_ROW_ONLY, st2)
-    assert torch.equal(ro["inc_coll"], inc_full) and torch.equal(ro["inc_smooth"], sm_full)
+    full = tb.cost_grad(tt, TM.STAGE_COLL | TM.STAGE_SMOOTH, st2, want_active=True)
+    inc_full, sm_full, act_full = full["inc_coll"].clone(), full["inc_smooth"].clone(), full["active"].clone()
+    for extra in (TM.STAGE_SMOOTH, 0):
+        ro = tb.cost_grad(tt, TM.STAGE_COLL | extra | TM.STAGE_COLL_ROW_ONLY, st2, want_active=True)
+        scale = float(inc_full.abs().max())
+        assert float((ro["inc_coll"] - inc_full).abs().max()) <= (1e-12 if dtype == "float64" else 2e-6) * scale
+        if extra:
+            assert torch.equal(ro["inc_smooth"], sm_full)
+        assert torch.equal(ro["active"], act_full)
+        assert float(ro["costs"][:, 5].abs().max()) == 0.0
+        assert float(ro["inc_coll"][0].abs().max()) == 0.0 and float(ro["inc_coll"][1, 1:].abs().max()) == 0.0
     assert float(inc_full[0].abs().max()) == 0.0 and float(inc_full[1, 1:].abs().max()) == 0.0
-    assert float(ro["costs"][:, 5].abs().max()) == 0.0
     # facade members agree with the fused call
     c = tb.getEndPoseCost(tt).double().cpu().numpy()
     w = O.torm_cost_grad(traj, targets, None, op, None, O.STAGE_POSE)["costs"]
