@@ -225,7 +225,10 @@ RLITG_DEV void block_reduce(T (&red)[NR], T* s_red, T (&tot)[NR]) {
 // ---- kernel 3a: end-pose error / pinv step (A5) + trajectory evaluator (A8) -------------------------------
 // Writes costs[0..4], [6..9]; costs[5] (collision) is zeroed when the collision kernel does not run.
 constexpr int kNRedPose = 11;
-template <typename T, int MAXREG, bool kFrames>
+// kGrad = false: no end-pose increments in this launch (the feasible half of a TSGD iteration asks for the evaluator only)
+// -> the waypoint walk keeps the end-effector frame alone, no joint axes / origins, no Jacobian, no QR: a lighter kernel
+// (fewer registers, more CTAs per SM) instead of a run-time branch around the heavy part.
+template <typename T, int MAXREG, bool kFrames, bool kGrad>
 __global__ void __launch_bounds__(kTormMaxThreads) __maxnreg__(MAXREG)
 torm_pose_eval_kernel(TormP<T> P, const T* __restrict__ traj, const T* __restrict__ targets, int stage_mask,
                       int zero_coll_cost, T* __restrict__ inc_pose, T* __restrict__ costs,
@@ -263,7 +266,7 @@ torm_pose_eval_kernel(TormP<T> P, const T* __restrict__ traj, const T* __restric
         }
         // ---- end-pose error at the waypoint: getEndPoseCost :1399-1425
         if (valid && i >= 1) {
-            FkJac<T, 7> fj;
+            typename std::conditional<kGrad, FkJac<T, 7>, EeOnly<T>>::type fj;
             walk_chain<T, 7>(q, fj);
             V3<T> tp, t0, t1, t2;
             waypoint_target<T, kFrames>(targets, i, tp, t0, t1, t2);
@@ -272,7 +275,7 @@ torm_pose_eval_kernel(TormP<T> P, const T* __restrict__ traj, const T* __restric
             const V3<T> dp = tp - fj.ee.p;
             red[R_WP_POS] += sqrt_t(dot(dp, dp));
             red[R_WP_ROT] += sqrt_t(dot(rv, rv));
-            if (do_pgrad && o_pose) {
+            if constexpr (kGrad) if (do_pgrad && o_pose) {
                 T J[42], dq[7];
                 fill_jac<T, 7>(fj, J);
                 const T tw[6] = {dp.x, dp.y, dp.z, rv.x, rv.y, rv.z};
@@ -532,7 +535,7 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
         static const int fk64r = [] { const char* e = getenv("RLITG_TORM_FK64"); return e ? atoi(e) : 1; }();
         SceneDev sd = scene_dev(scene);
         const int S = sd.S;
-        const size_t smem = sizeof(T) * kRowWarps * (size_t)(7 * ((3 * S) | 1) + 42);
+        const size_t smem = sizeof(T) * kRowWarps * (size_t)(7 * ((4 * S) | 1) + 42);
         using RowK = void (*)(TormP<T>, const T*, SceneDev, int, int, int64_t, const int32_t*, T*, T*, float*, const int32_t*);
         RowK rk;
         if constexpr (sizeof(T) == 4) rk = fk64r ? torm_coll_row_kernel<T, true> : torm_coll_row_kernel<T, false>;
@@ -557,7 +560,7 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
             sd = scene_dev(scene);
             S = sd.S;
         }
-        const size_t smem = sizeof(T) * ((size_t)(CH + 12) * 7 + 8 * 2 + (size_t)(std::min(CH, (int)p->T) + 6) * ((3 * S) | 1));
+        const size_t smem = sizeof(T) * ((size_t)(CH + 12) * 7 + 8 * 2 + (size_t)(std::min(CH, (int)p->T) + 6) * ((4 * S) | 1));
         if (smem > 220 * 1024) return set_error(RLITG_ERR_SHAPE, "too many spheres for the shared-memory tile");
         // FP32 build: chain walk of phase 1 in FP64 (accuracy of the 1 / dt^2 stencils, torm_coll.cuh); RLITG_TORM_FK64=0
         // keeps it in FP32 (measurement knob).  Register budget: 2 CTAs/SM (128 regs) or 3 (96); RLITG_TORM_COLL_OCC
@@ -591,10 +594,12 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
         // register budget of the pose kernel: 2 CTAs/SM (128 regs) or 3 (96 regs at 224 threads); RLITG_TORM_POSE_OCC
         static const int occ = [] { const char* e = getenv("RLITG_TORM_POSE_OCC"); return e ? atoi(e) : 2; }();
         using PoseK = void (*)(TormP<T>, const T*, const T*, int, int, T*, T*, const int32_t*);
-        constexpr int kR2 = sizeof(T) == 4 ? 128 : 255, kR3 = sizeof(T) == 4 ? 96 : 255;
+        constexpr int kR2 = sizeof(T) == 4 ? 128 : 255, kR3 = sizeof(T) == 4 ? 96 : 255, kRL = sizeof(T) == 4 ? 72 : 255;
+        const bool grad = (stage_mask & RLITG_STAGE_POSE_GRAD) != 0;
         PoseK kern;
-        if (frames) kern = (sizeof(T) == 4 && occ == 3) ? torm_pose_eval_kernel<T, kR3, true> : torm_pose_eval_kernel<T, kR2, true>;
-        else kern = (sizeof(T) == 4 && occ == 3) ? torm_pose_eval_kernel<T, kR3, false> : torm_pose_eval_kernel<T, kR2, false>;
+        if (!grad) kern = frames ? torm_pose_eval_kernel<T, kRL, true, false> : torm_pose_eval_kernel<T, kRL, false, false>;
+        else if (frames) kern = (sizeof(T) == 4 && occ == 3) ? torm_pose_eval_kernel<T, kR3, true, true> : torm_pose_eval_kernel<T, kR2, true, true>;
+        else kern = (sizeof(T) == 4 && occ == 3) ? torm_pose_eval_kernel<T, kR3, false, true> : torm_pose_eval_kernel<T, kR2, false, true>;
         {
             int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "torm_pose_eval_kernel");
             if (rc_attr) return rc_attr;

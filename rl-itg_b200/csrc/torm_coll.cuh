@@ -41,15 +41,28 @@ namespace rlitg {
 
 constexpr int kCollThreads = 256;
 
+RLITG_DEV float cell_to_bits(int c, float) { return __int_as_float(c); }
+RLITG_DEV double cell_to_bits(int c, double) { return __longlong_as_double((long long)c); }
+RLITG_DEV int bits_to_cell(float b) { return __float_as_int(b); }
+RLITG_DEV int bits_to_cell(double b) { return (int)__double_as_longlong(b); }
+
 // Chain visitor of phase 1.  FT = precision of the walk (double in the FP32 production build), T = storage precision.
 template <typename T, typename FT, bool kJoints>
 struct CollVisit {
     V3<T> a[7], b[7];      // Jacobian table: column j of getJacobian (:1170-1178) = a_j x (x - o_j) = a_j x x + b_j
-    T* pos_row;            // shared-memory row [S][3] of this waypoint's sphere centres (planning frame)
+    T* pos_row;            // shared-memory row [S][4] of this waypoint's sphere centres (planning frame) + cell index bits
+    const GridMap<T>* gm;  // nullptr: the cell index is not wanted (halo rows)
     const float4* sph;
     const int* link_start;
     V3<FT> off;
     int quirk;
+    // centre + the linear index of its grid cell (-1 outside): the cell arithmetic sits here, next to the other spheres of
+    // the link, instead of in front of every gather of phase 2's serial sphere loop
+    RLITG_DEV void put(int s, V3<T> x) const {
+        T* d = pos_row + 4 * s;
+        d[0] = x.x; d[1] = x.y; d[2] = x.z;
+        if (gm != nullptr) d[3] = cell_to_bits((int)gm->cell(x), T(0));
+    }
     template <int K>
     RLITG_DEV void operator()(jidx<K>, const FrameC<FT>& f) {
         const V3<FT> o = f.p + off;
@@ -68,9 +81,10 @@ struct CollVisit {
             if constexpr (std::is_same<FT, T>::value) {
                 for (int s = s0; s < s1; s++) {
                     const float4 c = sph[s];
-                    pos_row[3 * s + 0] = o.x + f.c0.x * T(c.x) + f.c1.x * T(c.y) + f.c2.x * T(c.z);
-                    pos_row[3 * s + 1] = o.y + f.c0.y * T(c.x) + f.c1.y * T(c.y) + f.c2.y * T(c.z);
-                    pos_row[3 * s + 2] = o.z + f.c0.z * T(c.x) + f.c1.z * T(c.y) + f.c2.z * T(c.z);
+                    const V3<T> x = {o.x + f.c0.x * T(c.x) + f.c1.x * T(c.y) + f.c2.x * T(c.z),
+                                     o.y + f.c0.y * T(c.x) + f.c1.y * T(c.y) + f.c2.y * T(c.z),
+                                     o.z + f.c0.z * T(c.x) + f.c1.z * T(c.y) + f.c2.z * T(c.z)};
+                    put(s, x);
                 }
             } else {
                 // R c in FP32 (|c| <= 0.2 m: error ~1e-8 m) added to the FP64 link origin, carried as oh + ol: the sum
@@ -80,9 +94,10 @@ struct CollVisit {
                             r2 = {T(f.c2.x), T(f.c2.y), T(f.c2.z)};
                 for (int s = s0; s < s1; s++) {
                     const float4 c = sph[s];
-                    pos_row[3 * s + 0] = oh.x + ((r0.x * c.x + r1.x * c.y + r2.x * c.z) + ol.x);
-                    pos_row[3 * s + 1] = oh.y + ((r0.y * c.x + r1.y * c.y + r2.y * c.z) + ol.y);
-                    pos_row[3 * s + 2] = oh.z + ((r0.z * c.x + r1.z * c.y + r2.z * c.z) + ol.z);
+                    const V3<T> x = {oh.x + ((r0.x * c.x + r1.x * c.y + r2.x * c.z) + ol.x),
+                                     oh.y + ((r0.y * c.x + r1.y * c.y + r2.y * c.z) + ol.y),
+                                     oh.z + ((r0.z * c.x + r1.z * c.y + r2.z * c.z) + ol.z)};
+                    put(s, x);
                 }
             }
         }
@@ -96,6 +111,7 @@ __device__ __noinline__ void halo_sphere_row(const T* qrow, T* sph_row, const fl
     CollVisit<T, FT, false> hv;
     hv.sph = sph; hv.link_start = link_start; hv.quirk = quirk;
     hv.off = {ox, oy, oz};
+    hv.gm = nullptr;
     hv.pos_row = sph_row;
     walk_chain<FT, 7, kFk64>(qrow, hv);
 }
@@ -107,14 +123,14 @@ __device__ __noinline__ void halo_sphere_row(const T* qrow, T* sph_row, const fl
 template <typename T, int NANC>
 RLITG_DEV void coll_sphere(const TormP<T>& P, const float4 rec, const T pot, const T* const (&nrow)[7], const V3<T> (&ja)[7],
                            const V3<T> (&jb)[7], int s, T (&acc)[7]) {
-    const T* pc = nrow[3] + 3 * s;
+    const T* pc = nrow[3] + 4 * s;
     const V3<T> xc = {pc[0], pc[1], pc[2]};
     // sphere velocity / acceleration: 7-point stencils across waypoints (:1364-1381), differenced against the centre row
     V3<T> vel = {T(0), T(0), T(0)}, ac = {T(0), T(0), T(0)};
 #pragma unroll
     for (int k = 0; k < 7; k++) {
         if (k == 3) continue;
-        const T* pk = nrow[k] + 3 * s;
+        const T* pk = nrow[k] + 4 * s;
         const V3<T> d = {pk[0] - xc.x, pk[1] - xc.y, pk[2] - xc.z};
         vel = axpy(vel, P.rv[k], d);
         ac = axpy(ac, P.ra[k], d);
@@ -198,8 +214,8 @@ torm_coll_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S, con
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* s_traj = reinterpret_cast<T*>(smem_raw);  // [(CH + 12)][7]
     T* s_red = s_traj + (CH + 12) * 7;           // [8][2]
-    T* s_pos = s_red + 8 * 2;                    // [(min(CH, T) + 6)][PS] rows c0-3 .. c0+CH+2, PS = 3 S padded to odd
-    const int PS = (3 * S) | 1;                  // odd row stride: thread-per-row accesses are bank-conflict free
+    T* s_pos = s_red + 8 * 2;                    // [(min(CH, T) + 6)][PS] rows c0-3 .. c0+CH+2, PS = 4 S padded to odd
+    const int PS = (4 * S) | 1;                  // odd row stride: thread-per-row accesses are bank-conflict free
     __shared__ float4 s_sph[kMaxSpheres];
     __shared__ int s_start[kNumLinks + 1];
     __shared__ int s_nanc[kMaxSpheres];  // joints that move sphere s: min(link + 1, 7) (torm_optimizer.cpp:263-309)
@@ -270,6 +286,7 @@ torm_coll_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S, con
         CollVisit<T, FT, true> v;
         v.sph = s_sph; v.link_start = s_start; v.quirk = P.quirk;
         v.off = {FT(P.off64[0]), FT(P.off64[1]), FT(P.off64[2])};
+        v.gm = &gm;
         if (valid && (!row_only || abs(i - stoch_row) <= 3)) {
             v.pos_row = PROW(i);
             walk_chain<FT, 7, kFk64>(TROW(i), v);
@@ -300,8 +317,7 @@ torm_coll_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S, con
             int nact = 0;
             // distance-record gathers run two spheres ahead of the arithmetic (L2 latency off the critical path)
             auto fetch = [&](int s) -> float4 {
-                const V3<T> x = {prow[3 * s], prow[3 * s + 1], prow[3 * s + 2]};
-                const int64_t c = gm.cell(x);
+                const int c = bits_to_cell(prow[4 * s + 3]);
                 return c >= 0 ? __ldg(sc.field + c) : make_float4(1e30f, 0.f, 0.f, 0.f);
             };
             float4 r0 = fetch(0), r1 = S > 1 ? fetch(1) : make_float4(1e30f, 0.f, 0.f, 0.f);
@@ -367,7 +383,7 @@ torm_coll_row_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S,
                      float* __restrict__ active, const int32_t* __restrict__ traj_stage) {
     using FT = typename std::conditional<kFk64, double, T>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int PS = (3 * S) | 1, Tn = P.Tn, F = Tn - 1;
+    const int PS = (4 * S) | 1, Tn = P.Tn, F = Tn - 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     T* s_pos = reinterpret_cast<T*>(smem_raw) + (size_t)warp * (7 * PS + 42);  // [7][PS] stencil rows
     T* s_tab = s_pos + 7 * PS;                                                // [42] (a_j, b_j) of the centre row
@@ -408,6 +424,7 @@ torm_coll_row_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S,
     if (lane < 7) {
         v.sph = s_sph; v.link_start = s_start; v.quirk = P.quirk;
         v.off = {FT(P.off64[0]), FT(P.off64[1]), FT(P.off64[2])};
+        v.gm = nullptr;
         v.pos_row = s_pos + lane * PS;
         const int r = min(max(row - 3 + lane, 0), Tn - 1);  // clamped at the ends of the path (torm_trajectory.cpp:81-96)
         walk_chain<FT, 7, kFk64>(tr + (size_t)r * 7, v);
@@ -428,7 +445,7 @@ torm_coll_row_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S,
         const T* nrow[7];
 #pragma unroll
         for (int k = 0; k < 7; k++) nrow[k] = s_pos + k * PS;
-        const T* pc = nrow[3] + 3 * s;
+        const T* pc = nrow[3] + 4 * s;
         const V3<T> x = {pc[0], pc[1], pc[2]};
         const GridMap<T> gm(sc);
         const int64_t cell = gm.cell(x);
