@@ -260,20 +260,33 @@ RLITG_DEV T pinv_qr_stream(T (&Q)[6 * D], T (&v)[6], T (&dq)[D]) {
 template <typename T, int D>
 RLITG_DEV T nullspace_norm(const T (&J)[6 * D], const T (&e)[D]) {
     if constexpr (sizeof(T) == 4) {
-        // e - Q^T Q e with the orthonormal rows of the QR of J^T, projected out one after the other
-        T Q[6 * D], R[36], r[D];
+        // e - Q^T Q e with the orthonormal rows of the QR of J^T.  Streaming sweep: as soon as row k is orthonormal it is
+        // projected out of the residual and of the rows behind it and is dead -- no R, no finished rows stay live
+        T Q[6 * D], r[D];
 #pragma unroll
         for (int i = 0; i < 6 * D; i++) Q[i] = J[i];
-        mgs_rows<T, D>(Q, R);
 #pragma unroll
         for (int i = 0; i < D; i++) r[i] = e[i];
 #pragma unroll
         for (int k = 0; k < 6; k++) {
+            T n2 = T(0);
+#pragma unroll
+            for (int i = 0; i < D; i++) n2 += Q[k * D + i] * Q[k * D + i];
+            const T rn = sqrt_t(n2);
+            const T inv = T(1) / (rn > T(1e-30) ? rn : T(1e-30));
             T c = T(0);
 #pragma unroll
-            for (int i = 0; i < D; i++) c += Q[k * D + i] * r[i];
+            for (int i = 0; i < D; i++) { Q[k * D + i] *= inv; c += Q[k * D + i] * r[i]; }
 #pragma unroll
             for (int i = 0; i < D; i++) r[i] -= c * Q[k * D + i];
+#pragma unroll
+            for (int j = k + 1; j < 6; j++) {
+                T d = T(0);
+#pragma unroll
+                for (int i = 0; i < D; i++) d += Q[k * D + i] * Q[j * D + i];
+#pragma unroll
+                for (int i = 0; i < D; i++) Q[j * D + i] -= d * Q[k * D + i];
+            }
         }
         T n2 = T(0);
 #pragma unroll

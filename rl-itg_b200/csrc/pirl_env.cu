@@ -138,8 +138,8 @@ struct PirlVisit {
     }
 };
 
-template <typename T, bool kStep>
-__global__ void __launch_bounds__(kEnvTile, sizeof(T) == 4 ? 4 : 1) pirl_env_kernel(
+template <typename T, bool kStep, int MINB>
+__global__ void __launch_bounds__(kEnvTile, MINB) pirl_env_kernel(
     PirlCfgT<T> cfg, int64_t B, T* __restrict__ q, const float* __restrict__ action, int32_t* __restrict__ timestep,
     const int32_t* __restrict__ max_timestep, const T* __restrict__ targets, const T* __restrict__ demos, int Tmax,
     const T* __restrict__ latent, SceneDev sc, int has_scene, T ox, T oy, T oz, T* __restrict__ obs,
@@ -687,7 +687,13 @@ static int launch_pirl(const RlitgPirlCfg* cfg, int64_t B, T* q, const float* ac
     }
     const size_t smem = sizeof(T) * kEnvTile * (size_t)(c.O | 1);
     if (smem > 200 * 1024) return set_error(RLITG_ERR_SHAPE, "observation too long for the shared-memory tile");
-    auto kern = pirl_env_kernel<T, kStep>;
+    // CTAs per SM the register allocation aims at: 4 (<= 128 registers) or 5 (<= 96); RLITG_PIRL_OCC
+    static const int pocc = [] { const char* e = getenv("RLITG_PIRL_OCC"); return e ? atoi(e) : 4; }();
+    using EnvK = void (*)(PirlCfgT<T>, int64_t, T*, const float*, int32_t*, const int32_t*, const T*, const T*, int, const T*,
+                          SceneDev, int, T, T, T, T*, T*, uint8_t*, uint8_t*, int32_t*, T*);
+    EnvK kern;
+    if constexpr (sizeof(T) == 4) kern = pocc == 5 ? pirl_env_kernel<T, kStep, 5> : pirl_env_kernel<T, kStep, 4>;
+    else kern = pirl_env_kernel<T, kStep, 1>;
     {
         int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "pirl_env_kernel");
         if (rc_attr) return rc_attr;

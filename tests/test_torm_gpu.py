@@ -231,6 +231,45 @@ def test_cost_grad_benchmark_shape_all_trajectories(cuda_device):
     gsc.close()
 
 
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_collision_point_and_stochastic_index(cuda_device, dtype):
+    """rlitg_torm_collision_point = isCurrentTrajectoryCollisionFree (torm/src/torm_optimizer.cpp:695-717: the first
+    colliding row, from row 0 = free_vars_start_ - 1) + the waypoint choice of use_stochastic_descent_ (:1502-1515),
+    against the oracle's per-configuration sphere test."""
+    import ctypes as C
+    import torch
+    from oracle import oracle as O
+    from rlitg_b200 import _lib, fetch, torm as TM
+    N, T = 40, 57
+    traj, targets, osc, gsc = make_problem(N, T, 11, cuda_device)
+    traj[3, :, 1] += 0.9                      # pushed into the table from the start row on
+    traj[5, 20:, 1] += 0.9                    # collides from row 20
+    hit = O.sphere_collide(traj.reshape(-1, 7), osc, fetch.BASE_OFFSET).reshape(N, T).astype(bool)
+    want_first = np.where(hit.any(1), hit.argmax(1), -1)
+    assert (want_first >= 0).sum() >= 2 and (want_first < 0).sum() >= 2
+    dt = getattr(torch, dtype)
+    tt = torch.tensor(traj, dtype=dt, device=cuda_device)
+    u = torch.rand(N, device=cuda_device, dtype=torch.float32, generator=torch.Generator(device=cuda_device).manual_seed(3))
+    first = torch.empty(N, dtype=torch.int32, device=cuda_device)
+    anyh = torch.empty(N, dtype=torch.uint8, device=cuda_device)
+    st = torch.empty(N, dtype=torch.int32, device=cuda_device)
+    off = (C.c_double * 3)(*fetch.BASE_OFFSET)
+    _lib.check(_lib.lib.rlitg_torm_collision_point(tt.data_ptr(), N, T, _lib.F32 if dtype == "float32" else _lib.F64,
+                                                   gsc.handle, off, u.data_ptr(), first.data_ptr(), anyh.data_ptr(),
+                                                   st.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    gf, ga, gs = first.cpu().numpy(), anyh.cpu().numpy(), st.cpu().numpy()
+    if dtype == "float64":
+        assert np.array_equal(gf, want_first)
+    else:  # an FP32 sphere centre on a voxel boundary may flip one row's flag (counted like the collide test does)
+        assert (gf != want_first).sum() <= 1
+    assert np.array_equal(ga.astype(bool), gf >= 0)
+    F = T - 1
+    un = u.cpu().numpy()
+    want_st = np.where(gf >= 0, gf - 1, np.clip((un * np.float32(F - 1)).astype(np.int64), 0, F - 1))
+    assert np.array_equal(gs, want_st) and (gs == -1).any()   # the start-row collision gives index -1
+    gsc.close()
+
+
 def test_traj_evaluator_anchors_on_gpu(cuda_device, init_traj):
     """SURVEY 8c regression anchors through the kernel (FP64 and FP32): real reference paths + saved initial
     trajectories (T = 553, 227, 209, 320 -> exercises the chunked path for T > 256)."""
