@@ -19,6 +19,10 @@
 //            Also measured in round 2 and rejected: every lane walking its own active spheres (mask first, then the
 //            k-th active sphere of each lane per pass: max-over-lanes passes instead of the union, 18 vs 22) -- the second
 //            pass re-gathers the record and the per-lane link defeats the compile-time joint count: 137 -> 149 us.
+//            Also rejected: the trajectory split over the CTAs of a thread-block cluster (chunks of 26 - 100 rows, six
+//            extra threads walking the halo rows, partial costs handed to rank 0 through DSMEM) to cut the 19 % of stall
+//            samples at the end-of-CTA barrier: 192 / 182 / 125 / 147 / 118 us at 26 / 34 / 50 / 67 / 100 rows per CTA
+//            against 113 us unsplit -- more, partly filled warps per trajectory and the per-CTA set-up outweigh it.
 // Round 2 also built and measured the lane-per-active-(row, sphere)-pair mapping (chunks of rows per CTA in a cluster,
 // compacted pair list, joint tables and contributions through shared memory): 208 - 262 us against this kernel's
 // figure in profiles/README.md -- the exchange of the 42-value joint table and of the contributions through shared
