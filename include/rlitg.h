@@ -187,7 +187,7 @@ typedef struct RlitgPirlCfg {
     double dist_p[4], rot_p[4], imit_p[4], null_p[4];                      /* (:165-168) */
     double w_col, w_jlimit, w_early_stop;                                  /* (:170-172) */
     int32_t row_floats;     /* values per row of the targets / demos tables: 0 or 7 = packed [B,Tmax,7]; 8 = rows padded to
-                               [B,Tmax,8] (32-byte rows, 16-byte aligned tables: one or two whole DRAM sectors per row) */
+                               [B,Tmax,8] (32-byte rows, 32-byte aligned tables: one whole DRAM sector per FP32 row) */
     int32_t reserved_;
 } RlitgPirlCfg;
 

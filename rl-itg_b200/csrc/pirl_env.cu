@@ -9,7 +9,9 @@
 //
 // HBM-bound in principle (536 B/env at the trained setting), launch/latency-bound at 16k envs.  Observation rows
 // are staged in shared memory (odd row stride -> conflict-free) and written back coalesced.
+#include <climits>
 #include <cstdlib>
+#include <type_traits>
 
 #include "fetch_chain.cuh"
 #include "linalg.cuh"
@@ -68,15 +70,27 @@ RLITG_DEV T calc_reward(T err, const T* p) {
     return p[0] * e - p[2] * (ke * ke);
 }
 
-// one 7-value row of the target / demo tables.  Padded rows (RS = 8) are 32-byte aligned: two 128-bit loads that touch
+// Loads that must be ISSUED where they stand.  ptxas otherwise sinks the q / action loads behind the first use of the
+// timestep (ncu source page, round 2: three serialised DRAM round trips at the head of every thread -- timestep, then
+// the target rows, then q and the action -- 34 % of all stall samples at 1M envs).  volatile asm keeps program order.
+RLITG_DEV float ld_issue(const float* p) { float v; asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v; }
+RLITG_DEV double ld_issue(const double* p) { double v; asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; }
+RLITG_DEV int ld_issue(const int32_t* p) { int v; asm volatile("ld.global.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+
+// one 7-value row of the target / demo tables.  Padded rows (kRow8) are 32-byte aligned: one 256-bit load that touches
 // exactly one sector (FP32), instead of seven 4-byte loads of a row that straddles two (the 28-byte rows of a
-// [B,Tmax,7] table start at multiples of 28 bytes: 1.41 x the algorithmic DRAM traffic at 1M envs, round 1)
-template <typename T>
-RLITG_DEV void load_row7(const T* __restrict__ row, int RS, T (&o)[7]) {
-    if (RS == 8) {
+// [B,Tmax,7] table start at multiples of 28 bytes: 1.41 x the algorithmic DRAM traffic at 1M envs, round 1).
+// The row width is a template parameter: as a run-time branch both paths were if-converted into predicated loads of
+// the same registers, and the second set waited for the first to land (a fourth round trip).
+template <typename T, bool kRow8>
+RLITG_DEV void load_row7(const T* __restrict__ row, T (&o)[7]) {
+    if constexpr (kRow8) {
         if constexpr (sizeof(T) == 4) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(row)), b = __ldg(reinterpret_cast<const float4*>(row) + 1);
-            o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z;
+            // one 256-bit load (sm_100: LDG.E.256) = one request for the row's single 32-byte sector
+            float pad;
+            asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]), "=f"(o[4]), "=f"(o[5]), "=f"(o[6]), "=f"(pad)
+                         : "l"(row));
         } else {
             const double2* r2 = reinterpret_cast<const double2*>(row);
             const double2 a = __ldg(r2), b = __ldg(r2 + 1), c = __ldg(r2 + 2), d = __ldg(r2 + 3);
@@ -84,7 +98,7 @@ RLITG_DEV void load_row7(const T* __restrict__ row, int RS, T (&o)[7]) {
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < 7; k++) o[k] = row[k];
+        for (int k = 0; k < 7; k++) o[k] = __ldg(row + k);
     }
 }
 
@@ -99,7 +113,32 @@ RLITG_DEV void npq_rot(const T* t7, V3<T>& c0, V3<T>& c1, V3<T>& c2) {
     c2 = {s * (x * z + y * w), s * (y * z - x * w), T(1) - s * (x * x + y * y)};
 }
 
+// the end-effector frame only: with link poses in the observation the Jacobian is rebuilt from the staged row
 template <typename T>
+struct EeKeep {
+    FrameC<T> ee;
+    template <int K>
+    RLITG_DEV void operator()(jidx<K>, const FrameC<T>& f) {
+        if constexpr (K == 7) ee = f;
+    }
+};
+
+// row-major [6][7] Jacobian from the link poses staged for the observation: link k's entry holds (p, c0, c1) of the very
+// frame joint k turns in, so z_k = c0 / c1 / c0 x c1 by the joint's axis and column k = [z_k x (p_ee - p_k); z_k]
+template <typename T>
+RLITG_DEV void jac_from_link_rows(const T* __restrict__ lrow, const V3<T>& eep, T (&J)[42]) {
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+        const T* f = lrow + 9 * k;
+        const V3<T> p = {f[0], f[1], f[2]}, c0 = {f[3], f[4], f[5]}, c1 = {f[6], f[7], f[8]};
+        const V3<T> z = arm_axis(k) == AX_X ? c0 : (arm_axis(k) == AX_Y ? c1 : cross(c0, c1));
+        const V3<T> lin = cross(z, eep - p);
+        J[0 * 7 + k] = lin.x; J[1 * 7 + k] = lin.y; J[2 * 7 + k] = lin.z;
+        J[3 * 7 + k] = z.x; J[4 * 7 + k] = z.y; J[5 * 7 + k] = z.z;
+    }
+}
+
+template <typename T, bool kLinkObs>
 struct PirlVisit {
     T* row;
     int link_off, ee_off;
@@ -109,7 +148,7 @@ struct PirlVisit {
     const int* link_start;
     V3<T> off;
     bool hit;
-    FkJac<T, 7> fj;
+    typename std::conditional<kLinkObs, EeKeep<T>, FkJac<T, 7>>::type fj;
     template <int K>
     RLITG_DEV void operator()(jidx<K> k, const FrameC<T>& f) {
         fj(k, f);
@@ -138,8 +177,10 @@ struct PirlVisit {
     }
 };
 
-template <typename T, bool kStep, int MINB>
-__global__ void __launch_bounds__(kEnvTile, MINB) pirl_env_kernel(
+// kLinkObs: the observation carries the link poses (obs types 1 and 3; 1 is the trained setting) -- the 42 joint origin /
+// axis values of the Jacobian then live in the staged observation row instead of registers (5 CTAs/SM instead of 4)
+template <typename T, bool kStep, int TILE, int MINB, bool kLinkObs, bool kRow8>
+__global__ void __launch_bounds__(TILE, MINB) pirl_env_kernel(
     PirlCfgT<T> cfg, int64_t B, T* __restrict__ q, const float* __restrict__ action, int32_t* __restrict__ timestep,
     const int32_t* __restrict__ max_timestep, const T* __restrict__ targets, const T* __restrict__ demos, int Tmax,
     const T* __restrict__ latent, SceneDev sc, int has_scene, T ox, T oy, T oz, T* __restrict__ obs,
@@ -147,7 +188,7 @@ __global__ void __launch_bounds__(kEnvTile, MINB) pirl_env_kernel(
     T* __restrict__ errs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int O = cfg.O, OS = O | 1;
-    T* s_obs = reinterpret_cast<T*>(smem_raw);  // [kEnvTile, OS]
+    T* s_obs = reinterpret_cast<T*>(smem_raw);  // [TILE, OS]
     __shared__ float4 s_sph[kMaxSpheres];
     __shared__ int s_start[kNumLinks + 1];
     if (has_scene) {
@@ -156,21 +197,27 @@ __global__ void __launch_bounds__(kEnvTile, MINB) pirl_env_kernel(
         __syncthreads();
     }
     const int tid = threadIdx.x;
-    const int64_t base = (int64_t)blockIdx.x * kEnvTile;
-    const int n = (int)min((int64_t)kEnvTile, B - base);
+    const int64_t base = (int64_t)blockIdx.x * TILE;
+    const int n = (int)min((int64_t)TILE, B - base);
     const int64_t b = base + tid;
     if (tid < n) {
         T* row = s_obs + tid * OS;
+        // first round trip: q, the action and the timestep together
         T cur[7];
 #pragma unroll
-        for (int j = 0; j < 7; j++) cur[j] = q[b * 7 + j];
-        int ts = timestep[b];
-        const int mts = max_timestep[b];
-        const int RS = cfg.RS;
+        for (int j = 0; j < 7; j++) cur[j] = ld_issue(q + b * 7 + j);
+        float act[7];
+        if constexpr (kStep) {
+#pragma unroll
+            for (int j = 0; j < 7; j++) act[j] = ld_issue(action + b * 7 + j);
+        }
+        int ts = ld_issue(timestep + b);
+        const int mts = ld_issue(max_timestep + b);
+        constexpr int RS = kRow8 ? 8 : 7;
         const T* tg = targets + (int64_t)b * Tmax * RS;
 
         const int ot = cfg.obs_type;
-        PirlVisit<T> v;
+        PirlVisit<T, kLinkObs> v;
         v.row = row;
         v.link_off = (ot == 1) ? 7 : (ot == 3 ? 0 : -1);
         v.ee_off = (ot == 2) ? 7 : -1;
@@ -185,19 +232,15 @@ __global__ void __launch_bounds__(kEnvTile, MINB) pirl_env_kernel(
         T pf_tp[7], pf_dm[7];
         int4 pf_cnt = make_int4(0, 0, 0, 0);
         if constexpr (kStep) {
-            ts += 1;
-            {
-                const int tsp = min(max(ts, 0), Tmax - 1);
-                load_row7(tg + (size_t)tsp * RS, RS, pf_tp);
-                if (demos != nullptr) load_row7(demos + ((int64_t)b * Tmax + tsp) * RS, RS, pf_dm);
-                if (counters) pf_cnt = *reinterpret_cast<const int4*>(counters + b * 4);
-            }
             // _set_action :184-207
             T cl[7];
             bool no_out = true;
 #pragma unroll
             for (int j = 0; j < 7; j++) {
-                T o2 = cur[j] + T(action[b * 7 + j]);
+                T o2 = cur[j] + T(act[j]);
+                // scheduling tie: the first consumer of q / action also consumes the timestep, so that all three
+                // loads are in flight together (see ld_issue); INT_MIN is not a timestep
+                if (j == 0 && ts == INT_MIN) o2 = T(0);
                 if (cfg.cj[j]) {
                     const T pi = T(3.14159265358979323846);
                     if (o2 > pi) o2 -= T(2) * pi;
@@ -207,6 +250,15 @@ __global__ void __launch_bounds__(kEnvTile, MINB) pirl_env_kernel(
                 // np.allclose(o2, clip(o2)): |a - b| <= 1e-8 + 1e-5 |b|
                 if (!(abs_t(o2 - c) <= T(1e-8) + T(1e-5) * abs_t(c))) no_out = false;
                 cl[j] = c;
+            }
+            // second round trip, under the chain walk: the rows the timestep points at (placed behind the first use
+            // of q and the action so that the scheduler does not hold those loads back behind the wait for the timestep)
+            ts += 1;
+            {
+                const int tsp = min(max(ts, 0), Tmax - 1);
+                load_row7<T, kRow8>(tg + (size_t)tsp * RS, pf_tp);
+                if (demos != nullptr) load_row7<T, kRow8>(demos + ((int64_t)b * Tmax + tsp) * RS, pf_dm);
+                if (counters) pf_cnt = *reinterpret_cast<const int4*>(counters + b * 4);
             }
             if (cfg.train_mode) {
                 if (no_out) {
@@ -248,7 +300,7 @@ __global__ void __launch_bounds__(kEnvTile, MINB) pirl_env_kernel(
             if (t > mts) t = mts;
             t = min(max(t, 0), Tmax - 1);  // memory-safety guard: a caller stepping a finished episode stays in its path
             T t7[7];
-            load_row7(tg + (size_t)t * RS, RS, t7);
+            load_row7<T, kRow8>(tg + (size_t)t * RS, t7);
             // calc_pos_and_rot_error :335-349: R_ct = tM inv(eM); columns 0 and 1
             V3<T> m0, m1, m2;
             npq_rot(t7, m0, m1, m2);
@@ -308,7 +360,8 @@ __global__ void __launch_bounds__(kEnvTile, MINB) pirl_env_kernel(
                 // reward or the caller asks for it through errs
                 if ((cfg.null_flag && !cfg.refine_flag) || errs != nullptr) {
                     T J[42];
-                    fill_jac<T, 7>(v.fj, J);
+                    if constexpr (kLinkObs) jac_from_link_rows<T>(row + v.link_off, ee.p, J);
+                    else fill_jac<T, 7>(v.fj, J);
                     null_obj = nullspace_norm<T, 7>(J, ce);
                     null_rwd = calc_reward(null_obj, cfg.null_p);
                 }
@@ -352,8 +405,8 @@ __global__ void __launch_bounds__(kEnvTile, MINB) pirl_env_kernel(
         // 128-bit stores: a row holds O / 4 whole float4 groups, so a group never straddles two rows
         const int G = O >> 2;
         int r = tid / G, g = tid - r * G;
-        const int dr = kEnvTile / G, dg = kEnvTile - dr * G;
-        for (int i = tid; i < n * G; i += kEnvTile) {
+        const int dr = TILE / G, dg = TILE - dr * G;
+        for (int i = tid; i < n * G; i += TILE) {
             const T* sp = s_obs + r * OS + 4 * g;
             st_stream(reinterpret_cast<float4*>(dst) + i, make_float4((float)sp[0], (float)sp[1], (float)sp[2], (float)sp[3]));
             r += dr; g += dg;
@@ -362,8 +415,8 @@ __global__ void __launch_bounds__(kEnvTile, MINB) pirl_env_kernel(
     } else {
         // (row, column) advance incrementally instead of dividing by the runtime O
         int r = tid / O, c = tid - r * O;
-        const int dr = kEnvTile / O, dc = kEnvTile - dr * O;
-        for (int i = tid; i < n * O; i += kEnvTile) {
+        const int dr = TILE / O, dc = TILE - dr * O;
+        for (int i = tid; i < n * O; i += TILE) {
             st_stream(dst + i, s_obs[r * OS + c]);
             r += dr; c += dc;
             if (c >= O) { c -= O; r++; }
@@ -427,7 +480,7 @@ RLITG_DEV void group_fk(T qv, int l, unsigned gmask, T* __restrict__ sc, T* __re
     __syncwarp(gmask);
 }
 
-template <typename T, bool kStep>
+template <typename T, bool kStep, bool kRow8>
 __global__ void __launch_bounds__(kLaneEnvs * 8) pirl_env_lanes_kernel(
     PirlCfgT<T> cfg, int64_t B, T* __restrict__ q, const float* __restrict__ action, int32_t* __restrict__ timestep,
     const int32_t* __restrict__ max_timestep, const T* __restrict__ targets, const T* __restrict__ demos, int Tmax,
@@ -457,24 +510,24 @@ __global__ void __launch_bounds__(kLaneEnvs * 8) pirl_env_lanes_kernel(
     T* fr = s_fr + g * 96;
     T* scv = s_sc + g * 14;
     T* row = s_obs + (size_t)g * O;
-    const int RS = cfg.RS;
+    constexpr int RS = kRow8 ? 8 : 7;
     const T* tg = targets + (int64_t)b * Tmax * RS;
     const int ot = cfg.obs_type;
 
-    T cur = l < 7 ? q[b * 7 + l] : T(0);
-    int ts = timestep[b];
-    const int mts = max_timestep[b];
+    T cur = l < 7 ? ld_issue(q + b * 7 + l) : T(0);
+    float act = 0.f;
+    if constexpr (kStep) {
+        if (l < 7) act = ld_issue(action + b * 7 + l);
+    }
+    int ts = ld_issue(timestep + b);
+    const int mts = ld_issue(max_timestep + b);
     bool collision_flag = false, joint_limit_flag = false;
     T tp[7], dm[7];
     int cnt = 0;
     if constexpr (kStep) {
-        ts += 1;
-        const int tsp = min(max(ts, 0), Tmax - 1);
-        load_row7(tg + (size_t)tsp * RS, RS, tp);  // every lane holds the whole row (one broadcast transaction per load)
-        if (demos != nullptr) load_row7(demos + ((int64_t)b * Tmax + tsp) * RS, RS, dm);
-        if (counters && l < 4) cnt = counters[b * 4 + l];
         // _set_action :184-207, joint l on lane l
-        T o2 = cur + (l < 7 ? T(action[b * 7 + l]) : T(0));
+        T o2 = cur + T(act);
+        if (ts == INT_MIN) o2 = T(0);  // scheduling tie, as in the thread-per-env kernel
         const int j = l < 7 ? l : 0;
         if (l < 7 && cfg.cj[j]) {
             const T pi = T(3.14159265358979323846);
@@ -486,6 +539,11 @@ __global__ void __launch_bounds__(kLaneEnvs * 8) pirl_env_lanes_kernel(
         // np.allclose(o2, clip(o2)): |a - b| <= 1e-8 + 1e-5 |b|
         const bool ok = l >= 7 || (abs_t(o2 - c) <= T(1e-8) + T(1e-5) * abs_t(c));
         const bool no_out = (__ballot_sync(gmask, ok) & gmask) == gmask;
+        ts += 1;
+        const int tsp = min(max(ts, 0), Tmax - 1);
+        load_row7<T, kRow8>(tg + (size_t)tsp * RS, tp);  // every lane holds the whole row (one broadcast transaction per load)
+        if (demos != nullptr) load_row7<T, kRow8>(demos + ((int64_t)b * Tmax + tsp) * RS, dm);
+        if (counters && l < 4) cnt = counters[b * 4 + l];
         if (cfg.train_mode) {
             if (no_out) {
                 group_fk<T>(c, l, gmask, scv, fr);
@@ -541,7 +599,7 @@ __global__ void __launch_bounds__(kLaneEnvs * 8) pirl_env_lanes_kernel(
         if (t > mts) t = mts;
         t = min(max(t, 0), Tmax - 1);  // memory-safety guard: a caller stepping a finished episode stays in its path
         T t7[7];
-        load_row7(tg + (size_t)t * RS, RS, t7);
+        load_row7<T, kRow8>(tg + (size_t)t * RS, t7);
         // calc_pos_and_rot_error :335-349: R_ct = tM inv(eM); columns 0 and 1
         V3<T> m0, m1, m2;
         npq_rot(t7, m0, m1, m2);
@@ -672,7 +730,7 @@ static int launch_pirl(const RlitgPirlCfg* cfg, int64_t B, T* q, const float* ac
     // instructions against 1.1 M) -- so the switch point sits at 2,048; RLITG_PIRL_LANES_MAX moves it
     static const int64_t lanes_max = [] { const char* e = getenv("RLITG_PIRL_LANES_MAX"); return e ? atoll(e) : 2048ll; }();
     if (B <= lanes_max && c.O <= 1024) {
-        auto kl = pirl_env_lanes_kernel<T, kStep>;
+        auto kl = c.RS == 8 ? pirl_env_lanes_kernel<T, kStep, true> : pirl_env_lanes_kernel<T, kStep, false>;
         const size_t sm = sizeof(T) * kLaneEnvs * (size_t)(96 + 14 + c.O);
         int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kl), sm, "pirl_env_lanes_kernel");
         if (rc_attr) return rc_attr;
@@ -685,15 +743,21 @@ static int launch_pirl(const RlitgPirlCfg* cfg, int64_t B, T* q, const float* ac
                                           (T)offl[0], (T)offl[1], (T)offl[2], obs, reward, done, flags, counters, errs);
         return check_launch("pirl_env_lanes_kernel");
     }
-    const size_t smem = sizeof(T) * kEnvTile * (size_t)(c.O | 1);
-    if (smem > 200 * 1024) return set_error(RLITG_ERR_SHAPE, "observation too long for the shared-memory tile");
-    // CTAs per SM the register allocation aims at: 4 (<= 128 registers) or 5 (<= 96); RLITG_PIRL_OCC
-    static const int pocc = [] { const char* e = getenv("RLITG_PIRL_OCC"); return e ? atoi(e) : 4; }();
+    // template axes: link poses in the observation (the Jacobian's joint frames then live in the staged row, not in
+    // registers) and the row width of the target / demo tables.  The CTA shape stays 128 threads x 4 CTAs/SM: with the
+    // staged observation rows (89 floats per env in the trained setting) shared memory allows 6 x 96 = 18 or 2 x 320 = 20
+    // warps/SM at 96 registers, and both measured SLOWER at 1M envs (197 / 216 vs 168 us).
+    const bool link_obs = c.obs_type == 1 || c.obs_type == 3;
+    const bool row8 = c.RS == 8;
+    constexpr int tile = kEnvTile;
+    constexpr int kMinB = sizeof(T) == 4 ? 4 : 1;
     using EnvK = void (*)(PirlCfgT<T>, int64_t, T*, const float*, int32_t*, const int32_t*, const T*, const T*, int, const T*,
                           SceneDev, int, T, T, T, T*, T*, uint8_t*, uint8_t*, int32_t*, T*);
     EnvK kern;
-    if constexpr (sizeof(T) == 4) kern = pocc == 5 ? pirl_env_kernel<T, kStep, 5> : pirl_env_kernel<T, kStep, 4>;
-    else kern = pirl_env_kernel<T, kStep, 1>;
+    if (link_obs) kern = row8 ? pirl_env_kernel<T, kStep, tile, kMinB, true, true> : pirl_env_kernel<T, kStep, tile, kMinB, true, false>;
+    else kern = row8 ? pirl_env_kernel<T, kStep, tile, kMinB, false, true> : pirl_env_kernel<T, kStep, tile, kMinB, false, false>;
+    const size_t smem = sizeof(T) * tile * (size_t)(c.O | 1);
+    if (smem > 200 * 1024) return set_error(RLITG_ERR_SHAPE, "observation too long for the shared-memory tile");
     {
         int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "pirl_env_kernel");
         if (rc_attr) return rc_attr;
@@ -706,8 +770,8 @@ static int launch_pirl(const RlitgPirlCfg* cfg, int64_t B, T* q, const float* ac
         has_scene = 1;
         off[0] = base_off[0]; off[1] = base_off[1]; off[2] = base_off[2];
     }
-    const unsigned grid = (unsigned)((B + kEnvTile - 1) / kEnvTile);
-    kern<<<grid, kEnvTile, smem, st>>>(c, B, q, action, timestep, max_timestep, targets, demos, Tmax, latent, sd,
+    const unsigned grid = (unsigned)((B + tile - 1) / tile);
+    kern<<<grid, tile, smem, st>>>(c, B, q, action, timestep, max_timestep, targets, demos, Tmax, latent, sd,
                                        has_scene, (T)off[0], (T)off[1], (T)off[2], obs, reward, done, flags, counters, errs);
     return check_launch("pirl_env_kernel");
 }
@@ -750,8 +814,8 @@ RLITG_API int rlitg_pirl_env_step(const RlitgPirlCfg* cfg, int64_t B, int dtype,
     if (sc && !base_off) return set_error(RLITG_ERR_NULL, "base_off is NULL");
     if ((reinterpret_cast<uintptr_t>(flags) & 7) || (counters && (reinterpret_cast<uintptr_t>(counters) & 15)))
         return set_error(RLITG_ERR_ALIGN, "flags must be 8-byte and counters 16-byte aligned");
-    if (cfg->row_floats == 8 && ((reinterpret_cast<uintptr_t>(targets) & 15) || (demos && (reinterpret_cast<uintptr_t>(demos) & 15))))
-        return set_error(RLITG_ERR_ALIGN, "padded target / demo rows (row_floats = 8) must be 16-byte aligned");
+    if (cfg->row_floats == 8 && ((reinterpret_cast<uintptr_t>(targets) & 31) || (demos && (reinterpret_cast<uintptr_t>(demos) & 31))))
+        return set_error(RLITG_ERR_ALIGN, "padded target / demo rows (row_floats = 8) must be 32-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == RLITG_F32)
         return launch_pirl<float, true>(cfg, B, (float*)q, action, timestep, max_timestep, (const float*)targets,
@@ -773,8 +837,8 @@ RLITG_API int rlitg_pirl_obs(const RlitgPirlCfg* cfg, int64_t B, int dtype, cons
     if (B == 0) return RLITG_OK;
     if (!q || !timestep || !max_timestep || !targets || !obs) return set_error(RLITG_ERR_NULL, "a required buffer is NULL");
     if (cfg->z_dim > 0 && !latent) return set_error(RLITG_ERR_NULL, "latent is NULL but z_dim > 0");
-    if (cfg->row_floats == 8 && (reinterpret_cast<uintptr_t>(targets) & 15))
-        return set_error(RLITG_ERR_ALIGN, "padded target rows (row_floats = 8) must be 16-byte aligned");
+    if (cfg->row_floats == 8 && (reinterpret_cast<uintptr_t>(targets) & 31))
+        return set_error(RLITG_ERR_ALIGN, "padded target rows (row_floats = 8) must be 32-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == RLITG_F32)
         return launch_pirl<float, false>(cfg, B, (float*)q, nullptr, (int32_t*)timestep, max_timestep,
