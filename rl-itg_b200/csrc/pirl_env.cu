@@ -87,13 +87,15 @@ RLITG_DEV void load_row7(const T* __restrict__ row, T (&o)[7]) {
     if constexpr (kRow8) {
         if constexpr (sizeof(T) == 4) {
             // one 256-bit load (sm_100: LDG.E.256) = one request for the row's single 32-byte sector
+            // L2-only (.cg): a 32-byte gather has no reuse in L1, and keeping the gathers out of it took the 1M-env step from
+            // 160 to 132 us in the same run (DRAM bytes unchanged; .nc / L1::no_allocate / .cs: 160 / 150 / 162 us)
             float pad;
-            asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                          : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]), "=f"(o[4]), "=f"(o[5]), "=f"(o[6]), "=f"(pad)
                          : "l"(row));
         } else {
             const double2* r2 = reinterpret_cast<const double2*>(row);
-            const double2 a = __ldg(r2), b = __ldg(r2 + 1), c = __ldg(r2 + 2), d = __ldg(r2 + 3);
+            const double2 a = __ldcg(r2), b = __ldcg(r2 + 1), c = __ldcg(r2 + 2), d = __ldcg(r2 + 3);
             o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; o[4] = c.x; o[5] = c.y; o[6] = d.x;
         }
     } else {
@@ -296,7 +298,7 @@ __global__ void __launch_bounds__(TILE, MINB) pirl_env_kernel(
                 const int tsp = min(max(ts, 0), Tmax - 1);
                 load_row7<T, kRow8>(tg + (size_t)tsp * RS, pf_tp);
                 if (demos != nullptr) load_row7<T, kRow8>(demos + ((int64_t)b * Tmax + tsp) * RS, pf_dm);
-                if (counters) pf_cnt = *reinterpret_cast<const int4*>(counters + b * 4);
+                if (counters) pf_cnt = __ldcg(reinterpret_cast<const int4*>(counters + b * 4));
                 if constexpr (kFast) {
                     const int tf = min(max(min(ts + 1, mts), 0), Tmax - 1);
                     load_row7<T, kRow8>(tg + (size_t)tf * RS, pf_ft);
