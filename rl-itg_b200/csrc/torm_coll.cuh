@@ -47,6 +47,11 @@ constexpr int kCollThreads = 256;
 
 RLITG_DEV float cell_to_bits(int c, float) { return __int_as_float(c); }
 RLITG_DEV double cell_to_bits(int c, double) { return __longlong_as_double((long long)c); }
+RLITG_DEV float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+RLITG_DEV int lds_s32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+template <typename T> RLITG_DEV int lds_cell(uint32_t a) {  // the cell index stored in a T-sized slot (low word)
+    return lds_s32(a);
+}
 RLITG_DEV int bits_to_cell(float b) { return __float_as_int(b); }
 RLITG_DEV int bits_to_cell(double b) { return (int)__double_as_longlong(b); }
 
@@ -320,8 +325,17 @@ torm_coll_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S, con
             T csum = T(0);
             int nact = 0;
             // distance-record gathers run two spheres ahead of the arithmetic (L2 latency off the critical path)
+            // shared-memory addresses of the three tables the loop head reads, formed ONCE: a static / dynamic shared
+            // symbol's address is (cluster CTA id << 24) + offset on this architecture, and under the register cap the
+            // compiler re-read SR_CgaCtaId twice per sphere to rebuild it (7 % of the stall samples, round 2)
+            // (the identity shuffle makes the value opaque to the register allocator's rematerialisation)
+            const unsigned am = __activemask();
+            const int ln = threadIdx.x & 31;
+            const uint32_t a_cell = smem_u32(prow) + 3 * (uint32_t)sizeof(T);
+            const uint32_t a_sphw = __shfl_sync(am, smem_u32(s_sph) + 12u, ln);
+            const uint32_t a_nanc = __shfl_sync(am, smem_u32(s_nanc), ln);
             auto fetch = [&](int s) -> float4 {
-                const int c = bits_to_cell(prow[4 * s + 3]);
+                const int c = lds_cell<T>(a_cell + (uint32_t)s * 4u * (uint32_t)sizeof(T));
                 return c >= 0 ? __ldg(sc.field + c) : make_float4(1e30f, 0.f, 0.f, 0.f);
             };
             float4 r0 = fetch(0), r1 = S > 1 ? fetch(1) : make_float4(1e30f, 0.f, 0.f, 0.f);
@@ -330,11 +344,11 @@ torm_coll_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S, con
                 r0 = r1;
                 if (s + 2 < S) r1 = fetch(s + 2);
                 if (!(rec.x < 1e29f)) continue;
-                const T pot = get_potential(T(rec.x), T(s_sph[s].w), P.clearance);
+                const T pot = get_potential(T(rec.x), T(lds_f32(a_sphw + 16u * (uint32_t)s)), P.clearance);
                 csum += pot;
                 if (!inc_row || pot < T(0.0001)) continue;
                 nact++;
-                switch (s_nanc[s]) {  // uniform over the warp: every lane is on sphere s
+                switch (lds_s32(a_nanc + 4u * (uint32_t)s)) {  // uniform over the warp: every lane is on sphere s
                     case 1: coll_sphere<T, 1>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
                     case 2: coll_sphere<T, 2>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
                     case 3: coll_sphere<T, 3>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
