@@ -228,8 +228,10 @@ __global__ void __launch_bounds__(TILE, MINB) pirl_env_kernel(
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int O = cfg.O, OS = kFast ? O : (O | 1);
     T* s_obs = reinterpret_cast<T*>(smem_raw);  // [TILE, OS]
-    __shared__ float4 s_sph[kMaxSpheres];
-    __shared__ int s_start[kNumLinks + 1];
+    // sphere table behind the observation rows, allocated only with a scene: without it the trained layout fits FIVE
+    // 128-thread CTAs per SM (5 x (45,056 + 1,024 reserved) bytes) instead of four
+    float4* s_sph = reinterpret_cast<float4*>(s_obs + (size_t)TILE * OS);  // [kMaxSpheres]
+    int* s_start = reinterpret_cast<int*>(s_sph + kMaxSpheres);              // [kNumLinks + 1]
     if (has_scene) {
         for (int i = threadIdx.x; i < sc.S; i += blockDim.x) s_sph[i] = sc.spheres[i];
         if (threadIdx.x <= kNumLinks) s_start[threadIdx.x] = sc.link_start[threadIdx.x];
@@ -239,6 +241,7 @@ __global__ void __launch_bounds__(TILE, MINB) pirl_env_kernel(
     const int64_t base = (int64_t)blockIdx.x * TILE;
     const int n = (int)min((int64_t)TILE, B - base);
     const int64_t b = base + tid;
+    const unsigned wmask = __ballot_sync(0xffffffffu, tid < n);  // lanes of this warp that own an environment
     if (tid < n) {
         T* row = s_obs + tid * OS;
         // first round trip: q, the action and the timestep together
@@ -351,6 +354,16 @@ __global__ void __launch_bounds__(TILE, MINB) pirl_env_kernel(
             v.rw.template put<85>(m0.x * r1.x + m1.x * r1.y + m2.x * r1.z);
             v.rw.template put<86>(m0.y * r1.x + m1.y * r1.y + m2.y * r1.z);
             v.rw.template put<87>(m0.z * r1.x + m1.z * r1.y + m2.z * r1.z);
+            // the rows of this warp are complete: start their bulk store now, under the reward arithmetic (the wait for
+            // the engine's shared-memory reads at the end of the kernel was 13 % of the stall samples at 16,384 envs)
+            fence_proxy_async_smem();  // every writer: its row becomes visible to the async proxy
+            __syncwarp(wmask);
+            if ((tid & 31) == 0) {
+                const int warp = tid >> 5;
+                bulk_store(obs + (base + 32 * warp) * O, s_obs + (size_t)32 * warp * O,
+                           (uint32_t)(min(32, n - 32 * warp) * O * sizeof(T)));
+                bulk_commit();
+            }
         } else {
             if (ot != 3) {
     #pragma unroll
@@ -462,15 +475,9 @@ __global__ void __launch_bounds__(TILE, MINB) pirl_env_kernel(
         }
     }
     if constexpr (kFast) {
-        // every warp drains its own (densely packed) rows with one bulk store; no CTA barrier
-        const int warp = tid >> 5, nrow = min(32, n - 32 * warp);
-        fence_proxy_async_smem();  // every writer: its row becomes visible to the async proxy
-        __syncwarp();
-        if (nrow > 0 && (tid & 31) == 0) {
-            bulk_store(obs + (base + 32 * warp) * O, s_obs + (size_t)32 * warp * O, (uint32_t)(nrow * O * sizeof(T)));
-            bulk_commit();
-            bulk_wait_read_all();
-        }
+        // every warp drained its own (densely packed) rows with one bulk store, no CTA barrier; the shared memory must
+        // stay allocated until the engine has read it
+        if ((tid & 31) == 0 && tid < n) bulk_wait_read_all();
         return;
     }
     __syncthreads();
@@ -832,11 +839,18 @@ static int launch_pirl(const RlitgPirlCfg* cfg, int64_t B, T* q, const float* ac
     static const int pfast = [] { const char* e = getenv("RLITG_PIRL_FAST"); return e ? atoi(e) : 1; }();
     const bool fast = pfast && c.obs_type == 1 && c.n_future == 1 && c.z_dim == 0 && (reinterpret_cast<uintptr_t>(obs) & 15) == 0;
     EnvK kern;
-    if (fast) kern = row8 ? pirl_env_kernel<T, kStep, tile, kMinB, true, true, true> : pirl_env_kernel<T, kStep, tile, kMinB, true, false, true>;
+    constexpr int kMinBF = sizeof(T) == 4 ? 5 : 1;
+    if (fast) kern = row8 ? pirl_env_kernel<T, kStep, tile, kMinBF, true, true, true> : pirl_env_kernel<T, kStep, tile, kMinBF, true, false, true>;
     else if (link_obs) kern = row8 ? pirl_env_kernel<T, kStep, tile, kMinB, true, true, false> : pirl_env_kernel<T, kStep, tile, kMinB, true, false, false>;
     else kern = row8 ? pirl_env_kernel<T, kStep, tile, kMinB, false, true, false> : pirl_env_kernel<T, kStep, tile, kMinB, false, false, false>;
-    const size_t smem = sizeof(T) * tile * (size_t)(fast ? c.O : (c.O | 1));
+    size_t smem = sizeof(T) * tile * (size_t)(fast ? c.O : (c.O | 1)) +
+                        (scene ? kMaxSpheres * sizeof(float4) + 16 * sizeof(int) : 0);
     if (smem > 200 * 1024) return set_error(RLITG_ERR_SHAPE, "observation too long for the shared-memory tile");
+    // resident CTAs per SM are set through the shared-memory request: FOUR (16 warps) -- five fit the trained layout, and
+    // measured slower from 262k envs on (40.5 vs 37.2 us; 141.7 vs 132.0 us at 1M: less L1 for the strided q / action
+    // rows); RLITG_PIRL_SMEM_MIN moves the floor
+    static const size_t smem_min = [] { const char* e = getenv("RLITG_PIRL_SMEM_MIN"); return e ? (size_t)atoll(e) : (size_t)46800; }();
+    if (sizeof(T) == 4 && smem < smem_min) smem = smem_min;
     {
         int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "pirl_env_kernel");
         if (rc_attr) return rc_attr;

@@ -305,6 +305,18 @@ torm_coll_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S, con
             if (hr >= 0 && hr < Tn && (hr < c0 || hr >= c0 + CH) && (!row_only || abs(hr - stoch_row) <= 3))
                 halo_sphere_row<T, FT, kFk64>(TROW(hr), PROW(hr), s_sph, s_start, v.off.x, v.off.y, v.off.z, P.quirk);
         }
+        // the first two distance records of this row (its own cells, written above by this thread): issued before the
+        // barrier so that their L2 round trip overlaps the wait for the slowest walker
+        const uint32_t a_cell = smem_u32(PROW(i)) + 3 * (uint32_t)sizeof(T);
+        auto fetch = [&](int s) -> float4 {
+            const int c = lds_cell<T>(a_cell + (uint32_t)s * 4u * (uint32_t)sizeof(T));
+            return c >= 0 ? __ldg(sc.field + c) : make_float4(1e30f, 0.f, 0.f, 0.f);
+        };
+        float4 r0 = make_float4(1e30f, 0.f, 0.f, 0.f), r1 = r0;
+        if (valid && !(row_only && i != stoch_row)) {
+            r0 = fetch(0);
+            if (S > 1) r1 = fetch(1);
+        }
         __syncthreads();
 
         // ---- phase 2: potentials and cost over all spheres, then the CHOMP increments of this row's active spheres
@@ -331,14 +343,8 @@ torm_coll_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S, con
             // (the identity shuffle makes the value opaque to the register allocator's rematerialisation)
             const unsigned am = __activemask();
             const int ln = threadIdx.x & 31;
-            const uint32_t a_cell = smem_u32(prow) + 3 * (uint32_t)sizeof(T);
             const uint32_t a_sphw = __shfl_sync(am, smem_u32(s_sph) + 12u, ln);
             const uint32_t a_nanc = __shfl_sync(am, smem_u32(s_nanc), ln);
-            auto fetch = [&](int s) -> float4 {
-                const int c = lds_cell<T>(a_cell + (uint32_t)s * 4u * (uint32_t)sizeof(T));
-                return c >= 0 ? __ldg(sc.field + c) : make_float4(1e30f, 0.f, 0.f, 0.f);
-            };
-            float4 r0 = fetch(0), r1 = S > 1 ? fetch(1) : make_float4(1e30f, 0.f, 0.f, 0.f);
             for (int s = 0; s < S; s++) {
                 const float4 rec = r0;
                 r0 = r1;
