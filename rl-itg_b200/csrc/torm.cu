@@ -80,6 +80,30 @@ template <typename T> RLITG_DEV T shortest_angular_distance(T start, T end) {
 }
 
 // getPotential torm/include/torm/torm_optimizer.h:146-168 (diff * clearance)
+// The (CH + 12) x 7 trajectory window of a chunk (rows c0 - 6 .. c0 + CH + 5, clamped into the trajectory) into shared
+// memory.  All of a thread's loads are issued before its first store: the plain copy loop went load / store / load in
+// two or more serialised global round trips (12 % of the stall samples of the end-pose kernel, round 2).
+template <typename T>
+RLITG_DEV void stage_traj_window(T* __restrict__ s_traj, const T* __restrict__ tr, int c0, int Tn, int CH, int tid) {
+    const int total = (CH + 12) * 7;
+    for (int base = tid; base < total; base += 8 * CH) {
+        T v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int idx = base + k * CH;
+            if (idx < total) {
+                const int r = idx / 7, j = idx - r * 7;
+                v[k] = tr[min(max(c0 - 6 + r, 0), Tn - 1) * 7 + j];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int idx = base + k * CH;
+            if (idx < total) s_traj[idx] = v[k];
+        }
+    }
+}
+
 template <typename T> RLITG_DEV T get_potential(T field_distance, T radius, T clearance) {
     const T d = field_distance - radius;
     if (d >= clearance) return T(0);
@@ -252,10 +276,7 @@ torm_pose_eval_kernel(TormP<T> P, const T* __restrict__ traj, const T* __restric
 
     for (int c0 = 0; c0 < Tn; c0 += CH) {
         __syncthreads();
-        for (int idx = tid; idx < (CH + 12) * 7; idx += CH) {
-            const int r = idx / 7, j = idx - r * 7;
-            s_traj[idx] = tr[min(max(c0 - 6 + r, 0), Tn - 1) * 7 + j];
-        }
+        stage_traj_window<T>(s_traj, tr, c0, Tn, CH, tid);
         __syncthreads();
         const int i = c0 + tid;
         const bool valid = i < Tn;

@@ -266,10 +266,7 @@ torm_coll_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S, con
 
     for (int c0 = 0; c0 < Tn; c0 += CH) {
         __syncthreads();
-        for (int idx = tid; idx < (CH + 12) * 7; idx += CH) {
-            const int r = idx / 7, j = idx - r * 7;
-            s_traj[idx] = tr[min(max(c0 - 6 + r, 0), Tn - 1) * 7 + j];
-        }
+        stage_traj_window<T>(s_traj, tr, c0, Tn, CH, tid);
         __syncthreads();
         const int i = c0 + tid;
         const bool valid = i < Tn;
