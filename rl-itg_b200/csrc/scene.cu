@@ -312,14 +312,60 @@ __global__ void __launch_bounds__(256) sphere_collide_smem_kernel(const T* __res
 // uniform u -- as a free-row index that is first_hit - 1, or (int)(u (F - 1)).  first_hit = 0 (the start row collides)
 // gives index -1, which the reference writes out of bounds; the cost kernel takes no
 // increment for it.  One CTA per trajectory, rows strided over the threads, block-wide minimum.
+// Sphere test against the dilated bit grids with the loads of a link's spheres batched four at a time (independent
+// L2 round trips instead of 2 x 24 dependent ones per waypoint: the class table sits in shared memory as a word offset)
 template <typename T>
-__global__ void __launch_bounds__(128) collision_point_kernel(const T* __restrict__ traj, int Tn, SceneDev sc, T ox, T oy, T oz,
+struct CollideVisitDil {
+    const SceneDev& sc;
+    const GridMap<T>& gm;
+    const float4* sph;      // shared-memory copy of the sphere table
+    const int* link_start;  // shared-memory copy
+    const int* cls_off;     // shared memory: class of sphere s times the words per class
+    V3<T> off;
+    bool hit = false;
+    template <int K>
+    RLITG_DEV void operator()(jidx<K>, const FrameC<T>& f) {
+        if constexpr (K < kNumLinks) {
+            const int s1 = link_start[K + 1];
+            for (int s0 = link_start[K]; s0 < s1; s0 += 4) {
+                uint32_t w[4];
+                int bit[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    w[k] = 0u;
+                    bit[k] = 0;
+                    const int s = s0 + k;
+                    if (s < s1) {
+                        const float4 c = sph[s];
+                        const T x = off.x + f.p.x + f.c0.x * T(c.x) + f.c1.x * T(c.y) + f.c2.x * T(c.z);
+                        const T y = off.y + f.p.y + f.c0.y * T(c.x) + f.c1.y * T(c.y) + f.c2.y * T(c.z);
+                        const T z = off.z + f.p.z + f.c0.z * T(c.x) + f.c1.z * T(c.y) + f.c2.z * T(c.z);
+                        const int cx = gm.cell1(x, gm.ox), cy = gm.cell1(y, gm.oy), cz = gm.cell1(z, gm.oz);
+                        if (cx >= 0 && cy >= 0 && cz >= 0 && cx < sc.nx && cy < sc.ny && cz < sc.nz) {
+                            w[k] = __ldg(sc.dil + (size_t)cls_off[s] + ((size_t)cz * sc.ny + cy) * sc.wx + (cx >> 5));
+                            bit[k] = cx & 31;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) hit = hit || ((w[k] >> bit[k]) & 1u);
+            }
+        }
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) collision_point_kernel(const T* __restrict__ traj, int Tn, SceneDev sc, T ox, T oy, T oz,
                                                              const float* __restrict__ u, int32_t* __restrict__ first_hit,
                                                              uint8_t* __restrict__ any_hit, int32_t* __restrict__ stoch_idx) {
     __shared__ float4 s_sph[kMaxSpheres];
     __shared__ int s_start[kNumLinks + 1];
     __shared__ int s_first;
-    for (int i = threadIdx.x; i < sc.S; i += blockDim.x) s_sph[i] = sc.spheres[i];
+    __shared__ int s_cls[kMaxSpheres];
+    for (int i = threadIdx.x; i < sc.S; i += blockDim.x) {
+        s_sph[i] = sc.spheres[i];
+        s_cls[i] = sc.dil ? sc.sph_class[i] * (sc.wx * sc.ny * sc.nz) : 0;
+    }
     if (threadIdx.x <= kNumLinks) s_start[threadIdx.x] = sc.link_start[threadIdx.x];
     if (threadIdx.x == 0) s_first = 0x7fffffff;
     __syncthreads();
@@ -332,9 +378,17 @@ __global__ void __launch_bounds__(128) collision_point_kernel(const T* __restric
         T qv[7];
 #pragma unroll
         for (int j = 0; j < 7; j++) qv[j] = tr[(size_t)i * 7 + j];
-        CollideVisit<T> v{sc, gm, s_sph, s_start, {ox, oy, oz}};
-        walk_chain<T, 7>(qv, v);
-        if (v.hit) mine = min(mine, i);
+        bool hit;
+        if (sc.dil) {
+            CollideVisitDil<T> v{sc, gm, s_sph, s_start, s_cls, {ox, oy, oz}};
+            walk_chain<T, 7>(qv, v);
+            hit = v.hit;
+        } else {
+            CollideVisit<T> v{sc, gm, s_sph, s_start, {ox, oy, oz}};
+            walk_chain<T, 7>(qv, v);
+            hit = v.hit;
+        }
+        if (hit) mine = min(mine, i);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, o));
@@ -560,12 +614,13 @@ RLITG_API int rlitg_torm_collision_point(const void* traj, int64_t N, int T, int
     if (!traj || !base_off) return set_error(RLITG_ERR_NULL, "traj / base_off is NULL");
     if (!scene_ready(s, true, true)) return set_error(RLITG_ERR_ARG, "scene needs a grid and a sphere table");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int cp_threads = std::min(256, ((T + 31) / 32) * 32);  // one waypoint per thread up to 256 rows per pass
     if (dtype == RLITG_F32)
-        collision_point_kernel<float><<<(unsigned)N, 128, 0, st>>>((const float*)traj, T, s->dev(), (float)base_off[0],
+        collision_point_kernel<float><<<(unsigned)N, cp_threads, 0, st>>>((const float*)traj, T, s->dev(), (float)base_off[0],
                                                                    (float)base_off[1], (float)base_off[2], u, first_hit,
                                                                    any_hit, stochastic_idx);
     else if (dtype == RLITG_F64)
-        collision_point_kernel<double><<<(unsigned)N, 128, 0, st>>>((const double*)traj, T, s->dev(), base_off[0], base_off[1],
+        collision_point_kernel<double><<<(unsigned)N, cp_threads, 0, st>>>((const double*)traj, T, s->dev(), base_off[0], base_off[1],
                                                                     base_off[2], u, first_hit, any_hit, stochastic_idx);
     else return set_error(RLITG_ERR_DTYPE, "dtype must be RLITG_F32 or RLITG_F64");
     return check_launch("collision_point_kernel");
