@@ -336,6 +336,7 @@ def main():
             nest("pirl", rec)
             summary["pirl"]["us_per_step"] = rec["us_per_step"]
             summary["pirl"]["us_per_step_cuda_graph"] = rec["us_per_step_cuda_graph"]
+            summary["pirl"]["us_per_step_50_steps_per_graph"] = rec.get("us_per_step_50_steps_per_graph")
             config["pirl"] = det.pop("config")
             also["pirl_env_step"] = det
         except Exception as e:  # noqa: BLE001

@@ -212,10 +212,22 @@ def run_pirl(torch, dev, rank, world, max_over_ranks, barrier, steps, warmup, hb
             us_graph = 1e3 * max_over_ranks(time_loop(torch, g.replay, steps, warmup, blocks=3))
         except Exception:  # noqa: BLE001
             pass
+        # the kernel without the launch path: 50 steps captured in ONE graph (what a captured roll-out loop pays per step)
+        us_gpu = None
+        try:
+            env.step(act); torch.cuda.synchronize()
+            g50 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g50):
+                for _ in range(50):
+                    env.step(act)
+            us_gpu = 1e3 * max_over_ranks(time_loop(torch, g50.replay, max(steps // 5, 3), 2, blocks=3)) / 50
+            del g50
+        except Exception:  # noqa: BLE001
+            pass
         gbs = BYTES_ENV * B / (ms * 1e-3) / 1e9
         d = {"envs_per_gpu": B, "path_poses": Tp, "us_per_step": ms * 1e3, "us_per_step_cold": ms_cold * 1e3,
-             "us_per_step_cuda_graph": us_graph, "env_steps_per_s": world * B / (ms * 1e-3), "gb_per_s": gbs,
-             "hbm_frac": gbs / hbm_peak}
+             "us_per_step_cuda_graph": us_graph, "us_per_step_50_steps_per_graph": us_gpu,
+             "env_steps_per_s": world * B / (ms * 1e-3), "gb_per_s": gbs, "hbm_frac": gbs / hbm_peak}
         detail["envs_%d" % B] = d
         if B == 16384:
             # ---- end to end at the BASELINE config: action H2D (pinned), step, obs / reward / done D2H (pinned)
@@ -256,7 +268,7 @@ def run_pirl(torch, dev, rank, world, max_over_ranks, barrier, steps, warmup, hb
                 cb = {"value": reps * B / dtc, "unit": "env-steps/s", "cores": O.num_threads(), "kind": "port",
                       "sample": "%d x %d envs, one step each, FP64 oracle (OpenMP), %.1f s" % (reps, B, dtc)}
             rec = {"metric": "pirl_env_steps_per_s", "value": world * B / (ms * 1e-3), "unit": "env-steps/s", "us_per_step": ms * 1e3,
-                   "us_per_step_cuda_graph": us_graph, "cpu_baseline": cb, "e2e": e2e}
+                   "us_per_step_cuda_graph": us_graph, "us_per_step_50_steps_per_graph": us_gpu, "cpu_baseline": cb, "e2e": e2e}
         del env, demos, targets_b
     big = detail.get("envs_1048576")
     if rec is not None:
@@ -265,7 +277,7 @@ def run_pirl(torch, dev, rank, world, max_over_ranks, barrier, steps, warmup, hb
                            "traffic": profile_traffic("pirl_env_kernel_1M"), "bytes_per_env": BYTES_ENV,
                            "at": "%d envs (the HBM-bound size; 16,384 envs = %.1f MB is launch / latency bound: %.1f us per step)"
                                  % (src["envs_per_gpu"], 16384 * BYTES_ENV / 1e6, detail["envs_16384"]["us_per_step"]),
-                           "kernel": "pirl_env_kernel<float,step>"}
+                           "kernel": "pirl_env_kernel<float,step,linkobs,row8,fast>"}
     detail["config"] = {"workload": "pirl_env_step", "obs": "Conf+LinkPoses t=1 z=0 (88 floats)", "reward": "Task+NullSpaceImitation",
                         "l2": "16k-env batch is L2 resident (8.8 MB); 1M envs (562 MB) is not; cold = L2 flushed"}
     return rec, detail

@@ -501,11 +501,14 @@ extern "C" RLITG_API int rlitg_greedy_select(const void* costs, int C, int Tseg,
 namespace rlitg {
 struct HostWs {
     std::mutex mu;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, st2 = nullptr;  // two streams: the chunks of a call alternate between them
+    cudaEvent_t ev = nullptr;
     void* buf = nullptr;
     size_t cap = 0;
     int ensure(size_t bytes) {
         if (!st && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return set_cuda_error("cudaStreamCreate");
+        if (!st2 && cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking) != cudaSuccess) return set_cuda_error("cudaStreamCreate");
+        if (!ev && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return set_cuda_error("cudaEventCreate");
         if (cap < bytes) {
             if (buf) cudaFree(buf);
             buf = nullptr; cap = 0;
@@ -542,20 +545,46 @@ extern "C" RLITG_API int rlitg_torm_cost_grad_host(const void* traj, const void*
     char* base = static_cast<char*>(g_torm_ws.buf);
     char *d_traj = base, *d_tg = d_traj + b_traj, *d_is = d_tg + b_tg, *d_ic = d_is + b_inc, *d_ip = d_ic + b_inc,
          *d_cost = d_ip + b_inc, *d_st = d_cost + b_cost;
-    cudaStream_t st = g_torm_ws.st;
-    if (cudaMemcpyAsync(d_traj, traj, es * N * T * 7, cudaMemcpyHostToDevice, st) != cudaSuccess ||
-        cudaMemcpyAsync(d_tg, targets, es * T * 7, cudaMemcpyHostToDevice, st) != cudaSuccess ||
-        (stochastic_idx && cudaMemcpyAsync(d_st, stochastic_idx, 4 * (size_t)N, cudaMemcpyHostToDevice, st) != cudaSuccess))
-        return set_cuda_error("H2D trajectories");
-    rc = rlitg_torm_cost_grad(d_traj, d_tg, N, dtype, scene, smooth, p, stage_mask,
-                              stochastic_idx ? reinterpret_cast<const int32_t*>(d_st) : nullptr,
-                              inc_smooth ? d_is : nullptr, inc_coll ? d_ic : nullptr, inc_pose ? d_ip : nullptr, d_cost,
-                              nullptr, st);
-    if (rc) return rc;
-    cudaError_t e = cudaMemcpyAsync(costs, d_cost, es * N * RLITG_TORM_NCOST, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && inc_smooth && (stage_mask & RLITG_STAGE_SMOOTH)) e = cudaMemcpyAsync(inc_smooth, d_is, es * N * F * 7, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && inc_coll && (stage_mask & RLITG_STAGE_COLL)) e = cudaMemcpyAsync(inc_coll, d_ic, es * N * F * 7, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && inc_pose && (stage_mask & RLITG_STAGE_POSE_GRAD)) e = cudaMemcpyAsync(inc_pose, d_ip, es * N * F * 7, cudaMemcpyDeviceToHost, st);
-    if (e != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return set_cuda_error("D2H increments");
+    // The trajectories go through in chunks that alternate between two streams: chunk k's increments travel back over
+    // PCIe (17 MB per 1,024 x 200 call: the longest leg) while chunk k + 1 computes and chunk k + 2 is on its way in.
+    const int64_t nchunk = N >= 512 ? 4 : 1;
+    const int64_t per = (N + nchunk - 1) / nchunk;
+    cudaStream_t sts[2] = {g_torm_ws.st, g_torm_ws.st2};
+    if (cudaMemcpyAsync(d_tg, targets, es * T * 7, cudaMemcpyHostToDevice, sts[0]) != cudaSuccess ||
+        cudaEventRecord(g_torm_ws.ev, sts[0]) != cudaSuccess || cudaStreamWaitEvent(sts[1], g_torm_ws.ev, 0) != cudaSuccess)
+        return set_cuda_error("H2D targets");
+    const char* h_traj = static_cast<const char*>(traj);
+    for (int64_t c = 0; c < nchunk; c++) {
+        const int64_t n0 = c * per, n = std::min(per, N - n0);
+        if (n <= 0) break;
+        cudaStream_t st = sts[c & 1];
+        const size_t o_tr = es * n0 * T * 7, o_inc = es * n0 * F * 7, o_cost = es * n0 * RLITG_TORM_NCOST;
+        if (cudaMemcpyAsync(d_traj + o_tr, h_traj + o_tr, es * n * T * 7, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            (stochastic_idx && cudaMemcpyAsync(d_st + 4 * n0, stochastic_idx + n0, 4 * (size_t)n, cudaMemcpyHostToDevice, st) != cudaSuccess))
+            return set_cuda_error("H2D trajectories");
+        rc = rlitg_torm_cost_grad(d_traj + o_tr, d_tg, n, dtype, scene, smooth, p, stage_mask,
+                                  stochastic_idx ? reinterpret_cast<const int32_t*>(d_st) + n0 : nullptr,
+                                  inc_smooth ? d_is + o_inc : nullptr, inc_coll ? d_ic + o_inc : nullptr,
+                                  inc_pose ? d_ip + o_inc : nullptr, d_cost + o_cost, nullptr, st);
+        if (rc) {
+            cudaStreamSynchronize(sts[0]);
+            cudaStreamSynchronize(sts[1]);
+            return rc;
+        }
+        cudaError_t e = cudaMemcpyAsync(static_cast<char*>(costs) + o_cost, d_cost + o_cost, es * n * RLITG_TORM_NCOST, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && inc_smooth && (stage_mask & RLITG_STAGE_SMOOTH))
+            e = cudaMemcpyAsync(static_cast<char*>(inc_smooth) + o_inc, d_is + o_inc, es * n * F * 7, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && inc_coll && (stage_mask & RLITG_STAGE_COLL))
+            e = cudaMemcpyAsync(static_cast<char*>(inc_coll) + o_inc, d_ic + o_inc, es * n * F * 7, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && inc_pose && (stage_mask & RLITG_STAGE_POSE_GRAD))
+            e = cudaMemcpyAsync(static_cast<char*>(inc_pose) + o_inc, d_ip + o_inc, es * n * F * 7, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) {
+            cudaStreamSynchronize(sts[0]);
+            cudaStreamSynchronize(sts[1]);
+            return set_cuda_error("D2H increments");
+        }
+    }
+    const cudaError_t e0 = cudaStreamSynchronize(sts[0]), e1 = cudaStreamSynchronize(sts[1]);
+    if (e0 != cudaSuccess || e1 != cudaSuccess) return set_cuda_error("D2H increments");
     return RLITG_OK;
 }
