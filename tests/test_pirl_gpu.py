@@ -39,7 +39,8 @@ def build_case(B, T, seed, with_scene, cuda_device):
 
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
 @pytest.mark.parametrize("reward_type,obs_type,t,z,with_scene,refine", [
-    ("Task+NullSpaceImitation", "Conf+LinkPoses", 1, 0, False, False),  # the trained setting (88-d obs)
+    ("Task+NullSpaceImitation", "Conf+LinkPoses", 1, 0, False, False),  # the trained setting (88-d obs): the fast-path kernel
+    ("Task+NullSpaceImitation", "Conf+LinkPoses", 1, 0, True, False),   # same with a scene: the row is re-assembled after a collision
     ("Task+NullSpaceImitation", "Conf+LinkPoses", 1, 32, True, False),  # obs scenes: 120-d obs + collision
     ("Task+Imitation", "Conf+EE", 3, 0, True, False),
     ("Imitation", "onlyConf", 2, 4, False, False),
