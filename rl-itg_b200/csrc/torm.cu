@@ -581,20 +581,23 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
             sd = scene_dev(scene);
             S = sd.S;
         }
-        const size_t smem = sizeof(T) * ((size_t)(CH + 12) * 7 + 8 * 2 + (size_t)(std::min(CH, (int)p->T) + 6) * ((4 * S) | 1));
+        static const int cocc = [] { const char* e = getenv("RLITG_TORM_COLL_OCC"); return e ? atoi(e) : 2; }();
+        const int PW = (sizeof(T) == 4 && cocc == 3) ? 3 : 4;  // three-value sphere rows: what lets a third CTA fit in shared memory
+        const size_t smem = sizeof(T) * ((size_t)(CH + 12) * 7 + 8 * 2 + (size_t)(std::min(CH, (int)p->T) + 6) * ((PW * S) | 1));
         if (smem > 220 * 1024) return set_error(RLITG_ERR_SHAPE, "too many spheres for the shared-memory tile");
         // FP32 build: chain walk of phase 1 in FP64 (accuracy of the 1 / dt^2 stencils, torm_coll.cuh); RLITG_TORM_FK64=0
-        // keeps it in FP32 (measurement knob).  Register budget: 2 CTAs/SM (128 regs) or 3 (96); RLITG_TORM_COLL_OCC
+        // keeps it in FP32 (measurement knob).  RLITG_TORM_COLL_OCC: 2 CTAs/SM (128 registers, four-value sphere rows with the
+        // cell index) or 3 (96 registers + three-value rows: 21 warps/SM, measured 125 vs 108 us -- more resident warps do
+        // not pay on this kernel)
         static const int fk64 = [] { const char* e = getenv("RLITG_TORM_FK64"); return e ? atoi(e) : 1; }();
-        static const int cocc = [] { const char* e = getenv("RLITG_TORM_COLL_OCC"); return e ? atoi(e) : 2; }();
         using KernT = void (*)(TormP<T>, const T*, SceneDev, int, const T*, int, int, const int32_t*, T*, T*, T*, float*,
                                const int32_t*);
         KernT kern;
         if constexpr (sizeof(T) == 4) {
-            if (cocc == 3) kern = fk64 ? torm_coll_kernel<T, true, 96> : torm_coll_kernel<T, false, 96>;
-            else kern = fk64 ? torm_coll_kernel<T, true, 128> : torm_coll_kernel<T, false, 128>;
+            if (cocc == 3) kern = fk64 ? torm_coll_kernel<T, true, 96, 3> : torm_coll_kernel<T, false, 96, 3>;
+            else kern = fk64 ? torm_coll_kernel<T, true, 128, 4> : torm_coll_kernel<T, false, 128, 4>;
         } else {
-            kern = torm_coll_kernel<T, false, 255>;
+            kern = torm_coll_kernel<T, false, 255, 4>;
         }
         {
             int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "torm_coll_kernel");

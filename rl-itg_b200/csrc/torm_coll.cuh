@@ -56,7 +56,7 @@ RLITG_DEV int bits_to_cell(float b) { return __float_as_int(b); }
 RLITG_DEV int bits_to_cell(double b) { return (int)__double_as_longlong(b); }
 
 // Chain visitor of phase 1.  FT = precision of the walk (double in the FP32 production build), T = storage precision.
-template <typename T, typename FT, bool kJoints>
+template <typename T, typename FT, bool kJoints, int PW = 4>
 struct CollVisit {
     V3<T> a[7], b[7];      // Jacobian table: column j of getJacobian (:1170-1178) = a_j x (x - o_j) = a_j x x + b_j
     T* pos_row;            // shared-memory row [S][4] of this waypoint's sphere centres (planning frame) + cell index bits
@@ -68,9 +68,11 @@ struct CollVisit {
     // centre + the linear index of its grid cell (-1 outside): the cell arithmetic sits here, next to the other spheres of
     // the link, instead of in front of every gather of phase 2's serial sphere loop
     RLITG_DEV void put(int s, V3<T> x) const {
-        T* d = pos_row + 4 * s;
+        T* d = pos_row + PW * s;
         d[0] = x.x; d[1] = x.y; d[2] = x.z;
-        if (gm != nullptr) d[3] = cell_to_bits((int)gm->cell(x), T(0));
+        if constexpr (PW == 4) {
+            if (gm != nullptr) d[3] = cell_to_bits((int)gm->cell(x), T(0));
+        }
     }
     template <int K>
     RLITG_DEV void operator()(jidx<K>, const FrameC<FT>& f) {
@@ -114,10 +116,10 @@ struct CollVisit {
 };
 
 // sphere centres of one halo row (chunked paths only): kept out of line so the chain walk is not inlined twice
-template <typename T, typename FT, bool kFk64>
+template <typename T, typename FT, bool kFk64, int PW = 4>
 __device__ __noinline__ void halo_sphere_row(const T* qrow, T* sph_row, const float4* sph, const int* link_start,
                                              FT ox, FT oy, FT oz, int quirk) {
-    CollVisit<T, FT, false> hv;
+    CollVisit<T, FT, false, PW> hv;
     hv.sph = sph; hv.link_start = link_start; hv.quirk = quirk;
     hv.off = {ox, oy, oz};
     hv.gm = nullptr;
@@ -129,17 +131,17 @@ __device__ __noinline__ void halo_sphere_row(const T* qrow, T* sph_row, const fl
 // nrow[k]: shared-memory rows of waypoints i-3 .. i+3 (clamped at the ends of the path, torm_trajectory.cpp:81-96).
 // NANC = joints that move the sphere (1..7): compile-time, so the masked joints cost nothing (the warp walks the spheres
 // in table order: the link, and with it NANC, is uniform over the warp).  acc -= z.
-template <typename T, int NANC>
+template <typename T, int NANC, int PW = 4>
 RLITG_DEV void coll_sphere(const TormP<T>& P, const float4 rec, const T pot, const T* const (&nrow)[7], const V3<T> (&ja)[7],
                            const V3<T> (&jb)[7], int s, T (&acc)[7]) {
-    const T* pc = nrow[3] + 4 * s;
+    const T* pc = nrow[3] + PW * s;
     const V3<T> xc = {pc[0], pc[1], pc[2]};
     // sphere velocity / acceleration: 7-point stencils across waypoints (:1364-1381), differenced against the centre row
     V3<T> vel = {T(0), T(0), T(0)}, ac = {T(0), T(0), T(0)};
 #pragma unroll
     for (int k = 0; k < 7; k++) {
         if (k == 3) continue;
-        const T* pk = nrow[k] + 4 * s;
+        const T* pk = nrow[k] + PW * s;
         const V3<T> d = {pk[0] - xc.x, pk[1] - xc.y, pk[2] - xc.z};
         vel = axpy(vel, P.rv[k], d);
         ac = axpy(ac, P.ra[k], d);
@@ -212,7 +214,7 @@ RLITG_DEV void coll_sphere(const TormP<T>& P, const float4 rec, const T pot, con
 
 // kFk64: the chain walk of phase 1 runs in FP64 inside the FP32 build (see the header); always T for the FP64 build.
 // Writes costs[5] and active[]; the other cost entries are zeroed when the pose / evaluator kernel does not run.
-template <typename T, bool kFk64, int MAXREG>
+template <typename T, bool kFk64, int MAXREG, int PW>
 __global__ void __launch_bounds__(kCollThreads) __maxnreg__(MAXREG)
 torm_coll_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S, const T* __restrict__ Aband, int stage_mask,
                  int zero_pose_costs, const int32_t* __restrict__ stoch, T* __restrict__ inc_smooth,
@@ -224,7 +226,7 @@ torm_coll_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S, con
     T* s_traj = reinterpret_cast<T*>(smem_raw);  // [(CH + 12)][7]
     T* s_red = s_traj + (CH + 12) * 7;           // [8][2]
     T* s_pos = s_red + 8 * 2;                    // [(min(CH, T) + 6)][PS] rows c0-3 .. c0+CH+2, PS = 4 S padded to odd
-    const int PS = (4 * S) | 1;                  // odd row stride: thread-per-row accesses are bank-conflict free
+    const int PS = (PW * S) | 1;                 // odd row stride: thread-per-row accesses are bank-conflict free
     __shared__ float4 s_sph[kMaxSpheres];
     __shared__ int s_start[kNumLinks + 1];
     __shared__ int s_nanc[kMaxSpheres];  // joints that move sphere s: min(link + 1, 7) (torm_optimizer.cpp:263-309)
@@ -289,7 +291,7 @@ torm_coll_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S, con
 
         // ---- phase 1: chain walk of this row -> Jacobian table in registers, sphere centres in shared memory
         //      (+ the halo rows of a chunked path)
-        CollVisit<T, FT, true> v;
+        CollVisit<T, FT, true, PW> v;
         v.sph = s_sph; v.link_start = s_start; v.quirk = P.quirk;
         v.off = {FT(P.off64[0]), FT(P.off64[1]), FT(P.off64[2])};
         v.gm = &gm;
@@ -300,13 +302,20 @@ torm_coll_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S, con
         if (tid < 6) {
             const int hr = tid < 3 ? c0 - 3 + tid : c0 + CH + (tid - 3);
             if (hr >= 0 && hr < Tn && (hr < c0 || hr >= c0 + CH) && (!row_only || abs(hr - stoch_row) <= 3))
-                halo_sphere_row<T, FT, kFk64>(TROW(hr), PROW(hr), s_sph, s_start, v.off.x, v.off.y, v.off.z, P.quirk);
+                halo_sphere_row<T, FT, kFk64, PW>(TROW(hr), PROW(hr), s_sph, s_start, v.off.x, v.off.y, v.off.z, P.quirk);
         }
         // the first two distance records of this row (its own cells, written above by this thread): issued before the
         // barrier so that their L2 round trip overlaps the wait for the slowest walker
         const uint32_t a_cell = smem_u32(PROW(i)) + 3 * (uint32_t)sizeof(T);
+        const T* prow_own = PROW(i);
         auto fetch = [&](int s) -> float4 {
-            const int c = lds_cell<T>(a_cell + (uint32_t)s * 4u * (uint32_t)sizeof(T));
+            int c;
+            if constexpr (PW == 4) {
+                c = lds_cell<T>(a_cell + (uint32_t)s * 4u * (uint32_t)sizeof(T));
+            } else {  // three-value rows (three resident CTAs per SM): the cell index is recomputed from the centre
+                const T* pp = prow_own + 3 * s;
+                c = (int)gm.cell(V3<T>{pp[0], pp[1], pp[2]});
+            }
             return c >= 0 ? __ldg(sc.field + c) : make_float4(1e30f, 0.f, 0.f, 0.f);
         };
         float4 r0 = make_float4(1e30f, 0.f, 0.f, 0.f), r1 = r0;
@@ -352,13 +361,13 @@ torm_coll_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S, con
                 if (!inc_row || pot < T(0.0001)) continue;
                 nact++;
                 switch (lds_s32(a_nanc + 4u * (uint32_t)s)) {  // uniform over the warp: every lane is on sphere s
-                    case 1: coll_sphere<T, 1>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
-                    case 2: coll_sphere<T, 2>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
-                    case 3: coll_sphere<T, 3>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
-                    case 4: coll_sphere<T, 4>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
-                    case 5: coll_sphere<T, 5>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
-                    case 6: coll_sphere<T, 6>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
-                    default: coll_sphere<T, 7>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
+                    case 1: coll_sphere<T, 1, PW>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
+                    case 2: coll_sphere<T, 2, PW>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
+                    case 3: coll_sphere<T, 3, PW>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
+                    case 4: coll_sphere<T, 4, PW>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
+                    case 5: coll_sphere<T, 5, PW>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
+                    case 6: coll_sphere<T, 6, PW>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
+                    default: coll_sphere<T, 7, PW>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
                 }
             }
             red[0] += csum;
