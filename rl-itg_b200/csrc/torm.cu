@@ -543,9 +543,9 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
                 cudaEventCreateWithFlags(&fk->join, cudaEventDisableTiming) != cudaSuccess)
                 return set_cuda_error("torm fork stream / events");
         }
-        if (cudaEventRecord(fk->fork, st) != cudaSuccess || cudaStreamWaitEvent(fk->side, fk->fork, 0) != cudaSuccess)
-            return set_cuda_error("torm fork");
         st_pose = fk->side;
+        if (cudaEventRecord(fk->fork, st) != cudaSuccess || cudaStreamWaitEvent(st_pose, fk->fork, 0) != cudaSuccess)
+            return set_cuda_error("torm fork");
     }
     // use_stochastic_descent_ inside the optimiser loop (RLITG_STAGE_COLL_ROW_ONLY): one waypoint per trajectory takes the
     // collision increment -> kernel 3c (a warp per trajectory, spheres on lanes); the smoothness stage, if asked for, keeps
@@ -570,6 +570,37 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
         rk<<<(unsigned)((N + kRowWarps - 1) / kRowWarps), kRowWarps * 32, smem, st>>>(P, traj, sd, S, zero, N, stoch, inc_coll,
                                                                                    costs, active, traj_stage);
         int rc = check_launch("torm_coll_row_kernel");
+        if (rc) return rc;
+    }
+    auto launch_pose = [&]() -> int {
+        const size_t smem = sizeof(T) * ((size_t)(CH + 12) * 7 + (size_t)(CH + 3) * 7 + 8 * kNRedPose);
+        // register budget of the pose kernel: 2 CTAs/SM (128 regs) or 3 (96 regs at 224 threads); RLITG_TORM_POSE_OCC
+        static const int occ = [] { const char* e = getenv("RLITG_TORM_POSE_OCC"); return e ? atoi(e) : 2; }();
+        using PoseK = void (*)(TormP<T>, const T*, const T*, int, int, T*, T*, const int32_t*);
+        constexpr int kR2 = sizeof(T) == 4 ? 128 : 255, kR3 = sizeof(T) == 4 ? 96 : 255, kRL = sizeof(T) == 4 ? 72 : 255;
+        const bool grad = (stage_mask & RLITG_STAGE_POSE_GRAD) != 0;
+        PoseK kern;
+        if (!grad) kern = frames ? torm_pose_eval_kernel<T, kRL, true, false> : torm_pose_eval_kernel<T, kRL, false, false>;
+        else if (frames) kern = (sizeof(T) == 4 && occ == 3) ? torm_pose_eval_kernel<T, kR3, true, true> : torm_pose_eval_kernel<T, kR2, true, true>;
+        else kern = (sizeof(T) == 4 && occ == 3) ? torm_pose_eval_kernel<T, kR3, false, true> : torm_pose_eval_kernel<T, kR2, false, true>;
+        {
+            int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "torm_pose_eval_kernel");
+            if (rc_attr) return rc_attr;
+        }
+        kern<<<(unsigned)N, CH, smem, st_pose>>>(P, traj, frames ? frames : targets, stage_mask,
+                                                 (run_coll || (stage_mask & RLITG_STAGE_KEEP_COSTS)) ? 0 : 1, inc_pose, costs,
+                                                 traj_stage);
+        return check_launch("torm_pose_eval_kernel");
+    };
+    // Launch order of the two concurrent kernels.  The heavy end-pose kernel (pinv step: 48 us alone, two CTAs per SM like
+    // the collision kernel) goes FIRST: the collision kernel's CTAs then move in as its CTAs retire and the two kernels'
+    // partial last waves overlap (full call 156.5 -> 146.6 us; a high-priority side stream gives 148.5).  The light
+    // evaluator-only kernel (23 us, four CTAs per SM) goes SECOND, into the gaps of the collision kernel: first, it would
+    // simply run ahead of it (feasible stage 130 vs 122 us).  RLITG_TORM_ORDER = 0 / 1 forces collision-first / pose-first.
+    static const int pose_first_env = [] { const char* e = getenv("RLITG_TORM_ORDER"); return e ? atoi(e) : -1; }();
+    const bool pose_first = pose_first_env < 0 ? (stage_mask & RLITG_STAGE_POSE_GRAD) != 0 : pose_first_env != 0;
+    if (run_pose && pose_first) {
+        int rc = launch_pose();
         if (rc) return rc;
     }
     if (run_coll && (coll_kernel_mask & (RLITG_STAGE_COLL | RLITG_STAGE_SMOOTH))) {
@@ -613,29 +644,12 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
         if (rc) return rc;
         stage_mask = stage_mask_pose;
     }
-    if (run_pose) {
-        const size_t smem = sizeof(T) * ((size_t)(CH + 12) * 7 + (size_t)(CH + 3) * 7 + 8 * kNRedPose);
-        // register budget of the pose kernel: 2 CTAs/SM (128 regs) or 3 (96 regs at 224 threads); RLITG_TORM_POSE_OCC
-        static const int occ = [] { const char* e = getenv("RLITG_TORM_POSE_OCC"); return e ? atoi(e) : 2; }();
-        using PoseK = void (*)(TormP<T>, const T*, const T*, int, int, T*, T*, const int32_t*);
-        constexpr int kR2 = sizeof(T) == 4 ? 128 : 255, kR3 = sizeof(T) == 4 ? 96 : 255, kRL = sizeof(T) == 4 ? 72 : 255;
-        const bool grad = (stage_mask & RLITG_STAGE_POSE_GRAD) != 0;
-        PoseK kern;
-        if (!grad) kern = frames ? torm_pose_eval_kernel<T, kRL, true, false> : torm_pose_eval_kernel<T, kRL, false, false>;
-        else if (frames) kern = (sizeof(T) == 4 && occ == 3) ? torm_pose_eval_kernel<T, kR3, true, true> : torm_pose_eval_kernel<T, kR2, true, true>;
-        else kern = (sizeof(T) == 4 && occ == 3) ? torm_pose_eval_kernel<T, kR3, false, true> : torm_pose_eval_kernel<T, kR2, false, true>;
-        {
-            int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "torm_pose_eval_kernel");
-            if (rc_attr) return rc_attr;
-        }
-        kern<<<(unsigned)N, CH, smem, st_pose>>>(P, traj, frames ? frames : targets, stage_mask,
-                                                 (run_coll || (stage_mask & RLITG_STAGE_KEEP_COSTS)) ? 0 : 1, inc_pose, costs,
-                                                 traj_stage);
-        int rc = check_launch("torm_pose_eval_kernel");
+    if (run_pose && !pose_first) {
+        int rc = launch_pose();
         if (rc) return rc;
     }
     if (fk) {
-        if (cudaEventRecord(fk->join, fk->side) != cudaSuccess || cudaStreamWaitEvent(st, fk->join, 0) != cudaSuccess)
+        if (cudaEventRecord(fk->join, st_pose) != cudaSuccess || cudaStreamWaitEvent(st, fk->join, 0) != cudaSuccess)
             return set_cuda_error("torm join");
     }
     return RLITG_OK;
