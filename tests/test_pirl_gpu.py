@@ -38,19 +38,20 @@ def build_case(B, T, seed, with_scene, cuda_device):
 
 
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
-@pytest.mark.parametrize("reward_type,obs_type,t,z,with_scene,refine", [
-    ("Task+NullSpaceImitation", "Conf+LinkPoses", 1, 0, False, False),  # the trained setting (88-d obs): the fast-path kernel
-    ("Task+NullSpaceImitation", "Conf+LinkPoses", 1, 0, True, False),   # same with a scene: the row is re-assembled after a collision
-    ("Task+NullSpaceImitation", "Conf+LinkPoses", 1, 32, True, False),  # obs scenes: 120-d obs + collision
-    ("Task+Imitation", "Conf+EE", 3, 0, True, False),
-    ("Imitation", "onlyConf", 2, 4, False, False),
-    ("Task", "onlyLinkPoses", 1, 0, False, True),
+@pytest.mark.parametrize("reward_type,obs_type,t,z,with_scene,refine,B", [
+    ("Task+NullSpaceImitation", "Conf+LinkPoses", 1, 0, False, False, 3001),  # the trained setting (88-d obs): the fast-path kernel
+    ("Task+NullSpaceImitation", "Conf+LinkPoses", 1, 0, False, False, 16384),  # BASELINE config 3: the benchmarked batch
+    ("Task+NullSpaceImitation", "Conf+LinkPoses", 1, 0, True, False, 3001),   # same with a scene: the row is re-assembled after a collision
+    ("Task+NullSpaceImitation", "Conf+LinkPoses", 1, 32, True, False, 3001),  # obs scenes: 120-d obs + collision
+    ("Task+Imitation", "Conf+EE", 3, 0, True, False, 3001),
+    ("Imitation", "onlyConf", 2, 4, False, False, 3001),
+    ("Task", "onlyLinkPoses", 1, 0, False, True, 3001),
 ])
-def test_env_step_parity(cuda_device, dtype, reward_type, obs_type, t, z, with_scene, refine):
+def test_env_step_parity(cuda_device, dtype, reward_type, obs_type, t, z, with_scene, refine, B):
     import torch
     from oracle import oracle as O
     from rlitg_b200 import pirl_env as P
-    B, T = 3001, 40
+    T = 40
     c = build_case(B, T, 5, with_scene, cuda_device)
     rng = np.random.default_rng(9)
     latent = rng.normal(size=(B, z)) if z else None
@@ -78,7 +79,7 @@ def test_env_step_parity(cuda_device, dtype, reward_type, obs_type, t, z, with_s
                (np.abs(e[:, 1] - 0.104) < 30 * tol) | (np.abs(e[:, 2] - 0.087) < tol)
         flag_mism = (g["flags"] != want["flags"]).any(axis=1)
         bad = flag_mism & ~near
-        assert bad.sum() <= (0 if f64 else 3), (int(bad.sum()), np.nonzero(bad)[0][:5])
+        assert bad.sum() <= (0 if f64 else 3 * (1 + B // 4096)), (int(bad.sum()), np.nonzero(bad)[0][:5])
         ok = ~flag_mism
         assert ok.mean() > 0.995
         if mode == "train":
