@@ -7,8 +7,15 @@
 //   pirl/src/kinematic_solver.cpp:332-351) -> reward / done / info flags :226-282.
 // The same observation math exists in C++ at torm/src/pirl_interpolator.cpp:176-274 (float32 output).
 //
-// HBM-bound in principle (536 B/env at the trained setting), launch/latency-bound at 16k envs.  Observation rows
-// are staged in shared memory (odd row stride -> conflict-free) and written back coalesced.
+// HBM-bound from ~256k envs on (536 B/env at the trained setting: 67 % of the measured HBM peak at 1M envs),
+// latency-bound at 16k envs (one wave of 4-warp SMs).  What round 2's per-instruction stall samples changed
+// (tools/ncu_sass_stalls.py, profiles/r02_pirl_*_stalls*.txt):
+//   * load schedule: q / action / timestep / max_timestep are issued together and consumed together, then the three
+//     table rows the timestep points at go out under the chain walk (ld_issue, load_row7);
+//   * the table rows are 32-byte records read with one L2-only 256-bit load each;
+//   * trained layout (kFast): the observation row is assembled in registers four values at a time (RowW) and each warp
+//     drains its 32 rows with one bulk store issued before the reward arithmetic;
+//   * other layouts: rows staged in shared memory at an odd stride (conflict-free), 128-bit cooperative copy-out.
 #include <climits>
 #include <cstdlib>
 #include <type_traits>
