@@ -256,7 +256,7 @@ template <typename T, int MAXREG, bool kFrames, bool kGrad>
 __global__ void __launch_bounds__(kTormMaxThreads) __maxnreg__(MAXREG)
 torm_pose_eval_kernel(TormP<T> P, const T* __restrict__ traj, const T* __restrict__ targets, int stage_mask,
                       int zero_coll_cost, T* __restrict__ inc_pose, T* __restrict__ costs,
-                      const int32_t* __restrict__ traj_stage) {
+                      const int32_t* __restrict__ traj_stage, const T* __restrict__ Aband, T* __restrict__ inc_smooth) {
     const int CH = blockDim.x, tid = threadIdx.x, Tn = P.Tn;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* s_traj = reinterpret_cast<T*>(smem_raw);  // [(CH + 12)][7]  rows c0-6 .. c0+CH+5, clamped
@@ -280,6 +280,23 @@ torm_pose_eval_kernel(TormP<T> P, const T* __restrict__ traj, const T* __restric
         __syncthreads();
         const int i = c0 + tid;
         const bool valid = i < Tn;
+        // ---- smoothness increments -(2 A_full x) on the free rows (torm_optimizer.cpp:1466-1473), when this launch is
+        //      given the band: the trajectory window is already here, and the collision kernel (or, with one stochastic
+        //      waypoint per trajectory, a whole extra 15 us launch of it) is spared the 13-tap band
+        if (Aband != nullptr && inc_smooth != nullptr && valid && i >= 1 && (!traj_stage || traj_stage[n] == 0)) {
+            const T* ab = Aband + (size_t)(i + 5) * 13;
+            T* o_smooth = inc_smooth + n * (int64_t)(Tn - 1) * 7;
+            T coef[13];
+#pragma unroll
+            for (int k = 0; k < 13; k++) coef[k] = ab[k];
+#pragma unroll
+            for (int j = 0; j < 7; j++) {
+                T sacc = T(0);
+#pragma unroll
+                for (int k = 0; k < 13; k++) sacc += coef[k] * (T(2) * TROW(i + k - 6)[j]);
+                o_smooth[(i - 1) * 7 + j] = -sacc;
+            }
+        }
         T q[7];
         if (valid) {
 #pragma unroll
@@ -551,7 +568,15 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
     // collision increment -> kernel 3c (a warp per trajectory, spheres on lanes); the smoothness stage, if asked for, keeps
     // the thread-per-waypoint kernel without its collision part
     const bool row_only = (stage_mask & RLITG_STAGE_COLL) && (stage_mask & RLITG_STAGE_COLL_ROW_ONLY) && stoch && inc_coll;
-    int coll_kernel_mask = stage_mask;
+    // the smoothness band rides in the end-pose / evaluator kernel whenever that kernel runs (RLITG_TORM_SMOOTH_IN_POSE=0:
+    // always in the collision kernel)
+    static const int sip = [] { const char* e = getenv("RLITG_TORM_SMOOTH_IN_POSE"); return e ? atoi(e) : 1; }();
+    const bool smooth_in_pose = sip && run_pose && (stage_mask & RLITG_STAGE_SMOOTH) && inc_smooth != nullptr && smooth != nullptr;
+    const T* pose_band = smooth_in_pose
+        ? reinterpret_cast<const T*>(sizeof(T) == 4 ? (const void*)smooth->d_band32 : (const void*)smooth->d_band64) : nullptr;
+    int coll_kernel_mask = smooth_in_pose ? (stage_mask & ~RLITG_STAGE_SMOOTH) : stage_mask;
+    // does any kernel of the collision side run (and own costs[5])?
+    const bool coll_side_runs = row_only || (run_coll && (coll_kernel_mask & (RLITG_STAGE_COLL | RLITG_STAGE_SMOOTH)) != 0);
     if (row_only) {
         static const int fk64r = [] { const char* e = getenv("RLITG_TORM_FK64"); return e ? atoi(e) : 1; }();
         SceneDev sd = scene_dev(scene);
@@ -563,7 +588,7 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
         else rk = torm_coll_row_kernel<T, false>;
         int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(rk), smem, "torm_coll_row_kernel");
         if (rc_attr) return rc_attr;
-        coll_kernel_mask = stage_mask & ~RLITG_STAGE_COLL;
+        coll_kernel_mask &= ~RLITG_STAGE_COLL;
         const bool other_coll_kernel = (coll_kernel_mask & RLITG_STAGE_SMOOTH) != 0;
         // who zeroes what: 1 = costs[5] only, 2 = the pose entries too; nothing when the smoothness launch below does it
         const int zero = other_coll_kernel ? 0 : ((run_pose || (stage_mask & RLITG_STAGE_KEEP_COSTS)) ? 1 : 2);
@@ -576,7 +601,7 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
         const size_t smem = sizeof(T) * ((size_t)(CH + 12) * 7 + (size_t)(CH + 3) * 7 + 8 * kNRedPose);
         // register budget of the pose kernel: 2 CTAs/SM (128 regs) or 3 (96 regs at 224 threads); RLITG_TORM_POSE_OCC
         static const int occ = [] { const char* e = getenv("RLITG_TORM_POSE_OCC"); return e ? atoi(e) : 2; }();
-        using PoseK = void (*)(TormP<T>, const T*, const T*, int, int, T*, T*, const int32_t*);
+        using PoseK = void (*)(TormP<T>, const T*, const T*, int, int, T*, T*, const int32_t*, const T*, T*);
         constexpr int kR2 = sizeof(T) == 4 ? 128 : 255, kR3 = sizeof(T) == 4 ? 96 : 255, kRL = sizeof(T) == 4 ? 72 : 255;
         const bool grad = (stage_mask & RLITG_STAGE_POSE_GRAD) != 0;
         PoseK kern;
@@ -588,8 +613,9 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
             if (rc_attr) return rc_attr;
         }
         kern<<<(unsigned)N, CH, smem, st_pose>>>(P, traj, frames ? frames : targets, stage_mask,
-                                                 (run_coll || (stage_mask & RLITG_STAGE_KEEP_COSTS)) ? 0 : 1, inc_pose, costs,
-                                                 traj_stage);
+                                                 (coll_side_runs || (stage_mask & RLITG_STAGE_KEEP_COSTS)) ? 0 : 1, inc_pose, costs,
+                                                 traj_stage, smooth_in_pose ? pose_band : nullptr,
+                                                 smooth_in_pose ? inc_smooth : nullptr);
         return check_launch("torm_pose_eval_kernel");
     };
     // Launch order of the two concurrent kernels.  The heavy end-pose kernel (pinv step: 48 us alone, two CTAs per SM like

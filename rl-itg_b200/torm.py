@@ -444,15 +444,18 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
         else:
             ts = None
             pose_mask, coll_mask = STAGE_POSE_GRAD | STAGE_EVAL, 0
+        # the smoothness band rides in the end-pose / evaluator launch (it has the trajectory window in shared memory
+        # anyway); what is left for the second call is the collision stage
+        smooth_mask, coll_mask = coll_mask & STAGE_SMOOTH, coll_mask & ~STAGE_SMOOTH
         two = bool(overlap and (coll_mask or need_point))
         if two:
             ev_fork.record(cur_stream)
             side.wait_event(ev_fork)
             with torch.cuda.stream(side):
-                r = self.cost_grad(traj, pose_mask | (KEEP if coll_mask else 0), traj_stage=ts)
+                r = self.cost_grad(traj, pose_mask | smooth_mask | (KEEP if coll_mask else 0), traj_stage=ts)
                 ev_join.record(side)
         else:
-            r = self.cost_grad(traj, pose_mask | (KEEP if coll_mask else 0), traj_stage=ts)
+            r = self.cost_grad(traj, pose_mask | smooth_mask | (KEEP if coll_mask else 0), traj_stage=ts)
         if need_point:
             with _lib.on_device(dev):
                 check(lib.rlitg_torm_collision_point(traj.data_ptr(), N, self.T, code, self.scene.handle, base_off,
@@ -480,8 +483,9 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
                                           None, lr_iter.data_ptr() if mode == 2 else None, C.byref(sch[stage]),
                                           cur_stream.cuda_stream))
         # ---- increments -> trajectory (:562-576)
-        if rc is not None:
-            inc_s, inc_c = rc["inc_smooth"], (rc["inc_coll"] if rc["inc_coll"] is not None else zeros)
+        if smooth_mask:
+            inc_s = r["inc_smooth"]
+            inc_c = rc["inc_coll"] if (rc is not None and rc["inc_coll"] is not None) else zeros
         else:
             inc_s = inc_c = None
         if mode == 1:
