@@ -539,6 +539,19 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
     const bool run_pose = (stage_mask & (RLITG_STAGE_POSE | RLITG_STAGE_POSE_GRAD | RLITG_STAGE_EVAL)) != 0;
     const bool run_coll = (stage_mask & (RLITG_STAGE_COLL | RLITG_STAGE_SMOOTH)) != 0;
     if (!run_pose && !run_coll) return set_error(RLITG_ERR_ARG, "stage_mask selects no stage");
+    // use_stochastic_descent_ inside the optimiser loop (RLITG_STAGE_COLL_ROW_ONLY): one waypoint per trajectory takes the
+    // collision increment -> kernel 3c (a warp per trajectory, spheres on lanes); the smoothness stage, if asked for, keeps
+    // the thread-per-waypoint kernel without its collision part
+    const bool row_only = (stage_mask & RLITG_STAGE_COLL) && (stage_mask & RLITG_STAGE_COLL_ROW_ONLY) && stoch && inc_coll;
+    // the smoothness band rides in the end-pose / evaluator kernel whenever that kernel runs (RLITG_TORM_SMOOTH_IN_POSE=0:
+    // always in the collision kernel)
+    static const int sip = [] { const char* e = getenv("RLITG_TORM_SMOOTH_IN_POSE"); return e ? atoi(e) : 1; }();
+    const bool smooth_in_pose = sip && run_pose && (stage_mask & RLITG_STAGE_SMOOTH) && inc_smooth != nullptr && smooth != nullptr;
+    const T* pose_band = smooth_in_pose
+        ? reinterpret_cast<const T*>(sizeof(T) == 4 ? (const void*)smooth->d_band32 : (const void*)smooth->d_band64) : nullptr;
+    int coll_kernel_mask = smooth_in_pose ? (stage_mask & ~RLITG_STAGE_SMOOTH) : stage_mask;
+    // does any kernel of the collision side run (and own costs[5])?
+    const bool coll_side_runs = row_only || (run_coll && (coll_kernel_mask & (RLITG_STAGE_COLL | RLITG_STAGE_SMOOTH)) != 0);
     // When both kernels run they are forked onto two streams (joined again before returning to the caller's
     // stream order): the pose kernel's CTAs fill the SMs that the collision kernel's last, partial wave leaves idle.
     // The side stream and its two events are shared by every caller on a device, so the fork .. join sequence is
@@ -549,7 +562,7 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
     static const int concurrent = [] { const char* e = getenv("RLITG_TORM_CONCURRENT"); return e ? atoi(e) : 1; }();
     cudaStream_t st_pose = st;
     Fork* fk = nullptr;
-    if (run_pose && run_coll && concurrent) {
+    if (run_pose && coll_side_runs && concurrent) {
         int dev = 0;
         cudaGetDevice(&dev);
         fk = &forks[dev & 63];
@@ -564,19 +577,6 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
         if (cudaEventRecord(fk->fork, st) != cudaSuccess || cudaStreamWaitEvent(st_pose, fk->fork, 0) != cudaSuccess)
             return set_cuda_error("torm fork");
     }
-    // use_stochastic_descent_ inside the optimiser loop (RLITG_STAGE_COLL_ROW_ONLY): one waypoint per trajectory takes the
-    // collision increment -> kernel 3c (a warp per trajectory, spheres on lanes); the smoothness stage, if asked for, keeps
-    // the thread-per-waypoint kernel without its collision part
-    const bool row_only = (stage_mask & RLITG_STAGE_COLL) && (stage_mask & RLITG_STAGE_COLL_ROW_ONLY) && stoch && inc_coll;
-    // the smoothness band rides in the end-pose / evaluator kernel whenever that kernel runs (RLITG_TORM_SMOOTH_IN_POSE=0:
-    // always in the collision kernel)
-    static const int sip = [] { const char* e = getenv("RLITG_TORM_SMOOTH_IN_POSE"); return e ? atoi(e) : 1; }();
-    const bool smooth_in_pose = sip && run_pose && (stage_mask & RLITG_STAGE_SMOOTH) && inc_smooth != nullptr && smooth != nullptr;
-    const T* pose_band = smooth_in_pose
-        ? reinterpret_cast<const T*>(sizeof(T) == 4 ? (const void*)smooth->d_band32 : (const void*)smooth->d_band64) : nullptr;
-    int coll_kernel_mask = smooth_in_pose ? (stage_mask & ~RLITG_STAGE_SMOOTH) : stage_mask;
-    // does any kernel of the collision side run (and own costs[5])?
-    const bool coll_side_runs = row_only || (run_coll && (coll_kernel_mask & (RLITG_STAGE_COLL | RLITG_STAGE_SMOOTH)) != 0);
     if (row_only) {
         static const int fk64r = [] { const char* e = getenv("RLITG_TORM_FK64"); return e ? atoi(e) : 1; }();
         SceneDev sd = scene_dev(scene);

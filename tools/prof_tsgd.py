@@ -80,7 +80,7 @@ def main():
                 for overlap in (True, False):
                     tw.copy_(traj)
                     tb.localOptimizeTSGD(tw, 3, lr_schedule_mode=mode, use_cuda_graph=use_graph, stochastic=stoch, overlap=overlap)
-                    iters = 60
+                    iters = 600 if use_graph else 60   # a graph is captured per call: amortise the capture (~10 ms)
                     tw.copy_(traj)
                     torch.cuda.synchronize(); t0 = time.perf_counter()
                     tb.localOptimizeTSGD(tw, iters, lr_schedule_mode=mode, use_cuda_graph=use_graph, stochastic=stoch, overlap=overlap)
