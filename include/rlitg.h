@@ -186,9 +186,12 @@ typedef struct RlitgPirlCfg {
     double thr_early_stop, thr_dist, thr_rot, thr_imitate, zero_task_dist; /* (:123-128) */
     double dist_p[4], rot_p[4], imit_p[4], null_p[4];                      /* (:165-168) */
     double w_col, w_jlimit, w_early_stop;                                  /* (:170-172) */
-    int32_t row_floats;     /* values per row of the targets / demos tables: 0 or 7 = packed [B,Tmax,7]; 8 = rows padded to
-                               [B,Tmax,8] (32-byte rows, 32-byte aligned tables: one whole DRAM sector per FP32 row) */
-    int32_t reserved_;
+    int32_t row_floats;     /* values per entry of the targets / demos tables: 0 or 7 = packed [B,Tmax,7]; 8 = rows padded to
+                               [B,Tmax,8] (32-byte rows, 32-byte aligned tables); 32 = STEP RECORDS: targets is [B,Tmax,32] with
+                               entry (b,t) = [target(t) 7 + pad | demo(t) 7 + pad | target(min(t+1, Tmax-1)) 7 + pad | pad 8]
+                               (128 bytes in FP32, 128-byte aligned), the demos argument is ignored.  A per-thread gather costs a
+                               whole 128-byte line on the B200, so everything one env step reads of the tables sits in one line */
+    int32_t record_has_demo; /* row_floats = 32 only: the records' demo slots are valid (demonstrations were given) */
 } RlitgPirlCfg;
 
 /* Observation length for a configuration (PirlEnv.py:79-89). */

@@ -39,7 +39,8 @@ struct PirlCfgT {
     T dist_p[4], rot_p[4], imit_p[4], null_p[4];
     T w_col, w_jl, w_es;
     int O;   // observation length
-    int RS;  // floats per target / demo row: 7, or 8 (rows padded to 32 bytes: every row is one or two whole DRAM sectors)
+    int RS;  // floats per entry of the targets table: 7 (packed rows), 8 (32-byte rows) or 32 (128-byte step records)
+    int rec_has_demo;  // RS = 32: the records carry demonstration rows
 };
 
 static int obs_dim_of(const RlitgPirlCfg& c) {
@@ -64,7 +65,8 @@ static PirlCfgT<T> convert_cfg(const RlitgPirlCfg& c) {
     for (int k = 0; k < 4; k++) { o.dist_p[k] = (T)c.dist_p[k]; o.rot_p[k] = (T)c.rot_p[k]; o.imit_p[k] = (T)c.imit_p[k]; o.null_p[k] = (T)c.null_p[k]; }
     o.w_col = (T)c.w_col; o.w_jl = (T)c.w_jlimit; o.w_es = (T)c.w_early_stop;
     o.O = obs_dim_of(c);
-    o.RS = c.row_floats == 8 ? 8 : 7;
+    o.RS = c.row_floats == 8 ? 8 : (c.row_floats == 32 ? 32 : 7);
+    o.rec_has_demo = c.record_has_demo;
     return o;
 }
 
@@ -89,9 +91,9 @@ RLITG_DEV int ld_issue(const int32_t* p) { int v; asm volatile("ld.global.s32 %0
 // [B,Tmax,7] table start at multiples of 28 bytes: 1.41 x the algorithmic DRAM traffic at 1M envs, round 1).
 // The row width is a template parameter: as a run-time branch both paths were if-converted into predicated loads of
 // the same registers, and the second set waited for the first to land (a fourth round trip).
-template <typename T, bool kRow8>
+template <typename T, int kRW>
 RLITG_DEV void load_row7(const T* __restrict__ row, T (&o)[7]) {
-    if constexpr (kRow8) {
+    if constexpr (kRW != 7) {
         if constexpr (sizeof(T) == 4) {
             // one 256-bit load (sm_100: LDG.E.256) = one request for the row's single 32-byte sector
             // L2-only (.cg): a 32-byte gather has no reuse in L1, and keeping the gathers out of it took the 1M-env step from
@@ -225,7 +227,7 @@ struct PirlVisit {
 // shared-memory stores into densely packed rows and every warp drains its 32 rows with one bulk store (TMA), without a
 // CTA barrier and without the copy-out loop (410 of 2,170 instructions per thread, and the instruction footprint of the
 // thread drops below the 32 KB instruction cache: 43 % of the stall samples at 16,384 envs were instruction fetches)
-template <typename T, bool kStep, int TILE, int MINB, bool kLinkObs, bool kRow8, bool kFast>
+template <typename T, bool kStep, int TILE, int MINB, bool kLinkObs, int kRW, bool kFast>
 __global__ void __launch_bounds__(TILE, MINB) pirl_env_kernel(
     PirlCfgT<T> cfg, int64_t B, T* __restrict__ q, const float* __restrict__ action, int32_t* __restrict__ timestep,
     const int32_t* __restrict__ max_timestep, const T* __restrict__ targets, const T* __restrict__ demos, int Tmax,
@@ -262,7 +264,11 @@ __global__ void __launch_bounds__(TILE, MINB) pirl_env_kernel(
         }
         int ts = ld_issue(timestep + b);
         const int mts = ld_issue(max_timestep + b);
-        constexpr int RS = kRow8 ? 8 : 7;
+        // kRW = 32: 128-byte step records [target(t) | demo(t) | target(min(t + 1, Tmax - 1)) | pad], one per (env, t).
+        // A per-thread gather costs a whole 128-byte line on this part whatever its size (tools/probes/gather_probe.cu:
+        // 4 L2 sectors and 128 DRAM bytes per 32-byte -- or 16-byte -- row), so the three rows a step needs sit in ONE line
+        constexpr int RS = kRW;
+        const bool has_demo = kRW == 32 ? cfg.rec_has_demo != 0 : demos != nullptr;
         const T* tg = targets + (int64_t)b * Tmax * RS;
 
         const int ot = cfg.obs_type;
@@ -306,12 +312,17 @@ __global__ void __launch_bounds__(TILE, MINB) pirl_env_kernel(
             ts += 1;
             {
                 const int tsp = min(max(ts, 0), Tmax - 1);
-                load_row7<T, kRow8>(tg + (size_t)tsp * RS, pf_tp);
-                if (demos != nullptr) load_row7<T, kRow8>(demos + ((int64_t)b * Tmax + tsp) * RS, pf_dm);
+                load_row7<T, kRW>(tg + (size_t)tsp * RS, pf_tp);
+                if (has_demo) {
+                    if constexpr (kRW == 32) load_row7<T, kRW>(tg + (size_t)tsp * RS + 8, pf_dm);
+                    else load_row7<T, kRW>(demos + ((int64_t)b * Tmax + tsp) * RS, pf_dm);
+                }
                 if (counters) pf_cnt = __ldcg(reinterpret_cast<const int4*>(counters + b * 4));
                 if constexpr (kFast) {
                     const int tf = min(max(min(ts + 1, mts), 0), Tmax - 1);
-                    load_row7<T, kRow8>(tg + (size_t)tf * RS, pf_ft);
+                    // records: the future target of step t is slot 2 of the record just read, except at the end of a path
+                    if (kRW == 32 && tf == tsp + 1) load_row7<T, kRW>(tg + (size_t)tsp * RS + 16, pf_ft);
+                    else load_row7<T, kRW>(tg + (size_t)tf * RS, pf_ft);
                 }
             }
             // one walk of the configuration the step will keep: the clipped candidate (test mode, or inside the
@@ -339,7 +350,7 @@ __global__ void __launch_bounds__(TILE, MINB) pirl_env_kernel(
         } else {
             if constexpr (kFast) {
                 const int tf = min(max(min(ts + 1, mts), 0), Tmax - 1);
-                load_row7<T, kRow8>(tg + (size_t)tf * RS, pf_ft);
+                load_row7<T, kRW>(tg + (size_t)tf * RS, pf_ft);
                 put_conf<T>(v.rw, cur);
             }
             walk_chain<T, 7>(cur, v);
@@ -382,7 +393,9 @@ __global__ void __launch_bounds__(TILE, MINB) pirl_env_kernel(
                 if (t > mts) t = mts;
                 t = min(max(t, 0), Tmax - 1);  // memory-safety guard: a caller stepping a finished episode stays in its path
                 T t7[7];
-                load_row7<T, kRow8>(tg + (size_t)t * RS, t7);
+                const int tbase = min(max(ts, 0), Tmax - 1);  // kStep: the record of this step (ts is already incremented)
+                if (kRW == 32 && kStep && i == 0 && t == tbase + 1) load_row7<T, kRW>(tg + (size_t)tbase * RS + 16, t7);
+                else load_row7<T, kRW>(tg + (size_t)t * RS, t7);
                 // calc_pos_and_rot_error :335-349: R_ct = tM inv(eM); columns 0 and 1
                 V3<T> m0, m1, m2;
                 npq_rot(t7, m0, m1, m2);
@@ -420,7 +433,7 @@ __global__ void __launch_bounds__(TILE, MINB) pirl_env_kernel(
 
             // ---- imitation :515-526 and null-space imitation :528-539
             T imitate_rwd = T(0), imitate_err = T(0), null_rwd = T(0), null_obj = T(0);
-            if (demos != nullptr) {
+            if (has_demo) {
                 const T* dm = pf_dm;
                 T ce[7];
                 T l1 = T(0);
@@ -569,7 +582,7 @@ RLITG_DEV void group_fk(T qv, int l, unsigned gmask, T* __restrict__ sc, T* __re
     __syncwarp(gmask);
 }
 
-template <typename T, bool kStep, bool kRow8>
+template <typename T, bool kStep, int kRW>
 __global__ void __launch_bounds__(kLaneEnvs * 8) pirl_env_lanes_kernel(
     PirlCfgT<T> cfg, int64_t B, T* __restrict__ q, const float* __restrict__ action, int32_t* __restrict__ timestep,
     const int32_t* __restrict__ max_timestep, const T* __restrict__ targets, const T* __restrict__ demos, int Tmax,
@@ -599,7 +612,8 @@ __global__ void __launch_bounds__(kLaneEnvs * 8) pirl_env_lanes_kernel(
     T* fr = s_fr + g * 96;
     T* scv = s_sc + g * 14;
     T* row = s_obs + (size_t)g * O;
-    constexpr int RS = kRow8 ? 8 : 7;
+    constexpr int RS = kRW;
+    const bool has_demo = kRW == 32 ? cfg.rec_has_demo != 0 : demos != nullptr;
     const T* tg = targets + (int64_t)b * Tmax * RS;
     const int ot = cfg.obs_type;
 
@@ -630,8 +644,11 @@ __global__ void __launch_bounds__(kLaneEnvs * 8) pirl_env_lanes_kernel(
         const bool no_out = (__ballot_sync(gmask, ok) & gmask) == gmask;
         ts += 1;
         const int tsp = min(max(ts, 0), Tmax - 1);
-        load_row7<T, kRow8>(tg + (size_t)tsp * RS, tp);  // every lane holds the whole row (one broadcast transaction per load)
-        if (demos != nullptr) load_row7<T, kRow8>(demos + ((int64_t)b * Tmax + tsp) * RS, dm);
+        load_row7<T, kRW>(tg + (size_t)tsp * RS, tp);  // every lane holds the whole row (one broadcast transaction per load)
+        if (has_demo) {
+            if constexpr (kRW == 32) load_row7<T, kRW>(tg + (size_t)tsp * RS + 8, dm);
+            else load_row7<T, kRW>(demos + ((int64_t)b * Tmax + tsp) * RS, dm);
+        }
         if (counters && l < 4) cnt = counters[b * 4 + l];
         if (cfg.train_mode) {
             if (no_out) {
@@ -688,7 +705,9 @@ __global__ void __launch_bounds__(kLaneEnvs * 8) pirl_env_lanes_kernel(
         if (t > mts) t = mts;
         t = min(max(t, 0), Tmax - 1);  // memory-safety guard: a caller stepping a finished episode stays in its path
         T t7[7];
-        load_row7<T, kRow8>(tg + (size_t)t * RS, t7);
+        const int tbase = min(max(ts, 0), Tmax - 1);
+        if (kRW == 32 && kStep && i == 0 && t == tbase + 1) load_row7<T, kRW>(tg + (size_t)tbase * RS + 16, t7);
+        else load_row7<T, kRW>(tg + (size_t)t * RS, t7);
         // calc_pos_and_rot_error :335-349: R_ct = tM inv(eM); columns 0 and 1
         V3<T> m0, m1, m2;
         npq_rot(t7, m0, m1, m2);
@@ -722,7 +741,7 @@ __global__ void __launch_bounds__(kLaneEnvs * 8) pirl_env_lanes_kernel(
 
         // ---- imitation :515-526 and null-space imitation :528-539, joint l on lane l
         T imitate_rwd = T(0), imitate_err = T(0), null_rwd = T(0), null_obj = T(0);
-        if (demos != nullptr) {
+        if (has_demo) {
             T e = T(0);
             if (l < 7) {
                 T dv = dm[0];
@@ -819,7 +838,8 @@ static int launch_pirl(const RlitgPirlCfg* cfg, int64_t B, T* q, const float* ac
     // instructions against 1.1 M) -- so the switch point sits at 2,048; RLITG_PIRL_LANES_MAX moves it
     static const int64_t lanes_max = [] { const char* e = getenv("RLITG_PIRL_LANES_MAX"); return e ? atoll(e) : 2048ll; }();
     if (B <= lanes_max && c.O <= 1024) {
-        auto kl = c.RS == 8 ? pirl_env_lanes_kernel<T, kStep, true> : pirl_env_lanes_kernel<T, kStep, false>;
+        auto kl = c.RS == 32 ? pirl_env_lanes_kernel<T, kStep, 32>
+                             : (c.RS == 8 ? pirl_env_lanes_kernel<T, kStep, 8> : pirl_env_lanes_kernel<T, kStep, 7>);
         const size_t sm = sizeof(T) * kLaneEnvs * (size_t)(96 + 14 + c.O);
         int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kl), sm, "pirl_env_lanes_kernel");
         if (rc_attr) return rc_attr;
@@ -837,7 +857,6 @@ static int launch_pirl(const RlitgPirlCfg* cfg, int64_t B, T* q, const float* ac
     // staged observation rows (89 floats per env in the trained setting) shared memory allows 6 x 96 = 18 or 2 x 320 = 20
     // warps/SM at 96 registers, and both measured SLOWER at 1M envs (197 / 216 vs 168 us).
     const bool link_obs = c.obs_type == 1 || c.obs_type == 3;
-    const bool row8 = c.RS == 8;
     constexpr int tile = kEnvTile;
     constexpr int kMinB = sizeof(T) == 4 ? 4 : 1;
     using EnvK = void (*)(PirlCfgT<T>, int64_t, T*, const float*, int32_t*, const int32_t*, const T*, const T*, int, const T*,
@@ -847,9 +866,13 @@ static int launch_pirl(const RlitgPirlCfg* cfg, int64_t B, T* q, const float* ac
     const bool fast = pfast && c.obs_type == 1 && c.n_future == 1 && c.z_dim == 0 && (reinterpret_cast<uintptr_t>(obs) & 15) == 0;
     EnvK kern;
     constexpr int kMinBF = sizeof(T) == 4 ? 5 : 1;
-    if (fast) kern = row8 ? pirl_env_kernel<T, kStep, tile, kMinBF, true, true, true> : pirl_env_kernel<T, kStep, tile, kMinBF, true, false, true>;
-    else if (link_obs) kern = row8 ? pirl_env_kernel<T, kStep, tile, kMinB, true, true, false> : pirl_env_kernel<T, kStep, tile, kMinB, true, false, false>;
-    else kern = row8 ? pirl_env_kernel<T, kStep, tile, kMinB, false, true, false> : pirl_env_kernel<T, kStep, tile, kMinB, false, false, false>;
+#define RLITG_PIRL_PICK(MB, LO, FA) \
+    (c.RS == 32 ? pirl_env_kernel<T, kStep, tile, MB, LO, 32, FA> \
+                : (c.RS == 8 ? pirl_env_kernel<T, kStep, tile, MB, LO, 8, FA> : pirl_env_kernel<T, kStep, tile, MB, LO, 7, FA>))
+    if (fast) kern = RLITG_PIRL_PICK(kMinBF, true, true);
+    else if (link_obs) kern = RLITG_PIRL_PICK(kMinB, true, false);
+    else kern = RLITG_PIRL_PICK(kMinB, false, false);
+#undef RLITG_PIRL_PICK
     size_t smem = sizeof(T) * tile * (size_t)(fast ? c.O : (c.O | 1)) +
                         (scene ? kMaxSpheres * sizeof(float4) + 16 * sizeof(int) : 0);
     if (smem > 200 * 1024) return set_error(RLITG_ERR_SHAPE, "observation too long for the shared-memory tile");
@@ -881,8 +904,8 @@ static int check_cfg(const RlitgPirlCfg* cfg) {
     if (cfg->obs_type < 0 || cfg->obs_type > 3) return set_error(RLITG_ERR_ARG, "obs_type must be 0..3");
     if (cfg->n_future < 0 || cfg->n_future > 64 || cfg->z_dim < 0 || cfg->z_dim > 4096)
         return set_error(RLITG_ERR_ARG, "n_future / z_dim out of range");
-    if (cfg->row_floats != 0 && cfg->row_floats != 7 && cfg->row_floats != 8)
-        return set_error(RLITG_ERR_ARG, "row_floats must be 0 / 7 (packed rows) or 8 (rows padded to 32 bytes)");
+    if (cfg->row_floats != 0 && cfg->row_floats != 7 && cfg->row_floats != 8 && cfg->row_floats != 32)
+        return set_error(RLITG_ERR_ARG, "row_floats must be 0 / 7 (packed rows), 8 (32-byte rows) or 32 (128-byte step records)");
     return RLITG_OK;
 }
 
@@ -916,6 +939,8 @@ RLITG_API int rlitg_pirl_env_step(const RlitgPirlCfg* cfg, int64_t B, int dtype,
         return set_error(RLITG_ERR_ALIGN, "flags must be 8-byte and counters 16-byte aligned");
     if (cfg->row_floats == 8 && ((reinterpret_cast<uintptr_t>(targets) & 31) || (demos && (reinterpret_cast<uintptr_t>(demos) & 31))))
         return set_error(RLITG_ERR_ALIGN, "padded target / demo rows (row_floats = 8) must be 32-byte aligned");
+    if (cfg->row_floats == 32 && (reinterpret_cast<uintptr_t>(targets) & 127))
+        return set_error(RLITG_ERR_ALIGN, "step records (row_floats = 32) must be 128-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == RLITG_F32)
         return launch_pirl<float, true>(cfg, B, (float*)q, action, timestep, max_timestep, (const float*)targets,
@@ -939,6 +964,8 @@ RLITG_API int rlitg_pirl_obs(const RlitgPirlCfg* cfg, int64_t B, int dtype, cons
     if (cfg->z_dim > 0 && !latent) return set_error(RLITG_ERR_NULL, "latent is NULL but z_dim > 0");
     if (cfg->row_floats == 8 && (reinterpret_cast<uintptr_t>(targets) & 31))
         return set_error(RLITG_ERR_ALIGN, "padded target rows (row_floats = 8) must be 32-byte aligned");
+    if (cfg->row_floats == 32 && (reinterpret_cast<uintptr_t>(targets) & 127))
+        return set_error(RLITG_ERR_ALIGN, "step records (row_floats = 32) must be 128-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == RLITG_F32)
         return launch_pirl<float, false>(cfg, B, (float*)q, nullptr, (int32_t*)timestep, max_timestep,

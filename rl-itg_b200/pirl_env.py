@@ -29,7 +29,7 @@ class RlitgPirlCfg(C.Structure):
                 ("thr_dist", C.c_double), ("thr_rot", C.c_double), ("thr_imitate", C.c_double),
                 ("zero_task_dist", C.c_double), ("dist_p", C.c_double * 4), ("rot_p", C.c_double * 4),
                 ("imit_p", C.c_double * 4), ("null_p", C.c_double * 4), ("w_col", C.c_double),
-                ("w_jlimit", C.c_double), ("w_early_stop", C.c_double), ("row_floats", C.c_int32), ("reserved_", C.c_int32)]
+                ("w_jlimit", C.c_double), ("w_early_stop", C.c_double), ("row_floats", C.c_int32), ("record_has_demo", C.c_int32)]
 
 
 _vp, _i64, _i = C.c_void_p, C.c_int64, C.c_int
@@ -169,7 +169,7 @@ class PirlVecEnv:
         self.flags = torch.empty(B, 8, dtype=torch.uint8, **kw)
         self.errs = torch.empty(B, 4, dtype=dtype, **kw) if want_errs else None
         self.target_poses = self.demo_configs = self.latent = None
-        self._targets8 = self._demos8 = None
+        self._records = None
         self.Tmax = 0
         self._pre = self._post = self._info = None
         self._base_off = np.ascontiguousarray(scene.base_offset if scene is not None else fetch.BASE_OFFSET, dtype=np.float64)
@@ -179,23 +179,26 @@ class PirlVecEnv:
         """target_poses [B,Tmax,7], demo_configs [B,Tmax,7] or None, max_timestep [B]; latent [B,zDim]."""
         conv = lambda a: None if a is None else torch.as_tensor(a).to(self.device, self.dtype).contiguous()
 
-        def rows8(a):
-            """[B,Tmax,7] -> [B,Tmax,8]: 32-byte rows (FP32), so that the per-env row gathers of the step touch whole
-            DRAM sectors (cfg.row_floats = 8); target_poses / demo_configs stay 7-wide views of the padded tables"""
-            if a is None:
-                return None
-            p = torch.zeros(a.shape[0], a.shape[1], 8, device=self.device, dtype=self.dtype)
-            p[..., :7] = a
-            return p
-
         tp, dc = conv(target_poses), conv(demo_configs)
         assert tp.shape[0] == self.B and tp.shape[2] == 7
         if dc is not None and not self._args["refineFlag"]:
             dc = refine_continuous_joints(dc)   # the reference refines EVERY demo row in reset (PirlEnv.py:362-365)
-        self._targets8, self._demos8 = rows8(tp), rows8(dc)
-        self.target_poses = self._targets8[..., :7]
-        self.demo_configs = None if dc is None else self._demos8[..., :7]
-        self.cfg.row_floats = 8
+        # 128-byte STEP RECORDS (cfg.row_floats = 32): entry (b,t) = [target(t) | demo(t) | target(min(t+1, Tmax-1)) | pad],
+        # 8 values each.  A per-thread gather costs a whole 128-byte line on the B200 whatever its size
+        # (tools/probes/gather_probe.cu), so all the table rows one env step reads sit in one line; target_poses /
+        # demo_configs stay 7-wide views of the records (slot 2 is derived: call set_problems again after editing them)
+        Tm = tp.shape[1]
+        rec = torch.zeros(self.B, Tm, 32, device=self.device, dtype=self.dtype)
+        rec[..., 0:7] = tp
+        if dc is not None:
+            rec[..., 8:15] = dc
+        rec[:, :-1, 16:23] = tp[:, 1:]
+        rec[:, -1, 16:23] = tp[:, -1]
+        self._records = rec
+        self.target_poses = rec[..., 0:7]
+        self.demo_configs = None if dc is None else rec[..., 8:15]
+        self.cfg.row_floats = 32
+        self.cfg.record_has_demo = 0 if dc is None else 1
         self.Tmax = int(self.target_poses.shape[1])
         self.max_timestep = torch.as_tensor(max_timestep).to(self.device, torch.int32).contiguous()
         self.latent = conv(latent)
@@ -208,8 +211,9 @@ class PirlVecEnv:
         (-pi, pi]) unless start_conf is given; counters and timestep cleared; returns the observation."""
         if mode != self.mode:
             self.mode = mode
+            rf, hd = self.cfg.row_floats, self.cfg.record_has_demo
             self.cfg = make_cfg(mode=mode, **self._args)
-            self.cfg.row_floats = 8
+            self.cfg.row_floats, self.cfg.record_has_demo = rf, hd
         if start_conf is None:
             q0 = self.demo_configs[:, 0, :].clone()   # already refined to (-pi, pi] by set_problems
         else:
@@ -224,7 +228,7 @@ class PirlVecEnv:
         with _lib.on_device(self.device):
             check(lib.rlitg_pirl_obs(C.byref(self.cfg), self.B, _code(self.cur_conf), self.cur_conf.data_ptr(),
                                      self.timestep.data_ptr(), self.max_timestep.data_ptr(),
-                                     self._targets8.data_ptr(), self.Tmax,
+                                     self._records.data_ptr(), self.Tmax,
                                      None if self.latent is None else self.latent.data_ptr(), self.obs.data_ptr(),
                                      _stream()))
         return self.obs
@@ -237,8 +241,8 @@ class PirlVecEnv:
                       "is_col": self.flags[:, 0], "is_jlimit": self.flags[:, 1], "is_early_stop": self.flags[:, 2],
                       "is_timeout": self.flags[:, 3]}
         self._pre = (C.byref(self.cfg), self.B, _code(self.cur_conf), self.cur_conf.data_ptr())
-        self._post = (self.timestep.data_ptr(), self.max_timestep.data_ptr(), self._targets8.data_ptr(),
-                      p(self._demos8), self.Tmax, p(self.latent),
+        self._post = (self.timestep.data_ptr(), self.max_timestep.data_ptr(), self._records.data_ptr(),
+                      None, self.Tmax, p(self.latent),
                       None if self.scene is None else self.scene.handle, self._base_off.ctypes.data,
                       self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(), self.flags.data_ptr(),
                       self.counters.data_ptr(), p(self.errs))

@@ -274,3 +274,60 @@ def test_manipulability_parity(cuda_device, D):
         got = P.manipulability(torch.tensor(q, dtype=dtype, device=cuda_device)).double().cpu().numpy()
         assert np.abs(got - want).max() <= rel * want.max() + (1e-12 if dtype == torch.float64 else 1e-6)
     assert want[0] < 1e-6
+
+
+@pytest.mark.parametrize("setting", [("Task+NullSpaceImitation", "Conf+LinkPoses", 1, 0), ("Task+Imitation", "Conf+EE", 3, 0)])
+def test_table_layouts_agree(cuda_device, setting):
+    """The step reads the target / demo tables in three layouts (RlitgPirlCfg.row_floats): packed [B,Tmax,7], 32-byte rows
+    [B,Tmax,8] and the 128-byte step records [B,Tmax,32] PirlVecEnv builds.  Same values in, so the outputs agree to FP32
+    rounding (the three template instantiations contract their multiply-adds differently: 2e-6); episodes that end on this
+    step exercise the records' end-of-path branch."""
+    import copy
+    import ctypes as C
+    import torch
+    from rlitg_b200 import _lib, pirl_env as P
+    reward_type, obs_type, t, z = setting
+    B, T = 2000, 30
+    c = build_case(B, T, 11, False, cuda_device)
+    env = P.PirlVecEnv(B, reward_type, obs_type, t, z, False, None, cuda_device, torch.float32, want_errs=True)
+    env.set_problems(c["targets"], c["demos"], c["mts"])
+    assert env.cfg.row_floats == 32
+    q0 = torch.tensor(c["q"], dtype=torch.float32, device=cuda_device)
+    ts0 = torch.tensor(c["ts"], device=cuda_device)
+    act = torch.tensor(c["act"], device=cuda_device)
+    tp = env.target_poses.contiguous()      # [B,T,7] packed copies of what the records hold
+    dc = env.demo_configs.contiguous()
+
+    def run(row_floats):
+        q, ts = q0.clone(), ts0.clone()
+        cnt = torch.zeros(B, 4, dtype=torch.int32, device=cuda_device)
+        obs = torch.empty(B, env.obs_dim, device=cuda_device); rew = torch.empty(B, device=cuda_device)
+        done = torch.empty(B, dtype=torch.uint8, device=cuda_device); flags = torch.empty(B, 8, dtype=torch.uint8, device=cuda_device)
+        errs = torch.empty(B, 4, device=cuda_device)
+        cfg = copy.copy(env.cfg)
+        if row_floats == 32:
+            tgt, dem = env._records, None
+        elif row_floats == 8:
+            tgt = torch.zeros(B, T, 8, device=cuda_device); tgt[..., :7] = tp
+            dem = torch.zeros(B, T, 8, device=cuda_device); dem[..., :7] = dc
+        else:
+            tgt, dem = tp, dc
+        cfg.row_floats = row_floats
+        with _lib.on_device(cuda_device):
+            _lib.check(_lib.lib.rlitg_pirl_env_step(C.byref(cfg), B, _lib.F32, q.data_ptr(), act.data_ptr(), ts.data_ptr(),
+                                                    env.max_timestep.data_ptr(), tgt.data_ptr(),
+                                                    None if dem is None else dem.data_ptr(), T, None, None, None,
+                                                    obs.data_ptr(), rew.data_ptr(), done.data_ptr(), flags.data_ptr(),
+                                                    cnt.data_ptr(), errs.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        return [x.cpu().numpy() for x in (q, ts, obs, rew, done, flags, cnt, errs)]
+
+    ref = run(32)
+    assert (c["ts"] + 1 >= c["mts"]).sum() > 50   # end-of-path steps are in the batch
+    for rf in (8, 7):
+        got = run(rf)
+        for k, (a, b) in enumerate(zip(ref, got)):
+            if a.dtype.kind == "f":
+                assert np.abs(a.astype(np.float64) - b).max() < (2e-4 if k == 3 else 2e-6), (rf, k)   # k = 3: the reward
+            else:
+                assert (a != b).sum() <= 2, (rf, k)   # a flag / counter may flip when an error sits on its threshold
