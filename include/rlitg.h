@@ -216,6 +216,19 @@ RLITG_API int rlitg_pirl_env_step(const RlitgPirlCfg* cfg, int64_t B, int dtype,
                                   const double* base_off, void* obs, void* reward, uint8_t* done, uint8_t* flags,
                                   int32_t* counters, void* errs, void* stream);
 
+/* The same step with its argument list bound once (a vectorised PirlEnv_Fetch steps the same buffers for a whole
+ * roll-out, PirlEnv.py:209-289 called from pirl/script/algos/sac/sac.py:285-334): rlitg_pirl_bind copies the
+ * configuration and the pointers (the caller keeps the buffers alive and re-binds when one of them is replaced),
+ * rlitg_pirl_step_bound is rlitg_pirl_env_step on them.  For bindings whose per-argument marshalling costs as much as
+ * the 5 us kernel at 16,384 envs (ctypes). */
+typedef struct RlitgPirlBound RlitgPirlBound;
+RLITG_API int rlitg_pirl_bind(const RlitgPirlCfg* cfg, int64_t B, int dtype, void* q, int32_t* timestep,
+                              const int32_t* max_timestep, const void* targets, const void* demos, int Tmax,
+                              const void* latent, const RlitgScene* scene, const double* base_off, void* obs, void* reward,
+                              uint8_t* done, uint8_t* flags, int32_t* counters, void* errs, RlitgPirlBound** out);
+RLITG_API int rlitg_pirl_step_bound(const RlitgPirlBound* bound, const float* action, void* stream);
+RLITG_API void rlitg_pirl_bound_destroy(RlitgPirlBound* bound);
+
 /* Observation only (env.reset, PirlEnv.py:378-392; PirlInterpolator::getObs, torm/src/pirl_interpolator.cpp:176-248). */
 RLITG_API int rlitg_pirl_obs(const RlitgPirlCfg* cfg, int64_t B, int dtype, const void* q, const int32_t* timestep,
                              const int32_t* max_timestep, const void* targets, int Tmax, const void* latent,

@@ -953,6 +953,52 @@ RLITG_API int rlitg_pirl_env_step(const RlitgPirlCfg* cfg, int64_t B, int dtype,
     return set_error(RLITG_ERR_DTYPE, "dtype must be RLITG_F32 or RLITG_F64");
 }
 
+// ---- bound step: the argument list of rlitg_pirl_env_step held by a handle ------------------------------------------
+// At 16,384 envs the kernel takes ~5 us and a binding that marshals twenty arguments per call (ctypes: ~4 us) makes the
+// step launch-bound.  A vectorised env steps the same buffers thousands of times: bind them once, pass the action.
+struct PirlBound {
+    RlitgPirlCfg cfg;
+    int64_t B;
+    int dtype, Tmax;
+    void *q, *obs, *reward, *errs;
+    int32_t *timestep, *counters;
+    const int32_t* max_timestep;
+    const void *targets, *demos, *latent;
+    const RlitgScene* scene;
+    double base_off[3];
+    bool has_off;
+    uint8_t *done, *flags;
+};
+
+RLITG_API int rlitg_pirl_bind(const RlitgPirlCfg* cfg, int64_t B, int dtype, void* q, int32_t* timestep,
+                              const int32_t* max_timestep, const void* targets, const void* demos, int Tmax,
+                              const void* latent, const RlitgScene* scene, const double* base_off, void* obs, void* reward,
+                              uint8_t* done, uint8_t* flags, int32_t* counters, void* errs, RlitgPirlBound** out) {
+    if (!out) return set_error(RLITG_ERR_NULL, "out is NULL");
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    PirlBound* b = new PirlBound();
+    b->cfg = *cfg; b->B = B; b->dtype = dtype; b->Tmax = Tmax;
+    b->q = q; b->obs = obs; b->reward = reward; b->errs = errs;
+    b->timestep = timestep; b->counters = counters; b->max_timestep = max_timestep;
+    b->targets = targets; b->demos = demos; b->latent = latent; b->scene = scene;
+    b->has_off = base_off != nullptr;
+    for (int k = 0; k < 3; k++) b->base_off[k] = base_off ? base_off[k] : 0.0;
+    b->done = done; b->flags = flags;
+    *out = reinterpret_cast<RlitgPirlBound*>(b);
+    return RLITG_OK;
+}
+
+RLITG_API int rlitg_pirl_step_bound(const RlitgPirlBound* h, const float* action, void* stream) {
+    if (!h) return set_error(RLITG_ERR_NULL, "bound handle is NULL");
+    const PirlBound* b = reinterpret_cast<const PirlBound*>(h);
+    return rlitg_pirl_env_step(&b->cfg, b->B, b->dtype, b->q, action, b->timestep, b->max_timestep, b->targets, b->demos, b->Tmax,
+                               b->latent, b->scene, b->has_off ? b->base_off : nullptr, b->obs, b->reward, b->done, b->flags,
+                               b->counters, b->errs, stream);
+}
+
+RLITG_API void rlitg_pirl_bound_destroy(RlitgPirlBound* h) { delete reinterpret_cast<PirlBound*>(h); }
+
 RLITG_API int rlitg_pirl_obs(const RlitgPirlCfg* cfg, int64_t B, int dtype, const void* q, const int32_t* timestep,
                              const int32_t* max_timestep, const void* targets, int Tmax, const void* latent,
                              void* obs, void* stream) {

@@ -87,6 +87,16 @@ except AttributeError:  # pragma: no cover
         return torch.cuda.current_stream(index).cuda_stream
 
 
+lib.rlitg_pirl_bind.argtypes = [C.POINTER(RlitgPirlCfg), _i64, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp,
+                                _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_void_p)]
+lib.rlitg_pirl_bind.restype = C.c_int
+lib.rlitg_pirl_step_bound.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+lib.rlitg_pirl_step_bound.restype = C.c_int
+lib.rlitg_pirl_bound_destroy.argtypes = [C.c_void_p]
+lib.rlitg_pirl_bound_destroy.restype = None
+_step_bound = lib.rlitg_pirl_step_bound
+
+
 def nullspace_norm(err, q):
     """jaco_srv(err, q).objective_value for a batch (pirl/src/kinematic_solver.cpp:332-351)."""
     err, q = err.contiguous(), q.contiguous()
@@ -171,7 +181,7 @@ class PirlVecEnv:
         self.target_poses = self.demo_configs = self.latent = None
         self._records = None
         self.Tmax = 0
-        self._pre = self._post = self._info = None
+        self._pre = self._post = self._info = self._bound = None
         self._base_off = np.ascontiguousarray(scene.base_offset if scene is not None else fetch.BASE_OFFSET, dtype=np.float64)
 
     # -- problems ------------------------------------------------------------------------------------------
@@ -246,6 +256,22 @@ class PirlVecEnv:
                       None if self.scene is None else self.scene.handle, self._base_off.ctypes.data,
                       self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(), self.flags.data_ptr(),
                       self.counters.data_ptr(), p(self.errs))
+        # the same argument list held by a C handle: the per-step call then marshals three arguments instead of twenty
+        self._unbind()
+        h = C.c_void_p()
+        check(lib.rlitg_pirl_bind(*self._pre, *self._post, C.byref(h)))
+        self._bound = h
+
+    def _unbind(self):
+        if getattr(self, "_bound", None):
+            lib.rlitg_pirl_bound_destroy(self._bound)
+        self._bound = None
+
+    def __del__(self):
+        try:
+            self._unbind()
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
 
     def step(self, action):
         """action: [B,7] tensor (any float dtype; converted to float32 like the policy output).
@@ -260,10 +286,10 @@ class PirlVecEnv:
         # stream / device objects are built when this env's device is already current)
         idx = self._dev_index
         if torch.cuda.current_device() == idx:
-            rc = lib.rlitg_pirl_env_step(*self._pre, a.data_ptr(), *self._post, _raw_stream(idx))
+            rc = _step_bound(self._bound, a.data_ptr(), _raw_stream(idx))
         else:
             with torch.cuda.device(idx):
-                rc = lib.rlitg_pirl_env_step(*self._pre, a.data_ptr(), *self._post, _raw_stream(idx))
+                rc = _step_bound(self._bound, a.data_ptr(), _raw_stream(idx))
         if rc:
             check(rc)
         return self.obs, self.reward, self.done, self._info
