@@ -204,6 +204,59 @@ static int rebuild_dilated(Scene* s, cudaStream_t st = nullptr) {
     return RLITG_OK;
 }
 
+// ---- two-phase bit test (dilated volumes in global memory) -----------------------------------------------------------
+// Phase 1: the chain walk stores, per sphere, the linear BIT index of its centre cell in the volume of its radius class
+// (0xffffffff outside the grid) into the thread's own shared-memory row; phase 2 gathers the words of all spheres with
+// independent loads, eight in flight, and ORs the bits.  The walk has no load in it and no branch per sphere; a waypoint
+// costs one L2 round trip per eight spheres instead of one per link (the loads of a link used to be consumed before the
+// walk went on: six to seven dependent round trips per thread and 52 KB of branchy code).
+constexpr uint32_t kNoCell = 0xffffffffu;
+
+template <typename T>
+struct CollideIndexVisit {
+    const SceneDev& sc;
+    const GridMap<T>& gm;
+    const float4* sph;          // shared-memory copy of the sphere table
+    const int* link_start;      // shared-memory copy
+    const uint32_t* cls_bits;   // shared memory: first bit of sphere s's class volume (class * words * 32)
+    uint32_t* row;              // shared memory: this thread's [S] bit indices
+    V3<T> off;
+    template <int K>
+    RLITG_DEV void operator()(jidx<K>, const FrameC<T>& f) {
+        if constexpr (K < kNumLinks) {
+            const int s1 = link_start[K + 1];
+            for (int s = link_start[K]; s < s1; s++) {
+                const float4 c = sph[s];
+                const T x = off.x + f.p.x + f.c0.x * T(c.x) + f.c1.x * T(c.y) + f.c2.x * T(c.z);
+                const T y = off.y + f.p.y + f.c0.y * T(c.x) + f.c1.y * T(c.y) + f.c2.y * T(c.z);
+                const T z = off.z + f.p.z + f.c0.z * T(c.x) + f.c1.z * T(c.y) + f.c2.z * T(c.z);
+                const int cx = gm.cell1(x, gm.ox), cy = gm.cell1(y, gm.oy), cz = gm.cell1(z, gm.oz);
+                const bool in = (unsigned)cx < (unsigned)sc.nx && (unsigned)cy < (unsigned)sc.ny && (unsigned)cz < (unsigned)sc.nz;
+                row[s] = in ? cls_bits[s] + (uint32_t)((cz * sc.ny + cy) * (sc.wx * 32) + cx) : kNoCell;
+            }
+        }
+    }
+};
+
+RLITG_DEV bool any_bit_set(const uint32_t* __restrict__ dil, const uint32_t* row, int S) {
+    uint32_t hit = 0u;
+    for (int s0 = 0; s0 < S; s0 += 8) {
+        uint32_t idx[8], w[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) idx[k] = s0 + k < S ? row[s0 + k] : kNoCell;
+#pragma unroll
+        for (int k = 0; k < 8; k++) w[k] = idx[k] != kNoCell ? __ldg(dil + (idx[k] >> 5)) : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; k++) hit |= w[k] >> (idx[k] & 31u);
+    }
+    return (hit & 1u) != 0u;
+}
+
+// the bit index is 32 bits wide: volumes beyond that (> 512 MB of dilated bits) keep the per-link test
+static inline bool dil_index_fits(const Scene* s) {
+    return s->dil != nullptr && (uint64_t)s->wx * s->ny * s->nz * 32ull * (uint64_t)s->ncls < 0xffffffffull;
+}
+
 // ---- binary collision: any sphere with d(centre cell) - r < 0 ---------------------------------------------
 // B200 stand-in for cc_srv / TormIKSolver::collisionChecking (pirl/src/collision_checker.cpp:39-61,
 // torm/src/torm_ik_solver.cpp:59-66): an approximation of FCL's mesh test, not a parity target.
@@ -229,13 +282,18 @@ struct CollideVisit {
     }
 };
 
-template <typename T>
+template <typename T, bool kIdx>
 __global__ void __launch_bounds__(128) sphere_collide_kernel(const T* __restrict__ q, int64_t B, SceneDev sc,
                                                              T ox, T oy, T oz,
                                                              uint8_t* __restrict__ out) {
+    extern __shared__ __align__(16) uint32_t s_rows[];  // kIdx: [blockDim.x][S | 1] bit indices
     __shared__ float4 s_sph[kMaxSpheres];
     __shared__ int s_start[kNumLinks + 1];
-    for (int i = threadIdx.x; i < sc.S; i += blockDim.x) s_sph[i] = sc.spheres[i];
+    __shared__ uint32_t s_cls[kMaxSpheres];
+    for (int i = threadIdx.x; i < sc.S; i += blockDim.x) {
+        s_sph[i] = sc.spheres[i];
+        if constexpr (kIdx) s_cls[i] = (uint32_t)sc.sph_class[i] * (uint32_t)(sc.wx * sc.ny * sc.nz) * 32u;
+    }
     if (threadIdx.x <= kNumLinks) s_start[threadIdx.x] = sc.link_start[threadIdx.x];
     __syncthreads();
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -244,9 +302,16 @@ __global__ void __launch_bounds__(128) sphere_collide_kernel(const T* __restrict
 #pragma unroll
     for (int j = 0; j < 7; j++) qv[j] = q[b * 7 + j];
     const GridMap<T> gm(sc);
-    CollideVisit<T> v{sc, gm, s_sph, s_start, {ox, oy, oz}};
-    walk_chain<T, 7>(qv, v);
-    out[b] = v.hit ? 1 : 0;
+    if constexpr (kIdx) {
+        uint32_t* row = s_rows + (size_t)threadIdx.x * (sc.S | 1);
+        CollideIndexVisit<T> v{sc, gm, s_sph, s_start, s_cls, row, {ox, oy, oz}};
+        walk_chain<T, 7>(qv, v);
+        out[b] = any_bit_set(sc.dil, row, sc.S) ? 1 : 0;
+    } else {
+        CollideVisit<T> v{sc, gm, s_sph, s_start, {ox, oy, oz}};
+        walk_chain<T, 7>(qv, v);
+        out[b] = v.hit ? 1 : 0;
+    }
 }
 
 // Persistent variant for grids whose dilated bit volumes fit in shared memory (e.g. the pirl_gazebo 50 x 70 x 50
@@ -354,17 +419,19 @@ struct CollideVisitDil {
     }
 };
 
-template <typename T>
+// kIdx: the two-phase bit test (CollideIndexVisit; needs blockDim.x * (S | 1) words of dynamic shared memory)
+template <typename T, bool kIdx>
 __global__ void __launch_bounds__(256) collision_point_kernel(const T* __restrict__ traj, int Tn, SceneDev sc, T ox, T oy, T oz,
                                                              const float* __restrict__ u, int32_t* __restrict__ first_hit,
                                                              uint8_t* __restrict__ any_hit, int32_t* __restrict__ stoch_idx) {
+    extern __shared__ __align__(16) uint32_t s_rows[];  // kIdx: [blockDim.x][S | 1] bit indices (odd stride: conflict free)
     __shared__ float4 s_sph[kMaxSpheres];
     __shared__ int s_start[kNumLinks + 1];
     __shared__ int s_first;
     __shared__ int s_cls[kMaxSpheres];
     for (int i = threadIdx.x; i < sc.S; i += blockDim.x) {
         s_sph[i] = sc.spheres[i];
-        s_cls[i] = sc.dil ? sc.sph_class[i] * (sc.wx * sc.ny * sc.nz) : 0;
+        s_cls[i] = sc.dil ? sc.sph_class[i] * (sc.wx * sc.ny * sc.nz) * (kIdx ? 32 : 1) : 0;
     }
     if (threadIdx.x <= kNumLinks) s_start[threadIdx.x] = sc.link_start[threadIdx.x];
     if (threadIdx.x == 0) s_first = 0x7fffffff;
@@ -379,7 +446,12 @@ __global__ void __launch_bounds__(256) collision_point_kernel(const T* __restric
 #pragma unroll
         for (int j = 0; j < 7; j++) qv[j] = tr[(size_t)i * 7 + j];
         bool hit;
-        if (sc.dil) {
+        if constexpr (kIdx) {
+            uint32_t* row = s_rows + (size_t)threadIdx.x * (sc.S | 1);
+            CollideIndexVisit<T> v{sc, gm, s_sph, s_start, reinterpret_cast<const uint32_t*>(s_cls), row, {ox, oy, oz}};
+            walk_chain<T, 7>(qv, v);
+            hit = any_bit_set(sc.dil, row, sc.S);
+        } else if (sc.dil) {
             CollideVisitDil<T> v{sc, gm, s_sph, s_start, s_cls, {ox, oy, oz}};
             walk_chain<T, 7>(qv, v);
             hit = v.hit;
@@ -425,8 +497,17 @@ int launch_sphere_collide(const T* q, int64_t B, const Scene* s, const double* b
         kern<<<grid, 256, dil_bytes, st>>>(q, B, s->dev(), (T)base_off[0], (T)base_off[1], (T)base_off[2], out);
         return check_launch("sphere_collide_smem_kernel");
     }
-    sphere_collide_kernel<T><<<blocks_for(B, 128), 128, 0, st>>>(q, B, s->dev(), (T)base_off[0], (T)base_off[1],
-                                                                 (T)base_off[2], out);
+    static const bool two_phase = [] { const char* e = getenv("RLITG_COLLIDE_TWO_PHASE"); return e ? atoi(e) != 0 : true; }();
+    if (two_phase && dil_index_fits(s)) {
+        auto kern = sphere_collide_kernel<T, true>;
+        const size_t smem = sizeof(uint32_t) * 128 * (size_t)(s->S | 1);
+        int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "sphere_collide_kernel");
+        if (rc_attr) return rc_attr;
+        kern<<<blocks_for(B, 128), 128, smem, st>>>(q, B, s->dev(), (T)base_off[0], (T)base_off[1], (T)base_off[2], out);
+        return check_launch("sphere_collide_kernel");
+    }
+    sphere_collide_kernel<T, false><<<blocks_for(B, 128), 128, 0, st>>>(q, B, s->dev(), (T)base_off[0], (T)base_off[1],
+                                                                        (T)base_off[2], out);
     return check_launch("sphere_collide_kernel");
 }
 template int launch_sphere_collide<float>(const float*, int64_t, const Scene*, const double*, uint8_t*, cudaStream_t);
@@ -615,15 +696,20 @@ RLITG_API int rlitg_torm_collision_point(const void* traj, int64_t N, int T, int
     if (!scene_ready(s, true, true)) return set_error(RLITG_ERR_ARG, "scene needs a grid and a sphere table");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int cp_threads = std::min(256, ((T + 31) / 32) * 32);  // one waypoint per thread up to 256 rows per pass
-    if (dtype == RLITG_F32)
-        collision_point_kernel<float><<<(unsigned)N, cp_threads, 0, st>>>((const float*)traj, T, s->dev(), (float)base_off[0],
-                                                                   (float)base_off[1], (float)base_off[2], u, first_hit,
-                                                                   any_hit, stochastic_idx);
-    else if (dtype == RLITG_F64)
-        collision_point_kernel<double><<<(unsigned)N, cp_threads, 0, st>>>((const double*)traj, T, s->dev(), base_off[0], base_off[1],
-                                                                    base_off[2], u, first_hit, any_hit, stochastic_idx);
-    else return set_error(RLITG_ERR_DTYPE, "dtype must be RLITG_F32 or RLITG_F64");
-    return check_launch("collision_point_kernel");
+    if (dtype != RLITG_F32 && dtype != RLITG_F64) return set_error(RLITG_ERR_DTYPE, "dtype must be RLITG_F32 or RLITG_F64");
+    static const bool two_phase = [] { const char* e = getenv("RLITG_COLLIDE_TWO_PHASE"); return e ? atoi(e) != 0 : true; }();
+    const bool idx = two_phase && dil_index_fits(s);
+    const size_t smem = idx ? sizeof(uint32_t) * (size_t)cp_threads * (s->S | 1) : 0;
+    auto launch = [&](auto kern, auto tag) -> int {
+        using TT = decltype(tag);
+        int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "collision_point_kernel");
+        if (rc_attr) return rc_attr;
+        kern<<<(unsigned)N, cp_threads, smem, st>>>((const TT*)traj, T, s->dev(), (TT)base_off[0], (TT)base_off[1], (TT)base_off[2],
+                                                   u, first_hit, any_hit, stochastic_idx);
+        return check_launch("collision_point_kernel");
+    };
+    if (dtype == RLITG_F32) return idx ? launch(collision_point_kernel<float, true>, float()) : launch(collision_point_kernel<float, false>, float());
+    return idx ? launch(collision_point_kernel<double, true>, double()) : launch(collision_point_kernel<double, false>, double());
 }
 
 RLITG_API int rlitg_sphere_grid_collide(const void* q, int64_t B, int dtype, const RlitgScene* h,
