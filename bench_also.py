@@ -154,12 +154,12 @@ def run_torm(torch, dev, rank, world, max_over_ranks, barrier, steps, warmup, fm
                 tw.copy_(traj)
                 tb.localOptimizeTSGD(tw, 3, lr_schedule_mode=3, use_cuda_graph=g, **kw)   # warm-up
                 tw.copy_(traj)
-                n_it = 300 if g else 30   # the graph is captured inside the call (~10 ms): amortised over 300 replays
+                n_it = 1201 if g else 30   # the graph (8 iterations per replay) is captured inside the call: amortised over 150 replays
                 torch.cuda.synchronize(); barrier(); t0 = time.perf_counter()
                 tb.localOptimizeTSGD(tw, n_it, lr_schedule_mode=3, use_cuda_graph=g, **kw)
                 torch.cuda.synchronize()
                 tsgd["ms_per_iteration_%s_%s" % (name, gname)] = max_over_ranks((time.perf_counter() - t0) * 1e3 / n_it)
-        tsgd["note"] = ("localOptimizeTSGD(30 iterations eager / 300 as CUDA-graph replays incl. the capture, lr_schedule_mode 3), "
+        tsgd["note"] = ("localOptimizeTSGD(30 iterations eager / 1,201 as CUDA-graph replays of 8 iterations each incl. the capture, lr_schedule_mode 3), "
                         "wall clock per iteration: two cost calls, two collision-point tests, two bookkeeping launches, two update "
                         "steps; stochastic = the reference's default (one waypoint per trajectory takes the collision increment)")
     except Exception as e:  # noqa: BLE001

@@ -347,7 +347,8 @@ TormBatch.applyIncrements = _apply_increments
 
 
 def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, check_collision=True, lr_schedule_mode=3,
-                         return_state=False, use_cuda_graph=None, stochastic=None, seed=0, rand=None, state=None, overlap=True):
+                         return_state=False, use_cuda_graph=None, stochastic=None, seed=0, rand=None, state=None, overlap=True,
+                         graph_iterations=8):
     """Lock-step two-stage gradient descent over the N trajectories of `traj` (in place): the loop body of
     TormOptimizer::localOptimizeTSGD (torm/src/torm_optimizer.cpp:397-598) entirely on the device -- cost +
     increments (kernels 3a / 3b), feasibility checks, the alpha_ / learning_rate_ schedule, the best-trajectory
@@ -368,8 +369,11 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
     reference then writes row -1 of the increment matrix) takes no increment.
     state: dict(alpha=[N], learning_rate=[N]) carried over from a previous call -- alpha_ / learning_rate_ are members of
     the reference's optimiser and persist across localOptimizeTSGD calls (infea_col / infea_vel are locals, :383).
-    There is no host synchronisation inside an iteration, so one iteration can also be captured in a CUDA graph and
-    replayed (use_cuda_graph=True; identical results).  overlap=False keeps every launch on one stream (measurement).
+    There is no host synchronisation inside an iteration, so the loop can also be captured in a CUDA graph and replayed
+    (use_cuda_graph=True; identical results): one graph holds `graph_iterations` iterations -- their draws and scheduled
+    rates sit in a block buffer refilled by one device copy per replay -- so that the graph-to-graph boundary and the
+    per-iteration refill are paid once per block; the iterations that do not fill a block run eagerly.
+    overlap=False keeps every launch on one stream (measurement).
     Returns (best_traj [N,T,7], best_cost [N]); best_cost stays +inf for trajectories never found feasible.
     return_state=True appends a dict with the final alpha / lr / feasibility tensors and the draws."""
     pr = self.parameters
@@ -395,7 +399,12 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
     infea_col = torch.zeros(N, dtype=torch.uint8, device=dev)        # :383
     infea_vel = torch.zeros(N, dtype=torch.uint8, device=dev)
     stage_idx = torch.zeros(N, dtype=torch.int32, device=dev)
-    lr_iter = torch.full((1,), lr0, device=dev, dtype=dt)            # mode 2: this iteration's scheduled rate
+    KB = max(int(graph_iterations), 1) if use_cuda_graph else 1      # iterations per block (= per graph replay)
+    lr_blk = torch.full((KB,), lr0, device=dev, dtype=dt)            # mode 2: the block's scheduled rates
+    if mode == 2:                                                    # cosine with period maxiter / 2 (:493-496)
+        period = max(maxiter // 2, 1)
+        ph = (np.arange(max(maxiter, 1)) % period) / period
+        lr_sched = torch.tensor(lr_min + 0.5 * (lr_max - lr_min) * (1.0 + np.cos(ph * np.pi)), device=dev, dtype=dt)
     zeros = None if has_scene else torch.zeros(N, self.T - 1, 7, device=dev, dtype=dt)
 
     if use_cuda_graph is None:
@@ -418,7 +427,7 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
             g.manual_seed(int(seed))
             rand = torch.rand((max(maxiter, 1), 2, N), generator=g, device=dev, dtype=torch.float32)
         assert rand.shape == (max(maxiter, 1), 2, N) and rand.dtype == torch.float32 and rand.is_cuda
-        u_cur = torch.empty(2, N, dtype=torch.float32, device=dev)   # this iteration's draws (fixed address: graph replay)
+        u_blk = torch.empty(KB, 2, N, dtype=torch.float32, device=dev)   # the block's draws (fixed address: graph replay)
     base_off = (C.c_double * 3)(*pr.base_offset)
 
     # Every half-iteration has two independent parts that only read the trajectory: the end-pose / evaluator kernel, and
@@ -428,7 +437,7 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
     ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
     KEEP = STAGE_KEEP_COSTS
 
-    def sub_step(stage):
+    def sub_step(stage, k):
         cur_stream = torch.cuda.current_stream(dev)
         if mode == 1:
             # every optimiser picks its own stage (:400-412) from the state before this half-iteration; the cost kernels
@@ -459,7 +468,7 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
         if need_point:
             with _lib.on_device(dev):
                 check(lib.rlitg_torm_collision_point(traj.data_ptr(), N, self.T, code, self.scene.handle, base_off,
-                                                     u_cur[stage].data_ptr() if stochastic else None, None,
+                                                     u_blk[k, stage].data_ptr() if stochastic else None, None,
                                                      any_hit.data_ptr(), stoch_idx.data_ptr() if stochastic else None,
                                                      cur_stream.cuda_stream))
         rc = None
@@ -480,7 +489,7 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
                                           any_hit.data_ptr() if sch[stage].use_collision_check else None,
                                           None if singular is None else singular.data_ptr(), al.data_ptr(), lr.data_ptr(),
                                           infea_col.data_ptr(), infea_vel.data_ptr(), best_cost.data_ptr(),
-                                          None, lr_iter.data_ptr() if mode == 2 else None, C.byref(sch[stage]),
+                                          None, lr_blk[k:k + 1].data_ptr() if mode == 2 else None, C.byref(sch[stage]),
                                           cur_stream.cuda_stream))
         # ---- increments -> trajectory (:562-576)
         if smooth_mask:
@@ -495,25 +504,23 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
         else:
             self.applyIncrements(traj, False, inc_pose=r["inc_pose"], alpha=al, learning_rate=lr, lr_schedule_mode=mode)
 
-    def iteration():
-        sub_step(0)
-        sub_step(1)
+    def iteration(k=0):
+        sub_step(0, k)
+        sub_step(1, k)
 
-    def set_iter(it):
+    def set_block(it0, n):
+        # the draws / scheduled rates of iterations it0 .. it0 + n - 1 into the block buffers (device-to-device)
         if mode == 2:
-            period = max(maxiter // 2, 1)
-            ph = float(it % period) / period
-            lr_iter.fill_(lr_min + 0.5 * (lr_max - lr_min) * (1.0 + np.cos(ph * np.pi)))
+            lr_blk[:n].copy_(lr_sched[it0:it0 + n])
         if stochastic:
-            u_cur.copy_(rand[it])
+            u_blk[:n].copy_(rand[it0:it0 + n])
 
-    graph = None
     start = 0
-    if use_cuda_graph and maxiter >= 2:
+    if use_cuda_graph and maxiter >= 1 + KB:
         # the first iteration runs eagerly: it is the warm-up a capture needs (kernel attributes, lazily built scene
         # volumes, output buffers of cost_grad) and it is real work, not thrown away
-        set_iter(0)
-        iteration()
+        set_block(0, 1)
+        iteration(0)
         start = 1
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
@@ -521,14 +528,16 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
         cap_stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(cap_stream):
             with torch.cuda.graph(graph, stream=cap_stream):
-                iteration()
+                for k in range(KB):
+                    iteration(k)
         torch.cuda.current_stream(dev).wait_stream(cap_stream)
-    for it in range(start, maxiter):
-        set_iter(it)
-        if graph is not None:
+        while start + KB <= maxiter:
+            set_block(start, KB)
             graph.replay()
-        else:
-            iteration()
+            start += KB
+    for it in range(start, maxiter):
+        set_block(it, 1)
+        iteration(0)
     if return_state:
         return best_traj, best_cost, dict(alpha=al, learning_rate=lr, infea_col=infea_col.bool(), infea_vel=infea_vel.bool(),
                                           rand=rand if stochastic else None)

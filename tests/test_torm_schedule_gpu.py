@@ -162,10 +162,11 @@ def test_iterative_exploration_restarts_as_batch(cuda_device, init_traj):
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2, 3])
-@pytest.mark.parametrize("dtype", ["float32", "float64"])
-def test_graph_replay_equals_eager(cuda_device, mode, dtype):
-    """localOptimizeTSGD replays one captured iteration per step (no host synchronisation inside): bit-identical to the
-    eager loop, for every schedule mode, including the per-iteration cosine rate of mode 2."""
+@pytest.mark.parametrize("dtype,block", [("float32", 8), ("float64", 8), ("float32", 1), ("float32", 4)])
+def test_graph_replay_equals_eager(cuda_device, mode, dtype, block):
+    """localOptimizeTSGD replays captured blocks of `block` iterations (no host synchronisation inside; 11 iterations =
+    one eager + full blocks + an eager remainder): bit-identical to the eager loop, for every schedule mode, including
+    the per-iteration cosine rate of mode 2 and the per-iteration draws of the stochastic waypoint."""
     import torch
     from rlitg_b200 import torm as TM
     N, T, maxiter = 24, 40, 11
@@ -177,7 +178,8 @@ def test_graph_replay_equals_eager(cuda_device, mode, dtype):
     bt_e, bc_e, st_e = tb.localOptimizeTSGD(a, maxiter, lr_schedule_mode=mode, return_state=True, use_cuda_graph=False)
     bt_e, bc_e = bt_e.clone(), bc_e.clone()
     st_e = {k: v.clone() for k, v in st_e.items()}
-    bt_g, bc_g, st_g = tb.localOptimizeTSGD(b, maxiter, lr_schedule_mode=mode, return_state=True, use_cuda_graph=True)
+    bt_g, bc_g, st_g = tb.localOptimizeTSGD(b, maxiter, lr_schedule_mode=mode, return_state=True, use_cuda_graph=True,
+                                            graph_iterations=block)
     torch.cuda.synchronize()
     assert torch.equal(a, b)
     assert torch.equal(bt_e, bt_g) and torch.equal(bc_e, bc_g)

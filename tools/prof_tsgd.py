@@ -76,17 +76,18 @@ def main():
     print("cost feasible stochastic (graph)          %.1f us" % graphed(lambda: tb.cost_grad(tw, feas, stochastic_idx=st_idx)))
     for mode in (3, 1):
         for stoch in (True, False):
-            for use_graph in (False, True):
+            for use_graph, block in ((False, 1), (True, 1), (True, 8)):
                 for overlap in (True, False):
                     tw.copy_(traj)
                     tb.localOptimizeTSGD(tw, 3, lr_schedule_mode=mode, use_cuda_graph=use_graph, stochastic=stoch, overlap=overlap)
-                    iters = 600 if use_graph else 60   # a graph is captured per call: amortise the capture (~10 ms)
+                    iters = 2401 if use_graph else 60   # a graph is captured per call: amortise the capture
                     tw.copy_(traj)
                     torch.cuda.synchronize(); t0 = time.perf_counter()
-                    tb.localOptimizeTSGD(tw, iters, lr_schedule_mode=mode, use_cuda_graph=use_graph, stochastic=stoch, overlap=overlap)
+                    tb.localOptimizeTSGD(tw, iters, lr_schedule_mode=mode, use_cuda_graph=use_graph, stochastic=stoch, overlap=overlap,
+                                         graph_iterations=block)
                     torch.cuda.synchronize()
-                    print("localOptimizeTSGD mode %d stochastic=%d graph=%d overlap=%d: %.3f ms per iteration (wall, %d iterations)" %
-                          (mode, stoch, use_graph, overlap, (time.perf_counter() - t0) * 1e3 / iters, iters))
+                    print("localOptimizeTSGD mode %d stochastic=%d graph=%d block=%d overlap=%d: %.3f ms per iteration (wall, %d iterations)" %
+                          (mode, stoch, use_graph, block, overlap, (time.perf_counter() - t0) * 1e3 / iters, iters))
 
 
 if __name__ == "__main__":
