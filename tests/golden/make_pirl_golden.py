@@ -3,8 +3,12 @@
 (/root/reference/pirl/script/envs/PirlEnv.py, imported from where it lies, never copied), on seeded episodes.
 
 STATUS: NOT RUN YET.  Executing code of the external reference repository (MinsungYoon/RL-ITG, mounted at
-/root/reference) needs a human's explicit authorisation in this environment; the attempt in round 1 was refused by
-the sandbox policy and was not worked around.  Until someone approves and runs
+/root/reference) needs a human's explicit authorisation in this environment; the attempts in round 1 and in round 2
+(`python tests/golden/make_pirl_golden.py`, as written below) were refused by the sandbox policy -- "needs human
+authorization for executing the external reference repo's code" -- and were not worked around.  THE ASK, for whoever
+operates this repository: approve importing and executing /root/reference/pirl/script/envs/PirlEnv.py (from the
+MinsungYoon/RL-ITG reference) in the dev container through this script; a plain yes is enough.  Until someone approves
+and runs
     python tests/golden/make_pirl_golden.py
 in the dev container (where /root/reference is mounted), tests/golden/pirl_steps.npz does not exist and the PIRL
 step stays "parity unpinned" (DESIGN.md section 2).  The GPU box has no /root/reference, so the vectors would be

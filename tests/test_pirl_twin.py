@@ -182,3 +182,68 @@ def test_oracle_env_step_matches_numpy_twin(reward_type, obs_type, t, z, mode):
             if done:
                 break
     assert n_jl + n_wrap > 0   # the episodes exercise the joint-limit rejection (train) / clipping (test) or the wrap
+
+
+def write_surrogate(path):
+    """A file in the layout of tests/golden/pirl_steps.npz written from the NumPy twin (scene-free episodes; the twin has
+    no collision service).  Returns the number of episodes."""
+    settings = [("Task+NullSpaceImitation", "Conf+LinkPoses", 1, 0, "train"), ("Task+Imitation", "Conf+EE", 3, 0, "train"),
+                ("Task", "onlyConf", 2, 4, "train"), ("Imitation", "onlyLinkPoses", 1, 0, "test")]
+    T = 12
+    rng = np.random.default_rng(77)
+    link, center, radius = fetch.default_spheres()
+    out = {"scene_occ_bits": np.packbits(np.zeros(8 * 8 * 8, np.uint8)), "scene_shape": np.array((8, 8, 8)),
+           "scene_origin": np.array((5.0, 5.0, 5.0)), "scene_res": np.array(0.02), "base_off": np.array(fetch.BASE_OFFSET),
+           "sphere_link": link, "sphere_center": center, "sphere_radius": radius}
+    meta, ep = [], 0
+    for si, (rtype, otype, t, z, mode) in enumerate(settings):
+        for k in range(2):
+            demos = synth.random_joint_paths(1, T, seed=500 + 10 * si + k)[0]
+            targets = np.round(O.fk_quat(demos + rng.normal(0, 0.004, size=demos.shape)), 6)
+            env = TwinEnv(rtype, otype, t, z, mode)
+            env.reset(targets, demos, demos[0], np.zeros(z))
+            rec = {n: [] for n in ("action", "obs", "reward", "done", "flags", "counters", "conf")}
+            obs0 = env.obs(env.link_frames()[0])
+            for step in range(env.max_timestep):
+                a = demos[step + 1] - env.cur
+                for j in (2, 4, 6):
+                    a[j] = (a[j] + np.pi) % (2 * np.pi) - np.pi
+                a = (a + rng.normal(0, 0.004, size=7)).astype(np.float32)
+                if step == 3:
+                    a[1] += 2.5   # a joint-limit hit
+                o, r, d, info = env.step(a)
+                rec["action"].append(a); rec["obs"].append(o); rec["reward"].append(r); rec["done"].append(bool(d))
+                rec["flags"].append([False, info["jlimit"], info["early"], info["timeout"]])
+                rec["counters"].append(list(env.counts)); rec["conf"].append(env.cur.copy())
+                if d:
+                    break
+            key = "ep%d_" % ep
+            out[key + "demos"], out[key + "targets"], out[key + "obs0"] = demos, targets, obs0
+            out[key + "action"] = np.array(rec["action"], np.float32)
+            out[key + "obs"], out[key + "reward"] = np.array(rec["obs"]), np.array(rec["reward"])
+            out[key + "done"], out[key + "flags"] = np.array(rec["done"], np.uint8), np.array(rec["flags"], np.uint8)
+            out[key + "counters"], out[key + "conf"] = np.array(rec["counters"], np.int32), np.array(rec["conf"])
+            meta.append([rtype, otype, str(t), str(z), mode, "0", str(env.max_timestep)])
+            ep += 1
+    out["meta"] = np.array(meta)
+    np.savez_compressed(path, **out)
+    return ep
+
+
+def test_golden_replay_plumbing(tmp_path):
+    """tests/test_pirl_golden.py replays tests/golden/pirl_steps.npz (episodes recorded from the reference's own env
+    class -- absent until a human authorises running it).  Its replay logic is exercised here on the surrogate file."""
+    from test_pirl_golden import replay_oracle
+    path = str(tmp_path / "surrogate_pirl_steps.npz")
+    ep = write_surrogate(path)
+    assert replay_oracle(np.load(path), tol=1e-9) >= ep * 4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_golden_replay_plumbing_gpu(cuda_device, tmp_path, dtype):
+    """the GPU half of the same replay (rlitg_pirl_env_step, FP64 and FP32 builds) on the surrogate file"""
+    from test_pirl_golden import replay_gpu
+    path = str(tmp_path / "surrogate_pirl_steps.npz")
+    ep = write_surrogate(path)
+    assert replay_gpu(np.load(path), cuda_device, dtype) >= ep * 4
