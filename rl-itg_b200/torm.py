@@ -348,7 +348,7 @@ TormBatch.applyIncrements = _apply_increments
 
 def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, check_collision=True, lr_schedule_mode=3,
                          return_state=False, use_cuda_graph=None, stochastic=None, seed=0, rand=None, state=None, overlap=True,
-                         graph_iterations=8):
+                         graph_iterations=8, parts=None):
     """Lock-step two-stage gradient descent over the N trajectories of `traj` (in place): the loop body of
     TormOptimizer::localOptimizeTSGD (torm/src/torm_optimizer.cpp:397-598) entirely on the device -- cost +
     increments (kernels 3a / 3b), feasibility checks, the alpha_ / learning_rate_ schedule, the best-trajectory
@@ -374,6 +374,10 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
     rates sit in a block buffer refilled by one device copy per replay -- so that the graph-to-graph boundary and the
     per-iteration refill are paid once per block; the iterations that do not fill a block run eagerly.
     overlap=False keeps every launch on one stream (measurement).
+    parts: the batch is cut into `parts` contiguous slices that run the same loop on streams of their own (trajectories
+    are independent, so the results are bit-identical): the latency-bound launches of one slice (update step,
+    bookkeeping, collision point: at most one wave of CTAs each) then run under the throughput-bound cost kernels of
+    another.  Only pays without the per-launch Python cost, i.e. inside a captured block -- default 1.
     Returns (best_traj [N,T,7], best_cost [N]); best_cost stays +inf for trajectories never found feasible.
     return_state=True appends a dict with the final alpha / lr / feasibility tensors and the draws."""
     pr = self.parameters
@@ -433,80 +437,131 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
     # Every half-iteration has two independent parts that only read the trajectory: the end-pose / evaluator kernel, and
     # the collision-point test followed by the collision / smoothness kernel (which needs the test's waypoint choice).
     # They run on two streams and share one costs buffer (RLITG_STAGE_KEEP_COSTS).
-    side = torch.cuda.Stream(device=dev)
-    ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
     KEEP = STAGE_KEEP_COSTS
+    sl_ = lambda t, s: None if t is None else t[s]
 
-    def sub_step(stage, k):
-        cur_stream = torch.cuda.current_stream(dev)
-        if mode == 1:
-            # every optimiser picks its own stage (:400-412) from the state before this half-iteration; the cost kernels
-            # then only do, per trajectory, what that stage needs
-            with _lib.on_device(dev):
-                check(lib.rlitg_torm_stage_decide(N, code, lr.data_ptr(), infea_col.data_ptr(), infea_vel.data_ptr(),
-                                                  C.byref(sch[stage]), stage_idx.data_ptr(), cur_stream.cuda_stream))
-            ts = stage_idx
-            pose_mask, coll_mask = STAGE_POSE_GRAD | STAGE_EVAL, STAGE_SMOOTH | (STAGE_COLL if has_scene else 0)
-        elif stage == 0:
-            ts = None
-            pose_mask, coll_mask = STAGE_EVAL, STAGE_SMOOTH | (STAGE_COLL if has_scene else 0)
-        else:
-            ts = None
-            pose_mask, coll_mask = STAGE_POSE_GRAD | STAGE_EVAL, 0
-        # the smoothness band rides in the end-pose / evaluator launch (it has the trajectory window in shared memory
-        # anyway); what is left for the second call is the collision stage
-        smooth_mask, coll_mask = coll_mask & STAGE_SMOOTH, coll_mask & ~STAGE_SMOOTH
-        two = bool(overlap and (coll_mask or need_point))
-        if two:
-            ev_fork.record(cur_stream)
-            side.wait_event(ev_fork)
-            with torch.cuda.stream(side):
-                r = self.cost_grad(traj, pose_mask | smooth_mask | (KEEP if coll_mask else 0), traj_stage=ts)
-                ev_join.record(side)
-        else:
-            r = self.cost_grad(traj, pose_mask | smooth_mask | (KEEP if coll_mask else 0), traj_stage=ts)
-        if need_point:
-            with _lib.on_device(dev):
-                check(lib.rlitg_torm_collision_point(traj.data_ptr(), N, self.T, code, self.scene.handle, base_off,
-                                                     u_blk[k, stage].data_ptr() if stochastic else None, None,
-                                                     any_hit.data_ptr(), stoch_idx.data_ptr() if stochastic else None,
-                                                     cur_stream.cuda_stream))
-        rc = None
-        if coll_mask:
-            use_st = bool(stochastic and (coll_mask & STAGE_COLL))
-            # one waypoint per trajectory takes the collision increment: only its seven stencil rows are walked
-            rc = self.cost_grad(traj, coll_mask | KEEP | (STAGE_COLL_ROW_ONLY if use_st else 0),
-                                stochastic_idx=stoch_idx if use_st else None, traj_stage=ts)
-        if two:
-            cur_stream.wait_event(ev_join)
-        if singular is not None:
-            from .pirl_env import manipulability
-            yosh = manipulability(traj[:, 1:].reshape(-1, 7)).reshape(N, self.T - 1)
-            singular.copy_((yosh.abs() < pr.singularity_lower_bound_).any(dim=1))
-        # stage choice (mode 1), feasibility flags, alpha_ / learning_rate_ and the best-trajectory record: one launch
-        with _lib.on_device(dev):
-            check(lib.rlitg_torm_bookkeep(traj.data_ptr(), best_traj.data_ptr(), N, self.T, code, r["costs"].data_ptr(),
-                                          any_hit.data_ptr() if sch[stage].use_collision_check else None,
-                                          None if singular is None else singular.data_ptr(), al.data_ptr(), lr.data_ptr(),
-                                          infea_col.data_ptr(), infea_vel.data_ptr(), best_cost.data_ptr(),
-                                          None, lr_blk[k:k + 1].data_ptr() if mode == 2 else None, C.byref(sch[stage]),
-                                          cur_stream.cuda_stream))
-        # ---- increments -> trajectory (:562-576)
-        if smooth_mask:
-            inc_s = r["inc_smooth"]
-            inc_c = rc["inc_coll"] if (rc is not None and rc["inc_coll"] is not None) else zeros
-        else:
-            inc_s = inc_c = None
-        if mode == 1:
-            self.applyIncrements(traj, True, inc_s, inc_c, r["inc_pose"], al, lr, lr_schedule_mode=mode, stage_idx=stage_idx)
-        elif stage == 0:
-            self.applyIncrements(traj, True, inc_s, inc_c, None, al, lr, lr_schedule_mode=mode)
-        else:
-            self.applyIncrements(traj, False, inc_pose=r["inc_pose"], alpha=al, learning_rate=lr, lr_schedule_mode=mode)
+    def make_part(tb, s):
+        """The loop body on trajectories traj[s]: `tb` is a view of this batch with output buffers of its own."""
+        traj_p, best_traj_p, best_cost_p = traj[s], best_traj[s], best_cost[s]
+        lr_p, al_p, infea_col_p, infea_vel_p, stage_idx_p = lr[s], al[s], infea_col[s], infea_vel[s], stage_idx[s]
+        singular_p, any_hit_p, stoch_idx_p, zeros_p = sl_(singular, s), sl_(any_hit, s), sl_(stoch_idx, s), sl_(zeros, s)
+        Np = traj_p.shape[0]
+        side = torch.cuda.Stream(device=dev)
+        ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
 
-    def iteration(k=0):
-        sub_step(0, k)
-        sub_step(1, k)
+        def sub_step(stage, k):
+            cur_stream = torch.cuda.current_stream(dev)
+            if mode == 1:
+                # every optimiser picks its own stage (:400-412) from the state before this half-iteration; the cost
+                # kernels then only do, per trajectory, what that stage needs
+                with _lib.on_device(dev):
+                    check(lib.rlitg_torm_stage_decide(Np, code, lr_p.data_ptr(), infea_col_p.data_ptr(),
+                                                      infea_vel_p.data_ptr(), C.byref(sch[stage]), stage_idx_p.data_ptr(),
+                                                      cur_stream.cuda_stream))
+                ts = stage_idx_p
+                pose_mask, coll_mask = STAGE_POSE_GRAD | STAGE_EVAL, STAGE_SMOOTH | (STAGE_COLL if has_scene else 0)
+            elif stage == 0:
+                ts = None
+                pose_mask, coll_mask = STAGE_EVAL, STAGE_SMOOTH | (STAGE_COLL if has_scene else 0)
+            else:
+                ts = None
+                pose_mask, coll_mask = STAGE_POSE_GRAD | STAGE_EVAL, 0
+            # the smoothness band rides in the end-pose / evaluator launch (it has the trajectory window in shared memory
+            # anyway); what is left for the second call is the collision stage
+            smooth_mask, coll_mask = coll_mask & STAGE_SMOOTH, coll_mask & ~STAGE_SMOOTH
+            two = bool(overlap and (coll_mask or need_point))
+            if two:
+                ev_fork.record(cur_stream)
+                side.wait_event(ev_fork)
+                with torch.cuda.stream(side):
+                    r = tb.cost_grad(traj_p, pose_mask | smooth_mask | (KEEP if coll_mask else 0), traj_stage=ts)
+                    ev_join.record(side)
+            else:
+                r = tb.cost_grad(traj_p, pose_mask | smooth_mask | (KEEP if coll_mask else 0), traj_stage=ts)
+            if need_point:
+                with _lib.on_device(dev):
+                    check(lib.rlitg_torm_collision_point(traj_p.data_ptr(), Np, self.T, code, self.scene.handle, base_off,
+                                                         u_blk[k, stage][s].data_ptr() if stochastic else None, None,
+                                                         any_hit_p.data_ptr(),
+                                                         stoch_idx_p.data_ptr() if stochastic else None,
+                                                         cur_stream.cuda_stream))
+            rc = None
+            if coll_mask:
+                use_st = bool(stochastic and (coll_mask & STAGE_COLL))
+                # one waypoint per trajectory takes the collision increment: only its seven stencil rows are walked
+                rc = tb.cost_grad(traj_p, coll_mask | KEEP | (STAGE_COLL_ROW_ONLY if use_st else 0),
+                                  stochastic_idx=stoch_idx_p if use_st else None, traj_stage=ts)
+            if two:
+                cur_stream.wait_event(ev_join)
+            if singular_p is not None:
+                from .pirl_env import manipulability
+                yosh = manipulability(traj_p[:, 1:].reshape(-1, 7)).reshape(Np, self.T - 1)
+                singular_p.copy_((yosh.abs() < pr.singularity_lower_bound_).any(dim=1))
+            # stage choice (mode 1), feasibility flags, alpha_ / learning_rate_ and the best-trajectory record: one launch
+            with _lib.on_device(dev):
+                check(lib.rlitg_torm_bookkeep(traj_p.data_ptr(), best_traj_p.data_ptr(), Np, self.T, code,
+                                              r["costs"].data_ptr(),
+                                              any_hit_p.data_ptr() if sch[stage].use_collision_check else None,
+                                              None if singular_p is None else singular_p.data_ptr(), al_p.data_ptr(),
+                                              lr_p.data_ptr(), infea_col_p.data_ptr(), infea_vel_p.data_ptr(),
+                                              best_cost_p.data_ptr(), None,
+                                              lr_blk[k:k + 1].data_ptr() if mode == 2 else None, C.byref(sch[stage]),
+                                              cur_stream.cuda_stream))
+            # ---- increments -> trajectory (:562-576)
+            if smooth_mask:
+                inc_s = r["inc_smooth"]
+                inc_c = rc["inc_coll"] if (rc is not None and rc["inc_coll"] is not None) else zeros_p
+            else:
+                inc_s = inc_c = None
+            if mode == 1:
+                tb.applyIncrements(traj_p, True, inc_s, inc_c, r["inc_pose"], al_p, lr_p, lr_schedule_mode=mode,
+                                   stage_idx=stage_idx_p)
+            elif stage == 0:
+                tb.applyIncrements(traj_p, True, inc_s, inc_c, None, al_p, lr_p, lr_schedule_mode=mode)
+            else:
+                tb.applyIncrements(traj_p, False, inc_pose=r["inc_pose"], alpha=al_p, learning_rate=lr_p,
+                                   lr_schedule_mode=mode)
+
+        def iteration(k=0):
+            sub_step(0, k)
+            sub_step(1, k)
+
+        return iteration
+
+    # slices of the batch (boundaries at multiples of 16 trajectories: every slice keeps the alignment of the whole)
+    n_parts = max(int(parts or 1), 1)
+    per = -(-N // n_parts)
+    per = -(-per // 16) * 16
+    bounds = [(h, min(h + per, N)) for h in range(0, N, per)] if n_parts > 1 else [(0, N)]
+    if len(bounds) == 1:
+        part_iters = [make_part(self, slice(0, N))]
+    else:
+        import copy
+        part_iters = []
+        for (h0, h1) in bounds:
+            tb = copy.copy(self)
+            tb._buf, tb._call_cache = {}, {}
+            part_iters.append(make_part(tb, slice(h0, h1)))
+        part_streams = [torch.cuda.Stream(device=dev) for _ in bounds]
+        ev_begin = torch.cuda.Event()
+        ev_done = [torch.cuda.Event() for _ in bounds]
+
+    def run_iterations(ks):
+        """Iterations ks (indices into the block buffers) of every slice: the slices advance independently."""
+        if len(part_iters) == 1:
+            for k in ks:
+                part_iters[0](k)
+            return
+        cur = torch.cuda.current_stream(dev)
+        ev_begin.record(cur)
+        for it, ps, ev in zip(part_iters, part_streams, ev_done):
+            ps.wait_event(ev_begin)
+            with torch.cuda.stream(ps):
+                for k in ks:
+                    it(k)
+                ev.record(ps)
+        for ev in ev_done:
+            cur.wait_event(ev)
 
     def set_block(it0, n):
         # the draws / scheduled rates of iterations it0 .. it0 + n - 1 into the block buffers (device-to-device)
@@ -520,7 +575,7 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
         # the first iteration runs eagerly: it is the warm-up a capture needs (kernel attributes, lazily built scene
         # volumes, output buffers of cost_grad) and it is real work, not thrown away
         set_block(0, 1)
-        iteration(0)
+        run_iterations([0])
         start = 1
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
@@ -528,8 +583,7 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
         cap_stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(cap_stream):
             with torch.cuda.graph(graph, stream=cap_stream):
-                for k in range(KB):
-                    iteration(k)
+                run_iterations(list(range(KB)))
         torch.cuda.current_stream(dev).wait_stream(cap_stream)
         while start + KB <= maxiter:
             set_block(start, KB)
@@ -537,7 +591,7 @@ def _local_optimize_tsgd(self, traj, maxiter, learning_rate=None, alpha=0.5, che
             start += KB
     for it in range(start, maxiter):
         set_block(it, 1)
-        iteration(0)
+        run_iterations([0])
     if return_state:
         return best_traj, best_cost, dict(alpha=al, learning_rate=lr, infea_col=infea_col.bool(), infea_vel=infea_vel.bool(),
                                           rand=rand if stochastic else None)

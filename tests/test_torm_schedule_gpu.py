@@ -187,3 +187,30 @@ def test_graph_replay_equals_eager(cuda_device, mode, dtype, block):
         assert torch.equal(st_e[k], st_g[k]), k
     assert float((a - torch.tensor(traj, dtype=a.dtype, device=cuda_device)).abs().max()) > 1e-3
     gsc.close()
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("dtype,parts,graph", [("float32", 2, True), ("float64", 3, True), ("float32", 2, False)])
+def test_batch_slices_equal_whole(cuda_device, mode, dtype, parts, graph):
+    """localOptimizeTSGD(parts=k) cuts the batch into k contiguous slices that run the loop on streams of their own (the
+    latency-bound launches of one slice under the cost kernels of another): trajectories are independent, so every
+    output is bit-identical to the single-slice loop -- also with a last slice that is shorter than the others."""
+    import torch
+    from rlitg_b200 import torm as TM
+    N, T, maxiter = 40, 40, 11
+    traj, targets, osc, gsc = make_problem(N, T, 34, cuda_device)
+    pr = TM.TormParameters(min_clearence_=0.3, learning_rate_=0.02)
+    tb = TM.TormBatch(targets, pr, gsc, cuda_device, getattr(torch, dtype))
+    a = torch.tensor(traj, dtype=getattr(torch, dtype), device=cuda_device)
+    b = a.clone()
+    bt_e, bc_e, st_e = tb.localOptimizeTSGD(a, maxiter, lr_schedule_mode=mode, return_state=True, use_cuda_graph=False)
+    bt_e, bc_e = bt_e.clone(), bc_e.clone()
+    st_e = {k: v.clone() for k, v in st_e.items()}
+    bt_g, bc_g, st_g = tb.localOptimizeTSGD(b, maxiter, lr_schedule_mode=mode, return_state=True, use_cuda_graph=graph,
+                                            graph_iterations=4, parts=parts)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    assert torch.equal(bt_e, bt_g) and torch.equal(bc_e, bc_g)
+    for k in st_e:
+        assert torch.equal(st_e[k], st_g[k]), k
+    gsc.close()
