@@ -36,6 +36,12 @@ struct Smooth {
     float* d_band32 = nullptr;
     double* d_inv64 = nullptr;
     double* d_chol = nullptr;
+    // partitioned substitution (torm_update.cu): the free rows in `parts` blocks of `rows` rows; spike[0][i][m] = response
+    // of y_i (L y = b) to the m-th row before its block, spike[1][i][m] = response of x_i (L^T x = y) to the m-th row
+    // behind its block; zero for the first / last block
+    int parts = 1, rows = 0;
+    std::vector<double> spike;   // [2][(T-1)][6]
+    double* d_spike = nullptr;
 };
 const double* smooth_inv_host(const Smooth* s);
 int smooth_T(const Smooth* s);

@@ -24,6 +24,11 @@ struct UpdP {
     double jmin[7], jmax[7];
 };
 
+struct SpikeP {   // partitioned substitution (smooth_build): blocks of `rows` rows, spike [2][F][6]
+    int parts, rows;
+    const double* spike;
+};
+
 constexpr int kUpdGroup = 64;  // threads that work on one trajectory
 
 // barrier over the 64 threads of one trajectory's group (hardware barrier 1 + group; 0 is __syncthreads)
@@ -45,11 +50,11 @@ __device__ __forceinline__ double group_max(double v, double* s_tmp, int g, int 
 // several CTAs share an SM (a warp-wide FP64 instruction costs the same for 7 active lanes as for 32), so the
 // 7 x PER solves of a CTA are packed into the lanes of warp 0: PER = 4 -> 28 lanes per FP64 instruction.
 template <typename T, int PER>
-__global__ void __launch_bounds__(kUpdGroup * PER)
+__global__ void __launch_bounds__(kUpdGroup * PER) __maxnreg__(PER > 0 ? 96 : 0)
 torm_update_kernel(UpdP P, T* __restrict__ traj, int64_t N, const T* __restrict__ inc_smooth,
                    const T* __restrict__ inc_coll, const T* __restrict__ inc_pose, const T* __restrict__ alpha,
                    const T* __restrict__ lr, const double* __restrict__ chol, const double* __restrict__ inv,
-                   const int32_t* __restrict__ stage_idx, int tab_in_smem) {
+                   const int32_t* __restrict__ stage_idx, int tab_in_smem, SpikeP SP) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Tn = P.Tn, F = Tn - 1, tid = threadIdx.x;
     const int g = tid / kUpdGroup, gt = tid - g * kUpdGroup;
@@ -69,6 +74,7 @@ torm_update_kernel(UpdP P, T* __restrict__ traj, int64_t N, const T* __restrict_
     __shared__ double s_best_all[PER][kUpdGroup];
     __shared__ int s_idx_all[PER][kUpdGroup];
     __shared__ int s_stage[PER];
+    __shared__ double s_wb[8][36];  // partitioned substitution: the 6 x 6 boundary rows of every inner block
     double* s_tmp = s_tmp_all[g];
     double* s_best = s_best_all[g];
     int* s_idx = s_idx_all[g];
@@ -115,23 +121,33 @@ torm_update_kernel(UpdP P, T* __restrict__ traj, int64_t N, const T* __restrict_
     // running rows live in registers, already divided by their diagonal; once unknown i is final it is pushed into
     // all six with independent FMAs and the first of them IS unknown i+1 -- one dependent FMA per step, no division.
     // Coefficient rows (smooth_build) are fetched one step ahead.
-    const int sg = tid / 7, sj = tid - sg * 7;  // solve lane -> (trajectory of this CTA, joint)
-    const bool solver = tid < 7 * PER && s_stage[sg < PER ? sg : 0] == 0;
+    // Partitioned (SP.parts > 1): the F rows are cut into blocks of SP.rows rows; warp w runs the recurrence of block w
+    // with zero history (all blocks at once: the chain is F / parts steps long instead of F), then warp 0 walks the
+    // block boundaries -- the true last six values of block p are its zero-history values plus W (six values in front
+    // of the block), W = spike table of smooth_build -- and finally every warp adds W (boundary) to the rest of its block.
+    // The same, mirrored, for L^T x = y.  One block = the plain sequential substitution.
+    const int lane = tid & 31, wp = tid >> 5;
+    const int sg = lane / 7, sj = lane - sg * 7;   // solve lane -> (trajectory of this CTA, joint)
+    const bool col_ok = lane < 7 * PER && s_stage[sg < PER ? sg : 0] == 0;
+    const int NP = SP.parts, R = SP.rows;
+    const bool solver = col_ok && wp < NP;
     double* sfin = base + (size_t)(sg < PER ? sg : 0) * stride + kPad + sj;  // column sj of that trajectory, row stride 7
+    const int s0 = wp * R, e0 = min(s0 + R, F);    // this warp's block
     // (rows -8..-1 and F..F+7 of sfin are zero; table rows outside 0..F-1 are never needed: their products are with
     //  those zeros, so the row index is simply clamped)
     if (solver) {
         const double4* tab = tab_in_smem ? s_tab : g_tab;  // one row = 2 x double4
-        // ---- forward: rows 0..6 start as b_r / L(r,r); a0 is the row being finalised
+        // ---- forward: rows s0..s0+6 start as b_r / L(r,r); a0 is the row being finalised.  Rows behind the block
+        // enter as zeros: they belong to the next warp, which overwrites them while this one runs
         double a[7];
 #pragma unroll
-        for (int r = 0; r < 7; r++) a[r] = sfin[r * 7] * tab[2 * min(r, F - 1) + 1].w;
-        double4 ca = tab[0], cb = tab[1];
-        double nb_rhs = sfin[7 * 7];
-        for (int i = 0; i < F; i++) {
+        for (int r = 0; r < 7; r++) a[r] = (s0 + r < e0 ? sfin[(s0 + r) * 7] : 0.0) * tab[2 * min(s0 + r, F - 1) + 1].w;
+        double4 ca = tab[2 * s0], cb = tab[2 * s0 + 1];
+        double nb_rhs = s0 + 7 < e0 ? sfin[(s0 + 7) * 7] : 0.0;
+        for (int i = s0; i < e0; i++) {
             const int in = min(i + 1, F - 1);
             const double4 na = tab[2 * in], nb = tab[2 * in + 1];
-            const double nrhs = sfin[(i + 8) * 7];
+            const double nrhs = i + 8 < e0 ? sfin[(i + 8) * 7] : 0.0;
             const double y = a[0];
             sfin[i * 7] = y;
             a[0] = a[1] - ca.x * y; a[1] = a[2] - ca.y * y; a[2] = a[3] - ca.z * y; a[3] = a[4] - ca.w * y;
@@ -143,20 +159,57 @@ torm_update_kernel(UpdP P, T* __restrict__ traj, int64_t N, const T* __restrict_
     __syncthreads();
     if (tab_in_smem)
         for (int k = tid; k < 2 * F; k += kUpdGroup * PER) s_tab[k] = g_tab[2 * F + k];  // backward table
+    if (NP > 1) {
+        const double* Wf = SP.spike;  // [F][6]
+        // the 6 x 6 spike rows warp 0 needs for block wp's boundary, fetched by block wp's own warp (all blocks at once)
+        if (wp >= 1 && wp < NP - 1) {
+            for (int k = lane; k < 36; k += 32) s_wb[wp][k] = __ldg(Wf + (size_t)(e0 - 1 - k / 6) * 6 + (k % 6));
+        }
+        __syncthreads();
+        if (wp == 0 && col_ok) {
+            // boundaries, block by block: the last six rows of block p become final here (block 0 is final already)
+            for (int p = 1; p < NP - 1; p++) {
+                const int pe = min(p * R + R, F);
+                double gb[6], t[6];
+#pragma unroll
+                for (int m = 0; m < 6; m++) gb[m] = sfin[(p * R - 1 - m) * 7];
+#pragma unroll
+                for (int q = 0; q < 6; q++) {
+                    const double* w = &s_wb[p][q * 6];
+                    t[q] = sfin[(pe - 1 - q) * 7] + ((w[0] * gb[0] + w[1] * gb[1]) + (w[2] * gb[2] + w[3] * gb[3]) + (w[4] * gb[4] + w[5] * gb[5]));
+                }
+#pragma unroll
+                for (int q = 0; q < 6; q++) sfin[(pe - 1 - q) * 7] = t[q];
+            }
+        }
+        __syncthreads();
+        if (solver && wp >= 1) {
+            double gb[6];
+#pragma unroll
+            for (int m = 0; m < 6; m++) gb[m] = sfin[(s0 - 1 - m) * 7];
+            const int ce = wp < NP - 1 ? e0 - 6 : e0;  // the last six rows of an inner block are final already
+            const double2* w2 = reinterpret_cast<const double2*>(Wf + (size_t)s0 * 6);  // rows of 48 bytes
+#pragma unroll 4
+            for (int i = s0; i < ce; i++) {
+                const double2 wa = __ldg(w2 + 3 * (i - s0)), wb2 = __ldg(w2 + 3 * (i - s0) + 1), wc2 = __ldg(w2 + 3 * (i - s0) + 2);
+                sfin[i * 7] += (wa.x * gb[0] + wa.y * gb[1]) + (wb2.x * gb[2] + wb2.y * gb[3]) + (wc2.x * gb[4] + wc2.y * gb[5]);
+            }
+        }
+    }
     __syncthreads();
     if (solver) {
-        // ---- backward: rows F-1 .. F-7 start as y_r / L(r,r)
+        // ---- backward: rows e0-1 .. e0-7 start as y_r / L(r,r); rows in front of the block enter as zeros
         const double4* tbk = tab_in_smem ? s_tab : g_tab + 2 * (size_t)F;
-        const int e = F - 1;
+        const int e = e0 - 1;
         double a[7];
 #pragma unroll
-        for (int r = 0; r < 7; r++) a[r] = sfin[(e - r) * 7] * tbk[2 * max(e - r, 0) + 1].w;
+        for (int r = 0; r < 7; r++) a[r] = (e - r >= s0 ? sfin[(e - r) * 7] : 0.0) * tbk[2 * max(e - r, 0) + 1].w;
         double4 ca = tbk[2 * e], cb = tbk[2 * e + 1];
-        double nb_rhs = sfin[(e - 7) * 7];
-        for (int i = e; i >= 0; i--) {
+        double nb_rhs = e - 7 >= s0 ? sfin[(e - 7) * 7] : 0.0;
+        for (int i = e; i >= s0; i--) {
             const int in = max(i - 1, 0);
             const double4 na = tbk[2 * in], nb = tbk[2 * in + 1];
-            const double nrhs = sfin[(i - 8) * 7];
+            const double nrhs = i - 8 >= s0 ? sfin[(i - 8) * 7] : 0.0;
             const double x = a[0];
             sfin[i * 7] = x;
             a[0] = a[1] - ca.x * x; a[1] = a[2] - ca.y * x; a[2] = a[3] - ca.z * x; a[3] = a[4] - ca.w * x;
@@ -166,6 +219,43 @@ torm_update_kernel(UpdP P, T* __restrict__ traj, int64_t N, const T* __restrict_
         }
     }
     __syncthreads();
+    if (NP > 1) {
+        const double* Wb = SP.spike + (size_t)F * 6;  // [F][6]
+        if (wp >= 1 && wp < NP - 1) {
+            for (int k = lane; k < 36; k += 32) s_wb[wp][k] = __ldg(Wb + (size_t)(s0 + k / 6) * 6 + (k % 6));
+        }
+        __syncthreads();
+        if (wp == 0 && col_ok) {
+            // boundaries from the back: the first six rows of block p become final (the last block is final already)
+            for (int p = NP - 2; p >= 1; p--) {
+                const int ps = p * R, pe = min(ps + R, F);
+                double hb[6], t[6];
+#pragma unroll
+                for (int m = 0; m < 6; m++) hb[m] = sfin[(pe + m) * 7];
+#pragma unroll
+                for (int q = 0; q < 6; q++) {
+                    const double* w = &s_wb[p][q * 6];
+                    t[q] = sfin[(ps + q) * 7] + ((w[0] * hb[0] + w[1] * hb[1]) + (w[2] * hb[2] + w[3] * hb[3]) + (w[4] * hb[4] + w[5] * hb[5]));
+                }
+#pragma unroll
+                for (int q = 0; q < 6; q++) sfin[(ps + q) * 7] = t[q];
+            }
+        }
+        __syncthreads();
+        if (solver && wp < NP - 1) {
+            double hb[6];
+#pragma unroll
+            for (int m = 0; m < 6; m++) hb[m] = sfin[(e0 + m) * 7];
+            const int cs = wp >= 1 ? s0 + 6 : s0;  // the first six rows of an inner block are final already
+            const double2* w2 = reinterpret_cast<const double2*>(Wb + (size_t)cs * 6);
+#pragma unroll 4
+            for (int i = cs; i < e0; i++) {
+                const double2 wa = __ldg(w2 + 3 * (i - cs)), wb2 = __ldg(w2 + 3 * (i - cs) + 1), wc2 = __ldg(w2 + 3 * (i - cs) + 2);
+                sfin[i * 7] += (wa.x * hb[0] + wa.y * hb[1]) + (wb2.x * hb[2] + wb2.y * hb[3]) + (wc2.x * hb[4] + wc2.y * hb[5]);
+            }
+        }
+        __syncthreads();
+    }
     if (!active) return;  // no CTA-wide barrier below this line
 
     if (stage == 0) {
@@ -248,8 +338,14 @@ static int launch_update_per(const UpdP& P, const Smooth* sm, T* traj, int64_t N
     int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem, "torm_update_kernel");
     if (rc_attr) return rc_attr;
     const unsigned grid = (unsigned)((N + PER - 1) / PER);
+    // one block of the partitioned substitution per warp; RLITG_UPD_PARTS=1 forces the sequential recurrence (measurement)
+    static const int parts_env = [] { const char* e = getenv("RLITG_UPD_PARTS"); return e ? atoi(e) : 0; }();
+    SpikeP SP;
+    SP.parts = (parts_env == 1 || sm->parts > kUpdGroup * PER / 32) ? 1 : sm->parts;
+    SP.rows = SP.parts > 1 ? sm->rows : P.Tn - 1;
+    SP.spike = sm->d_spike;
     kern<<<grid, kUpdGroup * PER, smem, st>>>(P, traj, N, inc_smooth, inc_coll, inc_pose, alpha, lr, sm->d_chol,
-                                              sm->d_inv64, stage_idx, tab_in_smem);
+                                              sm->d_inv64, stage_idx, tab_in_smem, SP);
     return check_launch("torm_update_kernel");
 }
 

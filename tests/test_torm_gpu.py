@@ -555,3 +555,18 @@ def test_binary_feasibility_members(cuda_device):
     want_sing = ~(np.abs(yosh) < 0.02).any(axis=1)
     assert np.array_equal(sing_ok, want_sing)
     gsc.close()
+
+
+def test_update_step_partitioned_substitution(cuda_device):
+    """RLITG_UPD_PARTS=8: the banded solve of the update step as eight blocks solved at once + boundary corrections
+    (spike tables of smooth_build) instead of one recurrence over all rows -- same parity tests, in a process of its own
+    because the knob is read once per process."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RLITG_UPD_PARTS="8")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_torm_gpu.py"), "-q", "-m", "gpu", "-x",
+                        "-k", "test_update_step_parity or test_lockstep_tsgd_on_reference_problem"],
+                       capture_output=True, text=True, env=env, cwd=root, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
+
