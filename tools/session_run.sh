@@ -1,5 +1,2 @@
-set -x
-mkdir -p gpurun_out/s8
-python -m pytest tests -q -m gpu -x > gpurun_out/s8/pytest_gpu.log 2>&1; tail -3 gpurun_out/s8/pytest_gpu.log
-python tools/prof_update.py > gpurun_out/s8/upd.log 2>&1; cat gpurun_out/s8/upd.log
-python tools/prof_tsgd.py 2>&1 | grep -v "stochastic=0\|block=1 " > gpurun_out/s8/prof_tsgd.log; grep "mode" gpurun_out/s8/prof_tsgd.log
+mkdir -p gpurun_out/s9
+for k in 1 2 3 4 5 6 7 8; do RLITG_TEST_SEED=$k python -m pytest tests -q -m gpu > gpurun_out/s9/seed$k.log 2>&1; echo "seed $k: $(tail -1 gpurun_out/s9/seed$k.log)"; done
