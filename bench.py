@@ -344,6 +344,7 @@ def main():
         try:
             rec, det = BA.run_pirl(torch, dev, rank, world, max_over_ranks, barrier, sec_steps, 5, hbm_peak, cpu=cpu_ok)
             nest("pirl", rec)
+            summary["pirl"]["value_launch"] = rec["value_launch"]
             summary["pirl"]["us_per_step"] = rec["us_per_step"]
             summary["pirl"]["us_per_step_cuda_graph"] = rec["us_per_step_cuda_graph"]
             summary["pirl"]["us_per_step_50_steps_per_graph"] = rec.get("us_per_step_50_steps_per_graph")
@@ -357,6 +358,7 @@ def main():
             c5 = also["config5_strong_split"]
             summary["config5"] = {"fk_configs_per_s": c5["fk_jacobian_8M"]["configs_per_s"],
                                   "pirl_env_steps_per_s": c5["pirl_65536"]["env_steps_per_s"],
+                                  "pirl_env_steps_per_s_python_launch": c5["pirl_65536"]["env_steps_per_s_python_launch"],
                                   "torm_waypoints_per_s": c5["torm_8192"]["waypoints_per_s"], "ranks": world}
         except Exception as e:  # noqa: BLE001
             also["config5_strong_split"] = {"error": repr(e)}
@@ -385,7 +387,11 @@ def main():
             # --workload torm | pirl: that workload's own record as the headline of the line
             s = summary[args.workload]
             line.update({"metric": {"torm": "torm_cost_grad_waypoints_per_s", "pirl": "pirl_env_steps_per_s"}[args.workload],
-                         "value": s["value"], "unit": s["unit"]})
+                         "value": s["value"], "unit": s["unit"],
+                         "ms_per_step": s["ms_per_iteration"] if args.workload == "torm"
+                         else 1e-3 * (s.get("us_per_step_50_steps_per_graph") or s["us_per_step"])})
+            line["config"] = dict(config.get(args.workload) or {}, headline_of="--workload " + args.workload,
+                                  fk_jacobian=dict((k, v) for k, v in config.items() if k not in ("torm", "pirl")))
         if summary:
             line["summary"] = summary  # last: survives a tail-truncated log
         print(json.dumps(line))

@@ -267,7 +267,13 @@ def run_pirl(torch, dev, rank, world, max_over_ranks, barrier, steps, warmup, hb
                 dtc = time.perf_counter() - t0
                 cb = {"value": reps * B / dtc, "unit": "env-steps/s", "cores": O.num_threads(), "kind": "port",
                       "sample": "%d x %d envs, one step each, FP64 oracle (OpenMP), %.1f s" % (reps, B, dtc)}
-            rec = {"metric": "pirl_env_steps_per_s", "value": world * B / (ms * 1e-3), "unit": "env-steps/s", "us_per_step": ms * 1e3,
+            # value = the device-side rate: 50 steps per CUDA-graph replay (what a captured roll-out loop pays per step; every
+            # step does all its work, the action tensor is the same).  One launch per step from Python is bound by the
+            # launch path at this batch size (us_per_step) and is kept next to it.
+            best_us = us_gpu if us_gpu else ms * 1e3
+            rec = {"metric": "pirl_env_steps_per_s", "value": world * B / (best_us * 1e-6), "unit": "env-steps/s",
+                   "value_launch": "50 steps per CUDA-graph replay" if us_gpu else "one launch per step from Python",
+                   "value_python_launch": world * B / (ms * 1e-3), "us_per_step": ms * 1e3,
                    "us_per_step_cuda_graph": us_graph, "us_per_step_50_steps_per_graph": us_gpu, "cpu_baseline": cb, "e2e": e2e}
         del env, demos, targets_b
     big = detail.get("envs_1048576")
@@ -300,7 +306,22 @@ def run_config5(torch, dev, rank, world, max_over_ranks, barrier, steps, warmup)
     env, act, ts0, q0, demos, tg = pirl_env(torch, dev, Be, 100, 100 + rank)
     barrier()
     ms = max_over_ranks(time_loop(torch, lambda: env.step(act), steps, warmup, blocks=3))
-    out["pirl_65536"] = {"envs_per_rank": Be, "us": ms * 1e3, "env_steps_per_s": 65536 / (ms * 1e-3)}
+    # the same 50 steps captured in one CUDA graph: at 8,192 envs per rank a launch from Python costs more than the step
+    us_g = None
+    try:
+        torch.cuda.synchronize()
+        g50 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g50):
+            for _ in range(50):
+                env.step(act)
+        barrier()
+        us_g = 1e3 * max_over_ranks(time_loop(torch, g50.replay, max(steps // 5, 3), 2, blocks=3)) / 50
+        del g50
+    except Exception:  # noqa: BLE001
+        pass
+    best_us = us_g if us_g else ms * 1e3
+    out["pirl_65536"] = {"envs_per_rank": Be, "us": best_us, "us_python_launch": ms * 1e3, "us_50_steps_per_graph": us_g,
+                         "env_steps_per_s": 65536 / (best_us * 1e-6), "env_steps_per_s_python_launch": 65536 / (ms * 1e-3)}
     del env
     Nt = 8192 // world
     traj, targets, occ, sc, tb = torm_problem(torch, dev, Nt, 200, 300 + rank)
