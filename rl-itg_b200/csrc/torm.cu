@@ -52,6 +52,11 @@ struct TormP {
     T vlim[7];
     T rule_v[7], rule_a[7], rule_j[7];  // DIFF_RULES / dt^(k+1) for the evaluator's finite differences
     T rv[7], ra[7];                     // the same velocity / acceleration rules for the sphere stencils (kernel 3b)
+    // fixed-point sphere centres of the FP32 build (torm_coll.cuh): integer units of res / 2^fix_shift from the grid origin;
+    // rvs / ras = rv / ra x the unit; a centre in metres = fix_org + units * fix_unit
+    T rvs[7], ras[7], fix_unit, fix_org[3];
+    double fix_scale;                   // units per metre
+    int fix_shift;
     T sqrt_ridge, ridge_t;
     double off64[3];
 };
@@ -571,10 +576,29 @@ static TormP<T> convert_params(const RlitgTormParams& p) {
         o.rule_j[k] = (T)(kRules[2][k] / std::pow(p.dt, 3));
         o.rv[k] = (T)((1.0 / p.dt) * kRules[0][k]);
         o.ra[k] = (T)((1.0 / p.dt) * (1.0 / p.dt) * kRules[1][k]);
+        o.rvs[k] = o.ras[k] = T(0);
     }
     o.sqrt_ridge = (T)std::sqrt(p.pinv_ridge); o.ridge_t = (T)p.pinv_ridge;
     for (int k = 0; k < 3; k++) o.off64[k] = p.base_off[k];
+    o.fix_unit = T(0); o.fix_org[0] = o.fix_org[1] = o.fix_org[2] = T(0); o.fix_scale = 0.0; o.fix_shift = 0;
     return o;
+}
+
+// The fixed-point grid of the sphere centres for one scene: 2^shift units per cell, the shift chosen so that +-5 m around
+// the grid origin fit 31 bits (res 0.02 m: shift 23, unit 2.4e-9 m).  The cell of a centre is then (units + half) >> shift.
+template <typename T>
+static void set_fixed_point(TormP<T>& P, const SceneDev& sd, double dt) {
+    int shift = 8;
+    while (shift < 26 && std::ldexp(5.12 / sd.res, shift + 1) < 2147483648.0) shift++;
+    P.fix_shift = shift;
+    P.fix_scale = std::ldexp(1.0, shift) / sd.res;
+    const double unit = sd.res / std::ldexp(1.0, shift);
+    P.fix_unit = (T)unit;
+    for (int k = 0; k < 3; k++) P.fix_org[k] = (T)sd.origin[k];
+    for (int k = 0; k < 7; k++) {
+        P.rvs[k] = (T)((1.0 / dt) * kRules[0][k] * unit);
+        P.ras[k] = (T)((1.0 / dt) * (1.0 / dt) * kRules[1][k] * unit);
+    }
 }
 
 template <typename T>
@@ -627,6 +651,7 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
     if (row_only) {
         static const int fk64r = [] { const char* e = getenv("RLITG_TORM_FK64"); return e ? atoi(e) : 1; }();
         SceneDev sd = scene_dev(scene);
+        set_fixed_point(P, sd, p->dt);
         const int S = sd.S;
         const size_t smem = sizeof(T) * kRowWarps * (size_t)(7 * ((4 * S) | 1) + 42);
         using RowK = void (*)(TormP<T>, const T*, SceneDev, int, int, int64_t, const int32_t*, T*, T*, float*, const int32_t*);
@@ -684,6 +709,7 @@ static int launch_torm(const T* traj, const T* targets, int64_t N, const Scene* 
         if (stage_mask & RLITG_STAGE_COLL) {
             sd = scene_dev(scene);
             S = sd.S;
+            set_fixed_point(P, sd, p->dt);
         }
         static const int cocc = [] { const char* e = getenv("RLITG_TORM_COLL_OCC"); return e ? atoi(e) : 2; }();
         const int PW = (sizeof(T) == 4 && cocc == 3) ? 3 : 4;  // three-value sphere rows: what lets a third CTA fit in shared memory

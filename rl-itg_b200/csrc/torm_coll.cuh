@@ -35,6 +35,13 @@
 //   (a) the FP32 build walks the chain in FP64 (lean sincos, rlitg_common.cuh; the FP64 pipe of this part runs at half
 //       the FP32 rate: 36 vs 71 TFLOP/s measured) and rounds each centre once to FP32; the stencils difference against
 //       the centre row before scaling (the rule rows sum to 0);
+//       Since the end of round 2 the centres of the FP32 build are kept as 32-BIT FIXED POINT on a grid aligned with the
+//       distance volume (res / 2^shift per unit from the grid origin: 2.4e-9 m at res 0.02, +-5 m): link origin from the
+//       FP64 walk rounded to that grid + R c / res in FP32; the stencil differences are then exact integer arithmetic
+//       rounded to FP32 once, relative to the DIFFERENCE instead of to the ~1 m position, and the grid cell of a centre is
+//       (units + half a cell) >> shift -- no second float -> int conversion, and decided 10 x closer to the oracle.  With
+//       FP32 centres 45 - 67 of the 203,776 benchmark rows were above 1e-4 (worst 3e-3: a slow sphere with a large
+//       acceleration, tests/test_torm_gpu.py::fp32_centre_rounding_bound); tools/coll_fp32_study.py (FIXED=29) predicts 0 - 2.
 //   (b) J^T (J J^T + ridge I)^-1 g is computed as Q1 R^-T g from the QR of [J^T ; sqrt(ridge) I] (modified Gram-Schmidt on
 //       three columns of length k + 3): error ~ sqrt(cond) eps instead of cond eps, same instruction count as forming
 //       J J^T, inverting it and applying J^T.
@@ -67,11 +74,27 @@ struct CollVisit {
     int quirk;
     // centre + the linear index of its grid cell (-1 outside): the cell arithmetic sits here, next to the other spheres of
     // the link, instead of in front of every gather of phase 2's serial sphere loop
+    // fixed-point centres: FP32 storage, chain walked in FP64, four-value rows (see the header)
+    static constexpr bool kFix = !std::is_same<FT, T>::value && sizeof(T) == 4 && PW == 4;
     RLITG_DEV void put(int s, V3<T> x) const {
         T* d = pos_row + PW * s;
         d[0] = x.x; d[1] = x.y; d[2] = x.z;
         if constexpr (PW == 4) {
             if (gm != nullptr) d[3] = cell_to_bits((int)gm->cell(x), T(0));
+        }
+    }
+    // fixed-point grid (kFix): units per metre, 2^fx_shift units per cell, grid origin (FP64)
+    FT fx_scale;
+    int fx_shift;
+    FT fx_ox, fx_oy, fx_oz;   // -origin x fx_scale
+    RLITG_DEV void put_fixed(int s, int ix, int iy, int iz) const {
+        T* d = pos_row + PW * s;
+        d[0] = __int_as_float(ix); d[1] = __int_as_float(iy); d[2] = __int_as_float(iz);
+        if (gm != nullptr) {  // nearest cell = floor(units / 2^shift + 0.5), as GridMap::cell1
+            const int h = 1 << (fx_shift - 1);
+            const int cx = (ix + h) >> fx_shift, cy = (iy + h) >> fx_shift, cz = (iz + h) >> fx_shift;
+            const bool out = cx < 0 || cy < 0 || cz < 0 || cx >= gm->nx || cy >= gm->ny || cz >= gm->nz;
+            d[3] = cell_to_bits(out ? -1 : (cz * gm->ny + cy) * gm->nx + cx, T(0));
         }
     }
     template <int K>
@@ -103,12 +126,29 @@ struct CollVisit {
                 const V3<T> ol = {T(o.x - FT(oh.x)), T(o.y - FT(oh.y)), T(o.z - FT(oh.z))};
                 const V3<T> r0 = {T(f.c0.x), T(f.c0.y), T(f.c0.z)}, r1 = {T(f.c1.x), T(f.c1.y), T(f.c1.z)},
                             r2 = {T(f.c2.x), T(f.c2.y), T(f.c2.z)};
-                for (int s = s0; s < s1; s++) {
-                    const float4 c = sph[s];
-                    const V3<T> x = {oh.x + ((r0.x * c.x + r1.x * c.y + r2.x * c.z) + ol.x),
-                                     oh.y + ((r0.y * c.x + r1.y * c.y + r2.y * c.z) + ol.y),
-                                     oh.z + ((r0.z * c.x + r1.z * c.y + r2.z * c.z) + ol.z)};
-                    put(s, x);
+                if constexpr (kFix) {
+                    // the link origin on the fixed-point grid (clamped to what an int32 holds next to |R c| <= 0.2 m)
+                    // (fx_o* = -origin x scale: one FP64 FMA per coordinate; the conversion saturates, the clamp is integer)
+                    constexpr int lim = 2040000000;
+                    const int oix = min(max(__double2int_rn(fma(o.x, fx_scale, fx_ox)), -lim), lim);
+                    const int oiy = min(max(__double2int_rn(fma(o.y, fx_scale, fx_oy)), -lim), lim);
+                    const int oiz = min(max(__double2int_rn(fma(o.z, fx_scale, fx_oz)), -lim), lim);
+                    const T sc32 = T(fx_scale);
+                    const V3<T> q0 = r0 * sc32, q1 = r1 * sc32, q2 = r2 * sc32;
+                    for (int s = s0; s < s1; s++) {
+                        const float4 c = sph[s];
+                        put_fixed(s, oix + __float2int_rn(q0.x * c.x + q1.x * c.y + q2.x * c.z),
+                                  oiy + __float2int_rn(q0.y * c.x + q1.y * c.y + q2.y * c.z),
+                                  oiz + __float2int_rn(q0.z * c.x + q1.z * c.y + q2.z * c.z));
+                    }
+                } else {
+                    for (int s = s0; s < s1; s++) {
+                        const float4 c = sph[s];
+                        const V3<T> x = {oh.x + ((r0.x * c.x + r1.x * c.y + r2.x * c.z) + ol.x),
+                                         oh.y + ((r0.y * c.x + r1.y * c.y + r2.y * c.z) + ol.y),
+                                         oh.z + ((r0.z * c.x + r1.z * c.y + r2.z * c.z) + ol.z)};
+                        put(s, x);
+                    }
                 }
             }
         }
@@ -118,11 +158,13 @@ struct CollVisit {
 // sphere centres of one halo row (chunked paths only): kept out of line so the chain walk is not inlined twice
 template <typename T, typename FT, bool kFk64, int PW = 4>
 __device__ __noinline__ void halo_sphere_row(const T* qrow, T* sph_row, const float4* sph, const int* link_start,
-                                             FT ox, FT oy, FT oz, int quirk) {
+                                             FT ox, FT oy, FT oz, int quirk, FT fx_scale, int fx_shift,
+                                             FT fx_ox, FT fx_oy, FT fx_oz) {
     CollVisit<T, FT, false, PW> hv;
     hv.sph = sph; hv.link_start = link_start; hv.quirk = quirk;
     hv.off = {ox, oy, oz};
     hv.gm = nullptr;
+    hv.fx_scale = fx_scale; hv.fx_shift = fx_shift; hv.fx_ox = fx_ox; hv.fx_oy = fx_oy; hv.fx_oz = fx_oz;
     hv.pos_row = sph_row;
     walk_chain<FT, 7, kFk64>(qrow, hv);
 }
@@ -131,20 +173,42 @@ __device__ __noinline__ void halo_sphere_row(const T* qrow, T* sph_row, const fl
 // nrow[k]: shared-memory rows of waypoints i-3 .. i+3 (clamped at the ends of the path, torm_trajectory.cpp:81-96).
 // NANC = joints that move the sphere (1..7): compile-time, so the masked joints cost nothing (the warp walks the spheres
 // in table order: the link, and with it NANC, is uniform over the warp).  acc -= z.
-template <typename T, int NANC, int PW = 4>
+template <typename T, int NANC, int PW = 4, bool kFix = false>
 RLITG_DEV void coll_sphere(const TormP<T>& P, const float4 rec, const T pot, const T* const (&nrow)[7], const V3<T> (&ja)[7],
                            const V3<T> (&jb)[7], int s, T (&acc)[7]) {
     const T* pc = nrow[3] + PW * s;
-    const V3<T> xc = {pc[0], pc[1], pc[2]};
     // sphere velocity / acceleration: 7-point stencils across waypoints (:1364-1381), differenced against the centre row
-    V3<T> vel = {T(0), T(0), T(0)}, ac = {T(0), T(0), T(0)};
+    V3<T> xc, vel = {T(0), T(0), T(0)}, ac = {T(0), T(0), T(0)};
+    if constexpr (kFix) {
+        // fixed-point centres: the rules are antisymmetric (velocity) / symmetric (acceleration) about the centre row, so the
+        // rows are paired in exact integer arithmetic first -- x(i+k) - x(i-k) and x(i+k) + x(i-k) - 2 x(i), modulo 2^32:
+        // the results are small -- and each pair is rounded to FP32 once: 6 conversions and 6 FMAs per coordinate for the
+        // two stencils (the FP32 form needs 6 subtractions and 12 FMAs).  rvs / ras = the rule entries x the unit in metres.
+        const unsigned cix = __float_as_uint(pc[0]), ciy = __float_as_uint(pc[1]), ciz = __float_as_uint(pc[2]);
+        xc = {fma_t(T((int)cix), P.fix_unit, P.fix_org[0]), fma_t(T((int)ciy), P.fix_unit, P.fix_org[1]),
+              fma_t(T((int)ciz), P.fix_unit, P.fix_org[2])};
+        const unsigned m2x = 0u - 2u * cix, m2y = 0u - 2u * ciy, m2z = 0u - 2u * ciz;
 #pragma unroll
-    for (int k = 0; k < 7; k++) {
-        if (k == 3) continue;
-        const T* pk = nrow[k] + PW * s;
-        const V3<T> d = {pk[0] - xc.x, pk[1] - xc.y, pk[2] - xc.z};
-        vel = axpy(vel, P.rv[k], d);
-        ac = axpy(ac, P.ra[k], d);
+        for (int k = 4; k < 7; k++) {
+            const T* pp = nrow[k] + PW * s;
+            const T* pm = nrow[6 - k] + PW * s;
+            const unsigned px = __float_as_uint(pp[0]), py = __float_as_uint(pp[1]), pz = __float_as_uint(pp[2]);
+            const unsigned qx = __float_as_uint(pm[0]), qy = __float_as_uint(pm[1]), qz = __float_as_uint(pm[2]);
+            const V3<T> dv = {T((int)(px - qx)), T((int)(py - qy)), T((int)(pz - qz))};
+            const V3<T> da = {T((int)(px + qx + m2x)), T((int)(py + qy + m2y)), T((int)(pz + qz + m2z))};
+            vel = axpy(vel, P.rvs[k], dv);   // rule_v[k] = -rule_v[6 - k]
+            ac = axpy(ac, P.ras[k], da);     // rule_a[k] =  rule_a[6 - k]
+        }
+    } else {
+        xc = {pc[0], pc[1], pc[2]};
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            if (k == 3) continue;
+            const T* pk = nrow[k] + PW * s;
+            const V3<T> d = {pk[0] - xc.x, pk[1] - xc.y, pk[2] - xc.z};
+            vel = axpy(vel, P.rv[k], d);
+            ac = axpy(ac, P.ra[k], d);
+        }
     }
     T vel_mag, inv_vm;
     if constexpr (sizeof(T) == 4) {
@@ -295,6 +359,8 @@ torm_coll_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S, con
         v.sph = s_sph; v.link_start = s_start; v.quirk = P.quirk;
         v.off = {FT(P.off64[0]), FT(P.off64[1]), FT(P.off64[2])};
         v.gm = &gm;
+        v.fx_scale = FT(P.fix_scale); v.fx_shift = P.fix_shift;
+        v.fx_ox = -FT(sc.origin[0]) * v.fx_scale; v.fx_oy = -FT(sc.origin[1]) * v.fx_scale; v.fx_oz = -FT(sc.origin[2]) * v.fx_scale;
         if (valid && (!row_only || abs(i - stoch_row) <= 3)) {
             v.pos_row = PROW(i);
             walk_chain<FT, 7, kFk64>(TROW(i), v);
@@ -302,7 +368,8 @@ torm_coll_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S, con
         if (tid < 6) {
             const int hr = tid < 3 ? c0 - 3 + tid : c0 + CH + (tid - 3);
             if (hr >= 0 && hr < Tn && (hr < c0 || hr >= c0 + CH) && (!row_only || abs(hr - stoch_row) <= 3))
-                halo_sphere_row<T, FT, kFk64, PW>(TROW(hr), PROW(hr), s_sph, s_start, v.off.x, v.off.y, v.off.z, P.quirk);
+                halo_sphere_row<T, FT, kFk64, PW>(TROW(hr), PROW(hr), s_sph, s_start, v.off.x, v.off.y, v.off.z, P.quirk, v.fx_scale,
+                                                  v.fx_shift, v.fx_ox, v.fx_oy, v.fx_oz);
         }
         // the first two distance records of this row (its own cells, written above by this thread): issued before the
         // barrier so that their L2 round trip overlaps the wait for the slowest walker
@@ -360,14 +427,15 @@ torm_coll_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S, con
                 csum += pot;
                 if (!inc_row || pot < T(0.0001)) continue;
                 nact++;
+                constexpr bool FX = CollVisit<T, FT, true, PW>::kFix;
                 switch (lds_s32(a_nanc + 4u * (uint32_t)s)) {  // uniform over the warp: every lane is on sphere s
-                    case 1: coll_sphere<T, 1, PW>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
-                    case 2: coll_sphere<T, 2, PW>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
-                    case 3: coll_sphere<T, 3, PW>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
-                    case 4: coll_sphere<T, 4, PW>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
-                    case 5: coll_sphere<T, 5, PW>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
-                    case 6: coll_sphere<T, 6, PW>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
-                    default: coll_sphere<T, 7, PW>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
+                    case 1: coll_sphere<T, 1, PW, FX>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
+                    case 2: coll_sphere<T, 2, PW, FX>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
+                    case 3: coll_sphere<T, 3, PW, FX>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
+                    case 4: coll_sphere<T, 4, PW, FX>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
+                    case 5: coll_sphere<T, 5, PW, FX>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
+                    case 6: coll_sphere<T, 6, PW, FX>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
+                    default: coll_sphere<T, 7, PW, FX>(P, rec, pot, nrow, v.a, v.b, s, acc); break;
                 }
             }
             red[0] += csum;
@@ -451,10 +519,13 @@ torm_coll_row_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S,
         return;
     }
     CollVisit<T, FT, true> v;
+    const GridMap<T> gm(sc);
     if (lane < 7) {
         v.sph = s_sph; v.link_start = s_start; v.quirk = P.quirk;
         v.off = {FT(P.off64[0]), FT(P.off64[1]), FT(P.off64[2])};
-        v.gm = nullptr;
+        v.gm = lane == 3 ? &gm : nullptr;  // the centre row keeps its grid cells (decided as in kernel 3b)
+        v.fx_scale = FT(P.fix_scale); v.fx_shift = P.fix_shift;
+        v.fx_ox = -FT(sc.origin[0]) * v.fx_scale; v.fx_oy = -FT(sc.origin[1]) * v.fx_scale; v.fx_oz = -FT(sc.origin[2]) * v.fx_scale;
         v.pos_row = s_pos + lane * PS;
         const int r = min(max(row - 3 + lane, 0), Tn - 1);  // clamped at the ends of the path (torm_trajectory.cpp:81-96)
         walk_chain<FT, 7, kFk64>(tr + (size_t)r * 7, v);
@@ -475,10 +546,7 @@ torm_coll_row_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S,
         const T* nrow[7];
 #pragma unroll
         for (int k = 0; k < 7; k++) nrow[k] = s_pos + k * PS;
-        const T* pc = nrow[3] + 4 * s;
-        const V3<T> x = {pc[0], pc[1], pc[2]};
-        const GridMap<T> gm(sc);
-        const int64_t cell = gm.cell(x);
+        const int cell = bits_to_cell(nrow[3][4 * s + 3]);
         if (cell < 0) continue;
         const float4 rec = __ldg(sc.field + cell);
         if (!(rec.x < 1e29f)) continue;
@@ -491,14 +559,15 @@ torm_coll_row_kernel(TormP<T> P, const T* __restrict__ traj, SceneDev sc, int S,
             ja[j] = {s_tab[6 * j], s_tab[6 * j + 1], s_tab[6 * j + 2]};
             jb[j] = {s_tab[6 * j + 3], s_tab[6 * j + 4], s_tab[6 * j + 5]};
         }
+        constexpr bool FX = CollVisit<T, FT, true>::kFix;
         switch (s_nanc[s]) {
-            case 1: coll_sphere<T, 1>(P, rec, pot, nrow, ja, jb, s, acc); break;
-            case 2: coll_sphere<T, 2>(P, rec, pot, nrow, ja, jb, s, acc); break;
-            case 3: coll_sphere<T, 3>(P, rec, pot, nrow, ja, jb, s, acc); break;
-            case 4: coll_sphere<T, 4>(P, rec, pot, nrow, ja, jb, s, acc); break;
-            case 5: coll_sphere<T, 5>(P, rec, pot, nrow, ja, jb, s, acc); break;
-            case 6: coll_sphere<T, 6>(P, rec, pot, nrow, ja, jb, s, acc); break;
-            default: coll_sphere<T, 7>(P, rec, pot, nrow, ja, jb, s, acc); break;
+            case 1: coll_sphere<T, 1, 4, FX>(P, rec, pot, nrow, ja, jb, s, acc); break;
+            case 2: coll_sphere<T, 2, 4, FX>(P, rec, pot, nrow, ja, jb, s, acc); break;
+            case 3: coll_sphere<T, 3, 4, FX>(P, rec, pot, nrow, ja, jb, s, acc); break;
+            case 4: coll_sphere<T, 4, 4, FX>(P, rec, pot, nrow, ja, jb, s, acc); break;
+            case 5: coll_sphere<T, 5, 4, FX>(P, rec, pot, nrow, ja, jb, s, acc); break;
+            case 6: coll_sphere<T, 6, 4, FX>(P, rec, pot, nrow, ja, jb, s, acc); break;
+            default: coll_sphere<T, 7, 4, FX>(P, rec, pot, nrow, ja, jb, s, acc); break;
         }
     }
     // sum over the lanes: butterfly, the same order on every run (the thread-per-waypoint kernel adds the spheres in table

@@ -58,7 +58,7 @@ def chain(q, dt):
 
 def emulate(traj, field, origin, res, link, center, radius, dtp, clearance=0.3, ridge=1e-4, quirk=True,
             d_fk=np.float32, d_st=np.float32, d_gr=np.float32, d_so=np.float32, d_jt=np.float32, rel_stencil=False,
-            solver="adj", d_fk_st=None, d_fk_jac=None):
+            solver="adj", d_fk_st=None, d_fk_jac=None, fixed_point=0):
     from rlitg_b200 import fetch
     N, T, _ = traj.shape
     S = len(link)
@@ -98,7 +98,22 @@ def emulate(traj, field, origin, res, link, center, radius, dtp, clearance=0.3, 
     idx = np.clip(np.arange(T)[:, None] + np.arange(-3, 4)[None], 0, T - 1)   # [T,7]
     xs = x_st[:, idx].astype(d_st)                                          # [N,T,7,S,3]
     inv = d_st(1.0 / dtp)
-    if rel_stencil:
+    if fixed_point:
+        # centres stored as 32-bit fixed point (2^-fixed_point metres per unit, from the FP64 walk): the differences against
+        # the centre row are exact integer subtractions, rounded to FP32 once (relative to the DIFFERENCE, not the position)
+        if os.environ.get("FIXED_RC32"):
+            # what the kernel can afford: link origin from the FP64 walk, R c in FP32 (|R c| <= 0.2 m: ~1e-8 m)
+            R64, p64 = chain(traj.reshape(-1, 7), np.float64)
+            o64 = (np.asarray(fetch.BASE_OFFSET) + p64[:, link])                                   # [M,S,3]
+            rc32 = np.einsum("msab,sb->msa", R64[:, link].astype(np.float32), center.astype(np.float32)).astype(np.float32)
+            xi_all = (np.rint(o64 * 2.0 ** fixed_point) + np.rint(rc32.astype(np.float64) * 2.0 ** fixed_point)).astype(np.int64)
+            xi = xi_all.reshape(N, T, S, 3)[:, idx]
+        else:
+            xi = np.rint(x_st[:, idx].astype(np.float64) * 2.0 ** fixed_point).astype(np.int64)
+        xr = ((xi - xi[:, :, 3:4]).astype(np.float64) * 2.0 ** -fixed_point).astype(d_st)
+        vel = sum((inv * d_st(RULE_V[k])) * xr[:, :, k] for k in range(7) if k != 3)
+        acc = sum((inv * inv * d_st(RULE_A[k])) * xr[:, :, k] for k in range(7) if k != 3)
+    elif rel_stencil:
         xr = xs - xs[:, :, 3:4]
         vel = sum((inv * d_st(RULE_V[k])) * xr[:, :, k] for k in range(7) if k != 3)
         acc = sum((inv * inv * d_st(RULE_A[k])) * xr[:, :, k] for k in range(7) if k != 3)
