@@ -289,14 +289,16 @@ def test_cost_grad_benchmark_shape_all_trajectories(cuda_device):
     assert np.array_equal(costs[:, 7], want["costs"][:, 7])
     assert abs(float(got["active"].mean()) - float(want["active"].mean())) < 1e-3
     assert rel_rows(got["inc_smooth"].double().cpu().numpy(), want["inc_smooth"], 1e-9).max() < 2e-4
-    skip = voxel_boundary_rows(traj, origin, res)
-    assert skip.mean() < 0.04
+    # the kernel decides a centre's grid cell on its fixed-point grid (origin from the FP64 walk, R c / res in FP32: ~2e-8 m),
+    # so the excluded band around a voxel boundary is 0.2 um here (the FP32-centre kernels of the other tests keep 1 um)
+    skip = voxel_boundary_rows(traj, origin, res, margin=2e-7)
+    assert skip.mean() < 0.01
     rr_all = rel_rows(got["inc_coll"].double().cpu().numpy(), want["inc_coll"], 1e-6)
     rr = rr_all[~skip]
-    assert np.median(rr) < 5e-6 and (rr > 1e-4).mean() < 0.01 and rr.max() < 1e-2, (np.median(rr), (rr > 1e-4).mean(), rr.max())
-    # the rows above 1e-4 (a few dozen of 203,776) are explained, row by row, by the rounding of the sphere centres to FP32
-    # through the 1 / dt^2-scaled stencil of a slow, strongly accelerated sphere: tolerance 1e-4 + the first-order bound
-    # (observed: the error is 1 - 7 % of the bound on the worst rows; seeds 0 .. 8 swept with RLITG_TEST_SEED)
+    assert np.median(rr) < 5e-6 and (rr > 1e-4).mean() < 1e-3 and rr.max() < 2e-3, (np.median(rr), (rr > 1e-4).mean(), rr.max())
+    # a row above 1e-4 (a handful of 203,776 since the centres are fixed point; 45 - 67 with FP32 centres) must be explained
+    # by its conditioning: tolerance 1e-4 + the first-order bound of fp32_centre_rounding_bound (a conservative one for the
+    # fixed-point build: it assumes half an FP32 ulp per centre)
     field = osc.field                                       # [nz, ny, nx, 4] distance records of the oracle scene
     over = np.argwhere((rr_all > 1e-4) & ~skip)
     for n, i in over:
