@@ -314,7 +314,6 @@ def run_config5(torch, dev, rank, world, max_over_ranks, barrier, steps, warmup)
         with torch.cuda.graph(g50):
             for _ in range(50):
                 env.step(act)
-        barrier()
         us_g = 1e3 * max_over_ranks(time_loop(torch, g50.replay, max(steps // 5, 3), 2, blocks=3)) / 50
         del g50
     except Exception:  # noqa: BLE001
