@@ -584,8 +584,8 @@ static TormP<T> convert_params(const RlitgTormParams& p) {
     return o;
 }
 
-// The fixed-point grid of the sphere centres for one scene: 2^shift units per cell, the shift chosen so that +-5 m around
-// the grid origin fit 31 bits (res 0.02 m: shift 23, unit 2.4e-9 m).  The cell of a centre is then (units + half) >> shift.
+// The fixed-point grid of the sphere centres for one scene: 2^shift units per cell, the shift chosen so that +-10 m around
+// the grid origin fit 31 bits (res 0.02 m: shift 22, unit 4.8e-9 m; res 0.01 m: shift 21).  The cell of a centre is then (units + half) >> shift.
 template <typename T>
 static void set_fixed_point(TormP<T>& P, const SceneDev& sd, double dt) {
     int shift = 8;

@@ -36,7 +36,7 @@
 //       the FP32 rate: 36 vs 71 TFLOP/s measured) and rounds each centre once to FP32; the stencils difference against
 //       the centre row before scaling (the rule rows sum to 0);
 //       Since the end of round 2 the centres of the FP32 build are kept as 32-BIT FIXED POINT on a grid aligned with the
-//       distance volume (res / 2^shift per unit from the grid origin: 2.4e-9 m at res 0.02, +-5 m): link origin from the
+//       distance volume (res / 2^shift per unit from the grid origin: 4.8e-9 m at res 0.02, +-10 m): link origin from the
 //       FP64 walk rounded to that grid + R c / res in FP32; the stencil differences are then exact integer arithmetic
 //       rounded to FP32 once, relative to the DIFFERENCE instead of to the ~1 m position, and the grid cell of a centre is
 //       (units + half a cell) >> shift -- no second float -> int conversion, and decided 10 x closer to the oracle.  With
