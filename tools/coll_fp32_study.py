@@ -214,6 +214,10 @@ def main():
         stats("only d_fk in FP32 (qr)", solver="qr", **kw)
         kw = dict(d_fk=f64, d_st=f32, d_gr=f32, d_so=f32, d_jt=f32)
         stats("FK FP64, rest FP32 qr+rel", solver="qr", rel_stencil=True, **kw)
+        stats("same + fixed-point centres (2^-29 m)", solver="qr", fixed_point=29, **kw)
+        os.environ["FIXED_RC32"] = "1"
+        stats("same, R c in FP32 (what the kernel does)", solver="qr", fixed_point=29, **kw)
+        os.environ.pop("FIXED_RC32")
         stats("FP64 but stencil positions from FP32 FK (qr)", solver="qr", d_fk_st=f32, **allf64)
         stats("FP64 but Jacobian inputs from FP32 FK (qr)", solver="qr", d_fk_jac=f32, **allf64)
         for st in ("d_fk", "d_st", "d_gr", "d_so", "d_jt"):
