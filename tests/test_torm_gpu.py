@@ -295,7 +295,8 @@ def test_cost_grad_benchmark_shape_all_trajectories(cuda_device):
     assert skip.mean() < 0.01
     rr_all = rel_rows(got["inc_coll"].double().cpu().numpy(), want["inc_coll"], 1e-6)
     rr = rr_all[~skip]
-    assert np.median(rr) < 5e-6 and (rr > 1e-4).mean() < 1e-3 and rr.max() < 2e-3, (np.median(rr), (rr > 1e-4).mean(), rr.max())
+    # observed on eight data sets (profiles/r02_coll_seed_stats.txt): 2 - 9 rows above 1e-4, none above 1e-3, worst 4e-4
+    assert np.median(rr) < 5e-6 and (rr > 1e-4).mean() < 1e-3 and rr.max() < 1e-3, (np.median(rr), (rr > 1e-4).mean(), rr.max())
     # a row above 1e-4 (a handful of 203,776 since the centres are fixed point; 45 - 67 with FP32 centres) must be explained
     # by its conditioning: tolerance 1e-4 + the first-order bound of fp32_centre_rounding_bound (a conservative one for the
     # fixed-point build: it assumes half an FP32 ulp per centre)

@@ -1,2 +1,2 @@
-mkdir -p gpurun_out/n4
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/n4/bench_n4.json 2> gpurun_out/n4/bench_n4.err; tail -c 400 gpurun_out/n4/bench_n4.json; tail -2 gpurun_out/n4/bench_n4.err
+mkdir -p gpurun_out/s18
+python tools/coll_seed_stats.py 0 1 2 3 4 5 6 7 > gpurun_out/s18/coll_seed_stats.txt 2>&1; cat gpurun_out/s18/coll_seed_stats.txt | tail -10
