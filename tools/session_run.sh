@@ -1,2 +1,4 @@
-mkdir -p gpurun_out/s18
-python tools/coll_seed_stats.py 0 1 2 3 4 5 6 7 > gpurun_out/s18/coll_seed_stats.txt 2>&1; cat gpurun_out/s18/coll_seed_stats.txt | tail -10
+mkdir -p gpurun_out/s19
+python -m pytest tests/test_torm_gpu.py -q -m gpu > gpurun_out/s19/pytest.log 2>&1; tail -2 gpurun_out/s19/pytest.log
+RLITG_TEST_SEED=1 python -m pytest tests/test_torm_gpu.py -q -m gpu -k benchmark_shape > gpurun_out/s19/pytest1.log 2>&1; tail -1 gpurun_out/s19/pytest1.log
+RLITG_TEST_SEED=5 python -m pytest tests/test_torm_gpu.py -q -m gpu -k benchmark_shape > gpurun_out/s19/pytest5.log 2>&1; tail -1 gpurun_out/s19/pytest5.log
